@@ -1,0 +1,1 @@
+"""Stand-in for biopython (absent from this image); golden generation only."""

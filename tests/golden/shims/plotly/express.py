@@ -1,0 +1,1 @@
+"""empty stand-in (plotting is out of scope for goldens)"""

@@ -1,0 +1,2 @@
+def figlet_format(text, font=None):
+    return text
