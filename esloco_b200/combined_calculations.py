@@ -1,0 +1,82 @@
+"""The drop-in seam: run_simulation_iteration / process_combination with the reference's signatures
+(src/esloco/combined_calculations.py:11-126), executed by the CUDA engine, plus a batched form that keeps
+many iterations in one launch set."""
+import logging
+
+import numpy as np
+
+from .config_handler import seq_read_data
+from .counting import label_counts_to_dict
+from .session import get_session, lognormal_pool
+
+
+def _length_pool_key_and_factory(seed, combo, mean_read_length, sequenced_data_path, sigma, min_read_length):
+    """Length source of one combination (combined_calculations.py:36-49): FASTA/FASTQ lengths > min_read_length
+    when the file parses, else the log-normal pool."""
+    if sequenced_data_path:
+        try:
+            lengths = seq_read_data(sequenced_data_path, distribution=True, min_read_length=min_read_length)
+            logging.info("Custom FASTA/FASTQ data provided.")
+            return ("file", sequenced_data_path, min_read_length), (lambda: lengths)
+        except Exception:
+            pass  # the reference falls back silently as well (combined_calculations.py:42)
+    logging.info("No custom read length distribution provided... Generating artificial one...")
+    return (("lognormal", seed, combo, mean_read_length, sigma, min_read_length),
+            lambda: lognormal_pool(seed, combo, mean_read_length, sigma, min_read_length))
+
+
+def run_simulation_batch(iteration_ids, param_dictionary, genome_size, target_regions, masked_tree, device=0,
+                         to_host=True):
+    """All combinations for a contiguous run of iterations.  Returns one BatchResult per combination (on the
+    host when to_host) plus the target keys; iteration i of the batch is iteration_ids[0] + i."""
+    iteration_ids = list(iteration_ids)
+    first, n_iter = iteration_ids[0], len(iteration_ids)
+    if iteration_ids != list(range(first, first + n_iter)):
+        raise ValueError("iteration_ids must be contiguous")
+    p = param_dictionary
+    sess = get_session(device)
+    sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"])
+    seed = int(p.get("seed", 0))
+    scaling = p["scaling"] if isinstance(p["scaling"], (int, float)) else 1
+    out = []
+    for combo, (mean_read_length, coverage) in enumerate(p["combinations"]):
+        key, factory = _length_pool_key_and_factory(seed, combo, mean_read_length, p.get("sequenced_data_path"),
+                                                    p["sigma"], p["min_read_length"])
+        sess.set_pool(key, factory)
+        res = sess.engine.run_batch(seed, combo, first, n_iter, coverage, p["consuming"],
+                                    p["min_overlap_for_detection"], scaling)
+        out.append(res.cpu() if to_host else res)
+    return out, sess.keys
+
+
+def format_iteration(res, i, keys, iteration_id, mean_read_length, coverage, n_barcodes):
+    """One iteration of a BatchResult -> the reference's (detected, barcode_distribution) pair
+    (combined_calculations.py:76-89)."""
+    t = res.tallies[i].numpy()
+    suffix = "_" + str(iteration_id)
+    detected = [{"target_region": k + suffix, "full_matches": int(t[j, 0]), "partial_matches": int(t[j, 1]),
+                 "on_target_bases": int(t[j, 2]), "mean_read_length": mean_read_length, "coverage": coverage}
+                for j, k in enumerate(keys)]
+    dist = label_counts_to_dict(res.label_counts[i].numpy(), n_barcodes)
+    dist["coverage"] = coverage
+    dist["mean_read_length"] = mean_read_length
+    dist["iteration"] = iteration_id
+    dist["N_bases"] = int(res.n_bases[i])
+    return detected, dist
+
+
+def run_simulation_iteration(iteration_id, param_dictionary, genome_size, target_regions, masked_tree, log_file=None,
+                             device=0):
+    """run_simulation_iteration(iteration_id, param_dictionary, genome_size, target_regions, masked_tree,
+    log_file) -> (results, barcode_distributions) with the reference's shapes (combined_calculations.py:97-126):
+    results[c] is the per-target list of dicts of combination c, barcode_distributions[c] its label histogram."""
+    batches, keys = run_simulation_batch([iteration_id], param_dictionary, genome_size, target_regions, masked_tree, device)
+    results, dists = [], []
+    for res, (mean_read_length, coverage) in zip(batches, param_dictionary["combinations"]):
+        if int(res.status[0]) & 2:
+            raise RuntimeError("coverage not reached")
+        detected, dist = format_iteration(res, 0, keys, iteration_id, mean_read_length, coverage,
+                                          param_dictionary["n_barcodes"])
+        results.append(detected)
+        dists.append(dist)
+    return results, dists

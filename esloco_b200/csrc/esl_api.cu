@@ -1,0 +1,582 @@
+// C ABI of the engine (include/esloco_b200.h): context, host-side index construction, kernel launches.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/esloco_b200.h"
+#include "kernels.cuh"
+
+using esl::i64;
+using esl::u64;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t upload(const void *src, size_t n)
+    {
+        if (n > bytes) {
+            if (p) cudaFree(p);
+            p = nullptr; bytes = 0;
+            cudaError_t e = cudaMalloc(&p, n ? n : 1);
+            if (e != cudaSuccess) return e;
+            bytes = n;
+        }
+        return n ? cudaMemcpy(p, src, n, cudaMemcpyHostToDevice) : cudaSuccess;
+    }
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+} // namespace
+
+struct esl_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    i64 launches = 0;
+
+    u64 G = 0;
+    int B = 0;
+    std::vector<double> cdf;
+    std::vector<i64> t_start, t_end;
+    std::vector<int32_t> t_bc;
+    std::vector<i64> m_start, m_end;
+    std::vector<double> m_w;
+    std::vector<int32_t> m_bc;
+    bool have_targets = false, have_pool = false;
+    bool index_dirty = true;
+    bool wide = false; // 64-bit coordinates
+    int n_layers = 0;
+    i64 n_indexed = 0, n_mask = 0;
+
+    // pool statistics
+    uint32_t n_pool = 0, pool_max = 0;
+    double pool_mean = 0, pool_sd = 0;
+
+    DevBuf d_pool, d_cdf, d_cdf_u32, d_ts, d_te, d_trow, d_seg_off, d_bc_seg, d_ms, d_me, d_mpmax, d_mw, d_grp_off;
+    DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
+
+    // optional per-kernel timing (esl_set_profiling): events around the bulk and the cut-off kernel
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return ctx->fail(ESL_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+// ---- host-side index construction ------------------------------------------------------------------
+
+struct Rec { i64 s, e; int32_t row; };
+
+// Split one barcode's targets (sorted by start, end) into the fewest layers whose ends are non-decreasing:
+// first-fit on the layers' last ends (patience sorting).  Non-nesting target sets give one layer.
+void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers)
+{
+    std::sort(v.begin(), v.end(), [](const Rec &a, const Rec &b) {
+        if (a.s != b.s) return a.s < b.s;
+        if (a.e != b.e) return a.e < b.e;
+        return a.row < b.row;
+    });
+    std::vector<i64> last; // last end per layer; strictly decreasing across layers under first-fit
+    for (const Rec &r : v) {
+        size_t lo = 0, hi = last.size();
+        while (lo < hi) { // first layer with last <= r.e
+            size_t mid = (lo + hi) / 2;
+            if (last[mid] <= r.e) hi = mid; else lo = mid + 1;
+        }
+        if (lo == last.size()) { last.push_back(r.e); layers.emplace_back(); }
+        else last[lo] = r.e;
+        layers[lo].push_back(r);
+    }
+}
+
+template <typename C> C clampc(i64 v, u64 G) { return (C)((u64)v > G + 1 ? G + 1 : (u64)v); }
+
+template <typename C>
+int upload_index(esl_ctx *ctx)
+{
+    const int B = ctx->B;
+    const u64 G = ctx->G;
+    // targets
+    std::vector<C> ts, te;
+    std::vector<int32_t> trow, seg_off(1, 0), bc_seg(B + 1, 0);
+    ctx->n_layers = 0;
+    for (int b = 0; b < B; ++b) {
+        std::vector<Rec> v;
+        for (size_t i = 0; i < ctx->t_start.size(); ++i)
+            if (ctx->t_bc[i] == b && ctx->t_end[i] > ctx->t_start[i]) v.push_back(Rec{ctx->t_start[i], ctx->t_end[i], (int32_t)i});
+        std::vector<std::vector<Rec>> layers;
+        build_layers(v, layers);
+        for (auto &ly : layers) {
+            for (const Rec &r : ly) { ts.push_back(clampc<C>(r.s, G)); te.push_back(clampc<C>(r.e, G)); trow.push_back(r.row); }
+            seg_off.push_back((int32_t)ts.size());
+        }
+        ctx->n_layers += (int)layers.size();
+        bc_seg[b + 1] = (int32_t)seg_off.size() - 1;
+    }
+    ctx->n_indexed = (i64)ts.size();
+    CU(ctx->d_ts.upload(ts.data(), ts.size() * sizeof(C)));
+    CU(ctx->d_te.upload(te.data(), te.size() * sizeof(C)));
+    CU(ctx->d_trow.upload(trow.data(), trow.size() * sizeof(int32_t)));
+    CU(ctx->d_seg_off.upload(seg_off.data(), seg_off.size() * sizeof(int32_t)));
+    CU(ctx->d_bc_seg.upload(bc_seg.data(), bc_seg.size() * sizeof(int32_t)));
+    // blocked intervals: group g < B = barcode g, group B = "ALL"; (start, end) order, running max of ends
+    std::vector<C> ms, me, mp;
+    std::vector<double> mw;
+    std::vector<int32_t> grp_off(B + 2, 0);
+    for (int g = 0; g <= B; ++g) {
+        const int want = g < B ? g : -1;
+        std::vector<size_t> idx;
+        for (size_t i = 0; i < ctx->m_start.size(); ++i)
+            if (ctx->m_bc[i] == want) idx.push_back(i);
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b2) {
+            if (ctx->m_start[a] != ctx->m_start[b2]) return ctx->m_start[a] < ctx->m_start[b2];
+            return ctx->m_end[a] < ctx->m_end[b2];
+        });
+        C run = 0;
+        for (size_t i : idx) {
+            const C s = clampc<C>(std::max<i64>(ctx->m_start[i], 0), G), e = clampc<C>(std::max<i64>(ctx->m_end[i], 0), G);
+            run = std::max(run, e);
+            ms.push_back(s); me.push_back(e); mp.push_back(run); mw.push_back(ctx->m_w[i]);
+        }
+        grp_off[g + 1] = (int32_t)ms.size();
+    }
+    ctx->n_mask = (i64)ms.size();
+    CU(ctx->d_ms.upload(ms.data(), ms.size() * sizeof(C)));
+    CU(ctx->d_me.upload(me.data(), me.size() * sizeof(C)));
+    CU(ctx->d_mpmax.upload(mp.data(), mp.size() * sizeof(C)));
+    CU(ctx->d_mw.upload(mw.data(), mw.size() * sizeof(double)));
+    CU(ctx->d_grp_off.upload(grp_off.data(), grp_off.size() * sizeof(int32_t)));
+    // barcode cdf
+    std::vector<uint32_t> cu(B);
+    for (int k = 0; k < B; ++k) {
+        const double v = std::ceil(ctx->cdf[k] * 4294967296.0);
+        cu[k] = v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
+    }
+    CU(ctx->d_cdf.upload(ctx->cdf.data(), B * sizeof(double)));
+    CU(ctx->d_cdf_u32.upload(cu.data(), B * sizeof(uint32_t)));
+    return ESL_OK;
+}
+
+int ensure_index(esl_ctx *ctx, bool need_pool)
+{
+    if (ctx->G == 0) return ctx->fail(ESL_ERR_STATE, "esl_set_genome has not been called");
+    if (ctx->B <= 0) return ctx->fail(ESL_ERR_STATE, "esl_set_barcode_cdf has not been called");
+    if (!ctx->have_targets) return ctx->fail(ESL_ERR_STATE, "esl_set_targets has not been called");
+    if (need_pool && !ctx->have_pool) return ctx->fail(ESL_ERR_STATE, "esl_set_length_table has not been called");
+    for (int32_t b : ctx->m_bc)
+        if (b >= ctx->B) return ctx->fail(ESL_ERR_INVALID, "blocked interval names barcode %d but n_barcodes is %d", b, ctx->B);
+    if (ctx->index_dirty) {
+        CU(cudaSetDevice(ctx->device));
+        ctx->wide = ctx->G > 0xFFFFFFF0ull;
+        int rc = ctx->wide ? upload_index<uint64_t>(ctx) : upload_index<uint32_t>(ctx);
+        if (rc) return rc;
+        ctx->index_dirty = false;
+    }
+    return ESL_OK;
+}
+
+template <typename C>
+esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i64 min_overlap, double scaling)
+{
+    esl::DevCtx<C> d;
+    d.G = ctx->G;
+    d.thr = (i64)std::ceil(coverage * (double)ctx->G);
+    d.min_overlap = min_overlap;
+    d.scaling = scaling;
+    d.n_barcodes = ctx->B;
+    d.consuming = consuming ? 1 : 0;
+    d.has_mask = ctx->n_mask > 0;
+    d.n_pool = ctx->n_pool;
+    d.pool = ctx->d_pool.as<uint32_t>();
+    d.cdf = ctx->d_cdf.as<double>();
+    d.cdf_u32 = ctx->d_cdf_u32.as<uint32_t>();
+    d.ts = ctx->d_ts.as<C>();
+    d.te = ctx->d_te.as<C>();
+    d.trow = ctx->d_trow.as<int32_t>();
+    d.seg_off = ctx->d_seg_off.as<int32_t>();
+    d.bc_seg = ctx->d_bc_seg.as<int32_t>();
+    d.n_targets = (i64)ctx->t_start.size();
+    d.ms = ctx->d_ms.as<C>();
+    d.me = ctx->d_me.as<C>();
+    d.mpmax = ctx->d_mpmax.as<C>();
+    d.mw = ctx->d_mw.as<double>();
+    d.grp_off = ctx->d_grp_off.as<int32_t>();
+    return d;
+}
+
+// Draws per iteration handed to the bulk kernel: the largest N with N*mean + z*sd*sqrt(N) <= coverage*G,
+// i.e. z standard deviations of the length sum below the expected cut-off (z = 8; Cantelli bounds the
+// overshoot probability by 1/(1+z^2) for ANY length distribution, and the tail kernel corrects an
+// overshoot exactly, so this only ever costs time).  Blocking with consuming=False only moves the
+// cut-off later, so the bound stays valid.
+i64 bulk_reads(const esl_ctx *ctx, double coverage)
+{
+    if (!ctx->have_pool || ctx->pool_mean <= 0) return 0;
+    const double thr = coverage * (double)ctx->G, z = 8.0, mu = ctx->pool_mean, sd = ctx->pool_sd;
+    if (!(thr > 0)) return 0;
+    const double r = (-z * sd + std::sqrt(z * z * sd * sd + 4.0 * mu * thr)) / (2.0 * mu);
+    i64 n = (i64)std::floor(r * r) - 1;
+    n -= n % esl::kBulkTile; // whole tiles
+    return n < 2 * esl::kBulkTile ? 0 : n;
+}
+
+size_t bulk_smem(int B) { return (size_t)(B + 2 + esl::kBulkBlock / 32) * 8 + (size_t)B * 4; }
+size_t tail_smem(int B) { return (size_t)(40 + B + 2) * 8 + (size_t)B * 4; }
+
+template <typename C, typename Src>
+int launch_pipeline(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, esl::DevOut out, const i64 *d_n_bulk,
+                    i64 n_bulk_const, i64 max_bulk, int n_iter, bool run_tail, cudaStream_t st)
+{
+    const int tiles_per_iter = (int)((max_bulk + esl::kBulkTile - 1) / esl::kBulkTile);
+    out.tiles_per_iter = tiles_per_iter;
+    const i64 total_tiles = (i64)tiles_per_iter * n_iter;
+    const bool prof = ctx->profiling && ctx->ev[0];
+    ctx->ev_valid = false;
+    if (prof) CU(cudaEventRecord(ctx->ev[0], st));
+    if (total_tiles > 0) {
+        auto kern = esl::k_place_tally_bulk<C, Src>;
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx->B)));
+        if (occ < 1) occ = 1;
+        const i64 grid = std::min<i64>(total_tiles, (i64)ctx->sm_count * occ);
+        kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx->B), st>>>(dc, src, out, d_n_bulk, n_bulk_const, total_tiles);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (prof) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); }
+    if (run_tail) {
+        auto kern = esl::k_cutoff_tail<C, Src>;
+        kern<<<(unsigned)n_iter, esl::kTailBlock, tail_smem(ctx->B), st>>>(dc, src, out, d_n_bulk, n_bulk_const);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (prof) { CU(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid = true; }
+    return ESL_OK;
+}
+
+int zero_outputs(esl_ctx *ctx, int n_iter, int64_t *d_tallies, int64_t *d_label_counts, int64_t *d_n_bases,
+                 int64_t *d_n_reads, int32_t *d_status, cudaStream_t st)
+{
+    const size_t T = ctx->t_start.size();
+    CU(cudaMemsetAsync(d_tallies, 0, (size_t)n_iter * T * 3 * sizeof(int64_t), st));
+    CU(cudaMemsetAsync(d_label_counts, 0, (size_t)n_iter * (ctx->B + 2) * sizeof(int64_t), st));
+    CU(cudaMemsetAsync(d_n_bases, 0, (size_t)n_iter * sizeof(int64_t), st));
+    CU(cudaMemsetAsync(d_n_reads, 0, (size_t)n_iter * sizeof(int64_t), st));
+    CU(cudaMemsetAsync(d_status, 0, (size_t)n_iter * sizeof(int32_t), st));
+    return ESL_OK;
+}
+
+int check_outputs(esl_ctx *ctx, const void *a, const void *b, const void *c, const void *d, const void *e)
+{
+    if (!a || !b || !c || !d || !e) return ctx->fail(ESL_ERR_INVALID, "an output pointer is NULL");
+    return ESL_OK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int esl_abi_version(void) { return 1; }
+
+const char *esl_last_error(const esl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int esl_create(esl_ctx **out, int device)
+{
+    if (!out) { g_create_error = "ctx out-pointer is NULL"; return ESL_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return ESL_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return ESL_ERR_INVALID; }
+    cudaDeviceProp p;
+    if ((e = cudaGetDeviceProperties(&p, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return ESL_ERR_CUDA; }
+    if (p.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; this library carries sm_100a code only", device, p.major, p.minor);
+        g_create_error = buf;
+        return ESL_ERR_NO_DEVICE;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return ESL_ERR_CUDA; }
+    esl_ctx *c = new esl_ctx();
+    c->device = device;
+    c->sm_count = p.multiProcessorCount;
+    *out = c;
+    return ESL_OK;
+}
+
+int esl_destroy(esl_ctx *ctx)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
+    delete ctx;
+    return ESL_OK;
+}
+
+int esl_set_genome(esl_ctx *ctx, uint64_t genome_size)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (genome_size == 0) return ctx->fail(ESL_ERR_INVALID, "genome_size must be > 0");
+    if (genome_size > (1ull << 62)) return ctx->fail(ESL_ERR_INVALID, "genome_size too large");
+    ctx->G = genome_size;
+    ctx->index_dirty = true;
+    return ESL_OK;
+}
+
+int esl_set_barcode_cdf(esl_ctx *ctx, const double *cdf, int32_t n_barcodes)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (!cdf || n_barcodes < 1 || n_barcodes > esl::kMaxBarcodes)
+        return ctx->fail(ESL_ERR_INVALID, "n_barcodes must be in [1, %d]", esl::kMaxBarcodes);
+    for (int k = 0; k < n_barcodes; ++k)
+        if (!(cdf[k] >= 0.0) || (k && cdf[k] < cdf[k - 1])) return ctx->fail(ESL_ERR_INVALID, "cdf must be non-decreasing and >= 0");
+    ctx->cdf.assign(cdf, cdf + n_barcodes);
+    ctx->B = n_barcodes;
+    ctx->index_dirty = true;
+    return ESL_OK;
+}
+
+int esl_set_targets(esl_ctx *ctx, const int64_t *start, const int64_t *end, const int32_t *barcode, int64_t n)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n < 0 || n > 0x7fffffff / 3 || (n && (!start || !end || !barcode))) return ctx->fail(ESL_ERR_INVALID, "bad target arrays");
+    for (int64_t i = 0; i < n; ++i)
+        if (start[i] < 0 || end[i] < 0) return ctx->fail(ESL_ERR_INVALID, "target %lld has a negative coordinate", (long long)i);
+    ctx->t_start.assign(start, start + n);
+    ctx->t_end.assign(end, end + n);
+    ctx->t_bc.assign(barcode, barcode + n);
+    ctx->have_targets = true;
+    ctx->index_dirty = true;
+    return ESL_OK;
+}
+
+int esl_set_blocked(esl_ctx *ctx, const int64_t *start, const int64_t *end, const double *weight,
+                    const int32_t *barcode, int64_t n)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n < 0 || n > 0x7fffffff || (n && (!start || !end || !weight || !barcode))) return ctx->fail(ESL_ERR_INVALID, "bad blocked arrays");
+    for (int64_t i = 0; i < n; ++i)
+        if (barcode[i] < -1) return ctx->fail(ESL_ERR_INVALID, "blocked interval %lld: barcode must be >= -1", (long long)i);
+    ctx->m_start.assign(start, start + n);
+    ctx->m_end.assign(end, end + n);
+    ctx->m_w.assign(weight, weight + n);
+    ctx->m_bc.assign(barcode, barcode + n);
+    ctx->index_dirty = true;
+    return ESL_OK;
+}
+
+int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (!lengths || n < 1 || n > 0xFFFFFFFFll) return ctx->fail(ESL_ERR_INVALID, "length table must hold 1 .. 2^32-1 entries");
+    long double s = 0, s2 = 0;
+    uint32_t mx = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (lengths[i] == 0) return ctx->fail(ESL_ERR_INVALID, "length table entry %lld is 0", (long long)i);
+        s += lengths[i];
+        s2 += (long double)lengths[i] * lengths[i];
+        mx = std::max(mx, lengths[i]);
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_pool.upload(lengths, (size_t)n * sizeof(uint32_t)));
+    ctx->n_pool = (uint32_t)n;
+    ctx->pool_max = mx;
+    ctx->pool_mean = (double)(s / n);
+    const long double var = s2 / n - (s / n) * (s / n);
+    ctx->pool_sd = var > 0 ? (double)sqrtl(var) : 0.0;
+    ctx->have_pool = true;
+    return ESL_OK;
+}
+
+int64_t esl_bulk_reads(const esl_ctx *ctx, double coverage) { return ctx ? bulk_reads(ctx, coverage) : 0; }
+
+int64_t esl_workspace_bytes(const esl_ctx *ctx, int32_t n_iter, double coverage, int64_t max_draws_per_iter)
+{
+    if (!ctx || n_iter < 0) return ESL_ERR_INVALID;
+    const i64 nb = max_draws_per_iter > 0 ? max_draws_per_iter : bulk_reads(ctx, coverage);
+    const i64 tiles = (nb + esl::kBulkTile - 1) / esl::kBulkTile;
+    return (int64_t)(((size_t)tiles * n_iter + n_iter + 2) * sizeof(u64)) + 256;
+}
+
+int esl_set_profiling(esl_ctx *ctx, int32_t on)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0])
+        for (cudaEvent_t &e : ctx->ev) CU(cudaEventCreate(&e));
+    ctx->profiling = on != 0;
+    ctx->ev_valid = false;
+    return ESL_OK;
+}
+
+int esl_get_timing(esl_ctx *ctx, float *bulk_ms, float *cutoff_ms)
+{
+    if (!ctx || !bulk_ms || !cutoff_ms) return ESL_ERR_INVALID;
+    if (!ctx->ev_valid) return ctx->fail(ESL_ERR_STATE, "no profiled launch: call esl_set_profiling(ctx, 1) before the run");
+    CU(cudaEventSynchronize(ctx->ev[3]));
+    CU(cudaEventElapsedTime(bulk_ms, ctx->ev[0], ctx->ev[1]));
+    CU(cudaEventElapsedTime(cutoff_ms, ctx->ev[2], ctx->ev[3]));
+    return ESL_OK;
+}
+
+int64_t esl_launch_count(const esl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int32_t esl_target_layers(const esl_ctx *ctx) { return ctx ? ctx->n_layers : 0; }
+
+int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_begin, int32_t n_iter, double coverage,
+                  int32_t consuming, int64_t min_overlap, double scaling, int64_t *d_tallies, int64_t *d_label_counts,
+                  int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status, void *d_ws, size_t ws_bytes, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n_iter < 1) return ctx->fail(ESL_ERR_INVALID, "n_iter must be >= 1");
+    if (!(coverage >= 0) || !std::isfinite(coverage)) return ctx->fail(ESL_ERR_INVALID, "coverage must be finite and >= 0");
+    if (combo >= (1u << 28)) return ctx->fail(ESL_ERR_INVALID, "combo index too large");
+    int rc = ensure_index(ctx, true);
+    if (rc) return rc;
+    if ((rc = check_outputs(ctx, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status))) return rc;
+    if ((u64)ctx->pool_max >= ctx->G) // numpy's randint(0, G - L) raises "low >= high" in the reference (read_operations.py:103)
+        return ctx->fail(ESL_ERR_INVALID, "longest read (%u) is not shorter than the genome (%llu)", ctx->pool_max, (unsigned long long)ctx->G);
+    const double expect = coverage * (double)ctx->G / ctx->pool_mean;
+    if (expect > 3.5e9) return ctx->fail(ESL_ERR_UNSUPPORTED, "more than 2^32 draws per iteration");
+    const i64 need = esl_workspace_bytes(ctx, n_iter, coverage, 0);
+    if (!d_ws || (i64)ws_bytes < need) return ctx->fail(ESL_ERR_WORKSPACE, "workspace %zu bytes < required %lld", ws_bytes, (long long)need);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
+    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0};
+    esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iter_begin};
+    const i64 nb = bulk_reads(ctx, coverage);
+    if (ctx->wide)
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, nullptr, nb, nb, n_iter, true, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, nullptr, nb, nb, n_iter, true, st);
+}
+
+int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,
+                     const int64_t *d_seg, int64_t total_reads, int32_t n_iter, int64_t min_overlap, int64_t *d_tallies,
+                     int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n_iter < 1 || total_reads < 0) return ctx->fail(ESL_ERR_INVALID, "bad n_iter / total_reads");
+    if (total_reads && (!d_start || !d_length || !d_label)) return ctx->fail(ESL_ERR_INVALID, "a read array is NULL");
+    if (!d_seg) return ctx->fail(ESL_ERR_INVALID, "seg_offsets is NULL");
+    int rc = ensure_index(ctx, false);
+    if (rc) return rc;
+    if ((rc = check_outputs(ctx, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status))) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
+    // the bulk kernel also records per-tile sums; replay level 1 has no cut-off, so they go to a private scratch
+    const i64 tiles = (total_reads + esl::kBulkTile - 1) / esl::kBulkTile + 1;
+    CU(ctx->d_scratch.reserve((size_t)tiles * n_iter * sizeof(u64)));
+    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, ctx->d_scratch.as<u64>(), 0};
+    esl::ReadSrc src{d_start, d_length, d_label, d_seg};
+    const i64 big = total_reads; // every iteration's reads are all "bulk" (clipped to its own count on device)
+    if (ctx->wide)
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, nullptr, big, big, n_iter, false, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, nullptr, big, big, n_iter, false, st);
+}
+
+int esl_replay_draws(esl_ctx *ctx, const double *d_ubc, const int64_t *d_length, const int64_t *d_start,
+                     const int64_t *d_uoff, const double *d_ublock, const int64_t *d_seg, int64_t max_draws,
+                     int64_t bulk_draws, int32_t n_iter, double coverage, int32_t consuming, int64_t min_overlap,
+                     int64_t *d_tallies, int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads,
+                     int32_t *d_status, void *d_ws, size_t ws_bytes, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n_iter < 1 || max_draws < 0) return ctx->fail(ESL_ERR_INVALID, "bad n_iter / max_draws_per_iter");
+    if (!d_ubc || !d_length || !d_start || !d_seg) return ctx->fail(ESL_ERR_INVALID, "a draw array is NULL");
+    int rc = ensure_index(ctx, false);
+    if (rc) return rc;
+    if (ctx->n_mask > 0 && (!d_uoff || !d_ublock)) return ctx->fail(ESL_ERR_INVALID, "a mask is set but the blocked-draw arrays are NULL");
+    if ((rc = check_outputs(ctx, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status))) return rc;
+    if (bulk_draws < 0) bulk_draws = 0;
+    if (bulk_draws > max_draws) bulk_draws = max_draws;
+    bulk_draws -= bulk_draws % esl::kBulkTile;
+    const i64 need = esl_workspace_bytes(ctx, n_iter, coverage, std::max<i64>(bulk_draws, 1));
+    if (!d_ws || (i64)ws_bytes < need) return ctx->fail(ESL_ERR_WORKSPACE, "workspace %zu bytes < required %lld", ws_bytes, (long long)need);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
+    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0};
+    esl::DrawSrc src{d_ubc, d_length, d_start, d_uoff, d_ublock, d_seg};
+    if (ctx->wide)
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, nullptr, bulk_draws, bulk_draws, n_iter, true, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, nullptr, bulk_draws, bulk_draws, n_iter, true, st);
+}
+
+int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iteration, int32_t consuming,
+                          int64_t n_reads, int64_t *d_start, int64_t *d_length, int32_t *d_label, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n_reads < 0 || (n_reads && (!d_start || !d_length || !d_label))) return ctx->fail(ESL_ERR_INVALID, "bad output arrays");
+    int rc = ensure_index(ctx, true);
+    if (rc) return rc;
+    if (n_reads == 0) return ESL_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iteration};
+    const unsigned grid = (unsigned)std::min<i64>((n_reads + 255) / 256, (i64)ctx->sm_count * 8);
+    const size_t sm = (size_t)ctx->B * 4 + 8;
+    if (ctx->wide)
+        esl::k_materialize<uint64_t><<<grid, 256, sm, st>>>(make_devctx<uint64_t>(ctx, 0.0, consuming, 1, 1.0), src, n_reads, d_start, d_length, d_label);
+    else
+        esl::k_materialize<uint32_t><<<grid, 256, sm, st>>>(make_devctx<uint32_t>(ctx, 0.0, consuming, 1, 1.0), src, n_reads, d_start, d_length, d_label);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return ESL_OK;
+}
+
+int esl_moments(esl_ctx *ctx, const int64_t *d_tallies, int32_t n_iter, int64_t *d_moments, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (!d_tallies || !d_moments || n_iter < 1) return ctx->fail(ESL_ERR_INVALID, "bad arguments");
+    if (!ctx->have_targets) return ctx->fail(ESL_ERR_STATE, "esl_set_targets has not been called");
+    const i64 T = (i64)ctx->t_start.size();
+    if (T == 0) return ESL_OK;
+    CU(cudaSetDevice(ctx->device));
+    esl::k_moments<<<(unsigned)((T + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_tallies, n_iter, T, d_moments);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return ESL_OK;
+}
+
+} // extern "C"

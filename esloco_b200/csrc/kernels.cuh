@@ -1,0 +1,554 @@
+// Device code of the esloco hot path for sm_100a.
+//
+// One placed read is resolved by the same inlined pipeline in every kernel:
+//   K1 Philox draw (or a recorded draw)            -> barcode uniform, length pick, start
+//   K2 length table gather                          read_operations.py:102 / combined_calculations.py:57
+//   K3 barcode CDF search + uniform placement       read_operations.py:96-103
+//   K4 blocked-interval search                      read_operations.py:59-67
+//   K6 target overlap search (read-centric, over monotone target layers)   counting.py:36-53
+//   K7 integer tallies via red.global               counting.py:54-57, :63-71
+// and K5, the coverage cut-off (read_operations.py:100), is split in two kernels:
+//   k_place_tally_bulk  : the first n_bulk draws of every iteration, which lie before the cut-off with
+//                         overwhelming probability; no ordering between reads is needed, so it is a flat
+//                         persistent grid.  Per-tile counted-length sums are kept.
+//   k_cutoff_tail       : one CTA per iteration continues from n_bulk in draw order with a block-scan
+//                         prefix sum until covered >= coverage*G, includes exactly the reads the
+//                         reference's while-loop would have drawn, and -- if the bulk range did overshoot
+//                         (checked exactly from the tile sums) -- regenerates the overshoot and subtracts
+//                         it again, so the result never depends on the statistical bound.
+// All counters are integers accumulated with atomics, so results are independent of scheduling.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "philox.cuh"
+
+namespace esl {
+
+typedef unsigned long long u64;
+typedef int64_t i64;
+
+constexpr int kBulkBlock = 256;
+constexpr int kBulkIpt = 4;
+constexpr int kBulkTile = kBulkBlock * kBulkIpt;
+constexpr int kTailBlock = 1024;
+constexpr int kTailIpt = 2;
+constexpr int kTailChunk = kTailBlock * kTailIpt;
+constexpr int kMaxBarcodes = 4096;
+
+constexpr int kLabelBlockedConsuming = -1;
+constexpr int kLabelBlockedNotConsuming = -2;
+
+// Everything a kernel needs to resolve one read; passed by value.
+template <typename C>
+struct DevCtx {
+    u64 G;           // genome size
+    i64 thr;         // ceil(coverage * G): covered < coverage*G  <=>  covered < thr for integer covered
+    i64 min_overlap; // min_overlap_for_detection
+    double scaling;  // >= 1: no thinning draw
+    int n_barcodes;
+    int consuming;
+    int has_mask;
+    uint32_t n_pool;
+    const uint32_t *__restrict__ pool;   // length table (K2)
+    const double *__restrict__ cdf;      // numpy-style cdf, replay path
+    const uint32_t *__restrict__ cdf_u32; // ceil(cdf * 2^32) saturated, native path
+    // target index: per barcode a run of "monotone layers" (starts AND ends ascending inside a layer), so
+    // the targets a read overlaps are one contiguous range per layer.
+    const C *__restrict__ ts;
+    const C *__restrict__ te;
+    const int32_t *__restrict__ trow;    // original row of the sorted target
+    const int32_t *__restrict__ seg_off; // [n_seg + 1]
+    const int32_t *__restrict__ bc_seg;  // [B + 1] layers of barcode b: bc_seg[b] .. bc_seg[b+1]
+    i64 n_targets;
+    // blocked index: group g < B is barcode g's tree, group B is "ALL"; inside a group sorted by
+    // (start, end) with a running max of ends for the lower bound.
+    const C *__restrict__ ms;
+    const C *__restrict__ me;
+    const C *__restrict__ mpmax;
+    const double *__restrict__ mw;
+    const int32_t *__restrict__ grp_off; // [B + 2]
+};
+
+struct DevOut {
+    u64 *tallies;      // [n_iter][T][3]
+    u64 *label_counts; // [n_iter][B+2]
+    u64 *n_bases;      // [n_iter]
+    u64 *n_reads;      // [n_iter]
+    int *status;       // [n_iter]
+    u64 *tile_sum;     // [n_iter][tiles_per_iter] counted-length sum of each bulk tile
+    int tiles_per_iter;
+};
+
+// ---------------------------------------------------------------- draw sources
+
+// Native stream.
+struct PhiloxSrc {
+    uint32_t k0, k1, combo, iter_begin;
+    static constexpr bool kHasLabel = false;
+    static constexpr bool kBounded = false;
+    __device__ __forceinline__ i64 count(int) const { return 0x7fffffffffffffffLL; }
+
+    template <typename C>
+    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *s_cdf, int it, i64 n, uint32_t &L,
+                                         C &start, int &bc) const
+    {
+        const Philox4 r = philox4x32_10((uint32_t)n, 0u, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, k0, k1);
+        L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool)); // uniform pick from the pool
+        const u64 range = cx.G - (u64)L;               // start ~ U{0 .. G-L-1}
+        start = (C)__umul64hi(((u64)r.x << 32) | r.y, range);
+        int k = 0;
+        if (cx.n_barcodes > 1) { // searchsorted(cdf, u, side='right') on integer thresholds
+            int lo = 0, hi = cx.n_barcodes - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_cdf[mid] <= r.w) lo = mid + 1; else hi = mid;
+            }
+            k = lo;
+        }
+        bc = k;
+    }
+    __device__ __forceinline__ double block_u(int it, i64 n, int j) const
+    {
+        const Philox4 r = philox4x32_10((uint32_t)n, (uint32_t)(j >> 1), iter_begin + (uint32_t)it,
+                                        (combo << 4) | ESL_SLOT_BLOCK, k0, k1);
+        return (j & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
+    }
+    __device__ __forceinline__ double scale_u(int it, i64 n, int row) const
+    {
+        const Philox4 r = philox4x32_10((uint32_t)n, (uint32_t)row, iter_begin + (uint32_t)it,
+                                        (combo << 4) | ESL_SLOT_SCALE, k0, k1);
+        return u53(r.x, r.y);
+    }
+};
+
+// Recorded raw draws (replay level 2).
+struct DrawSrc {
+    const double *__restrict__ ubc;
+    const i64 *__restrict__ length;
+    const i64 *__restrict__ start;
+    const i64 *__restrict__ uoff;
+    const double *__restrict__ ublock;
+    const i64 *__restrict__ seg;
+    static constexpr bool kHasLabel = false;
+    static constexpr bool kBounded = true;
+    __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
+
+    template <typename C>
+    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *, int it, i64 n, uint32_t &L, C &st,
+                                         int &bc) const
+    {
+        const i64 g = seg[it] + n;
+        L = (uint32_t)length[g];
+        st = (C)start[g];
+        const double u = ubc[g];
+        int k = 0;
+        while (k < cx.n_barcodes - 1 && cx.cdf[k] <= u) ++k;
+        bc = k;
+    }
+    __device__ __forceinline__ double block_u(int it, i64 n, int j) const { return ublock[uoff[seg[it] + n] + j]; }
+    __device__ __forceinline__ double scale_u(int, i64, int) const { return 0.0; }
+};
+
+// Recorded reads (replay level 1): the label is given, no CDF / blocked search.
+struct ReadSrc {
+    const i64 *__restrict__ start;
+    const i64 *__restrict__ length;
+    const int32_t *__restrict__ label;
+    const i64 *__restrict__ seg;
+    static constexpr bool kHasLabel = true;
+    static constexpr bool kBounded = true;
+    __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
+
+    template <typename C>
+    __device__ __forceinline__ void draw(const DevCtx<C> &, const uint32_t *, int it, i64 n, uint32_t &L, C &st,
+                                         int &bc) const
+    {
+        const i64 g = seg[it] + n;
+        L = (uint32_t)length[g];
+        st = (C)start[g];
+        bc = label[g];
+    }
+    __device__ __forceinline__ double block_u(int, i64, int) const { return 0.0; }
+    __device__ __forceinline__ double scale_u(int, i64, int) const { return 0.0; }
+};
+
+// ---------------------------------------------------------------- per-read pipeline
+
+// K4: is [rs, re) blocked for barcode bc?  Trees: the barcode's own, then "ALL"; hits in (start, end)
+// order; one uniform per visited hit; u < weight blocks (read_operations.py:59-67).
+template <typename C, typename Src>
+__device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, int it, i64 n, int bc, C rs, C re)
+{
+    int j = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int g = pass == 0 ? bc : cx.n_barcodes;
+        const int lo = __ldg(cx.grp_off + g), hi = __ldg(cx.grp_off + g + 1);
+        if (lo == hi) continue;
+        int a = lo, z = hi; // first interval whose running max of ends exceeds rs
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (__ldg(cx.mpmax + mid) <= rs) a = mid + 1; else z = mid;
+        }
+        for (int k = a; k < hi; ++k) {
+            if (__ldg(cx.ms + k) >= re) break;
+            if (__ldg(cx.me + k) > rs) {
+                const double u = src.block_u(it, n, j++);
+                if (u < __ldg(cx.mw + k)) return true;
+            }
+        }
+    }
+    return false;
+}
+
+// K6 + K7: add (sign = +1) or take back (sign = -1) the read's contribution to every target it overlaps.
+template <typename C, typename Src>
+__device__ __forceinline__ void tally_read(const DevCtx<C> &cx, const Src &src, u64 *__restrict__ tallies_it, int it,
+                                           i64 n, C rs, C re, int bc, i64 sign)
+{
+    const int s0 = __ldg(cx.bc_seg + bc), s1 = __ldg(cx.bc_seg + bc + 1);
+#pragma unroll 1
+    for (int sg = s0; sg < s1; ++sg) {
+        const int lo = __ldg(cx.seg_off + sg), hi = __ldg(cx.seg_off + sg + 1);
+        int a = lo, z = hi; // first target of the layer with end > rs (ends ascend inside a layer)
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (__ldg(cx.te + mid) <= rs) a = mid + 1; else z = mid;
+        }
+        for (int j = a; j < hi; ++j) {
+            const C s = __ldg(cx.ts + j);
+            if (s >= re) break; // starts ascend: nothing further overlaps
+            const C e = __ldg(cx.te + j);
+            const C ov = (e < re ? e : re) - (s > rs ? s : rs);
+            if ((i64)ov >= cx.min_overlap) {
+                const int row = __ldg(cx.trow + j);
+                if (cx.scaling < 1.0 && !(src.scale_u(it, n, row) <= cx.scaling)) continue;
+                const bool full = rs <= s && e <= re;
+                u64 *t = tallies_it + (i64)row * 3;
+                atomicAdd(t + (full ? 0 : 1), (u64)sign);
+                atomicAdd(t + 2, (u64)(sign * (i64)ov));
+            }
+        }
+    }
+}
+
+// Resolve label + counted length of one drawn read (read_operations.py:104-121).
+template <typename C, typename Src>
+__device__ __forceinline__ void resolve_read(const DevCtx<C> &cx, const Src &src, int it, i64 n, uint32_t L, C st,
+                                             int bc, int &label, uint32_t &counted)
+{
+    label = bc;
+    counted = L;
+    if (Src::kHasLabel) {
+        if (bc == kLabelBlockedNotConsuming) counted = 0;
+        return;
+    }
+    if (cx.has_mask && is_blocked(cx, src, it, n, bc, st, (C)(st + L))) {
+        label = cx.consuming ? kLabelBlockedConsuming : kLabelBlockedNotConsuming;
+        counted = cx.consuming ? L : 0u;
+    }
+}
+
+__device__ __forceinline__ int label_slot(int label, int B) { return label >= 0 ? label : (label == -1 ? B : B + 1); }
+
+__device__ __forceinline__ u64 warp_sum(u64 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------- bulk kernel
+
+// Persistent flat grid; CTA c owns a contiguous run of (iteration, tile) pairs so the per-iteration
+// counters are flushed once per iteration change, not once per tile.
+template <typename C, typename Src>
+__global__ void __launch_bounds__(kBulkBlock)
+k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__restrict__ n_bulk_arr,
+                   const i64 n_bulk_const, const i64 total_tiles)
+{
+    extern __shared__ u64 smem[];
+    u64 *s_hist = smem;                                   // [B + 2]
+    u64 *s_part = smem + cx.n_barcodes + 2;               // [kBulkBlock / 32]
+    uint32_t *s_cdf = (uint32_t *)(s_part + kBulkBlock / 32); // [B]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int B = cx.n_barcodes;
+    for (int i = tid; i < B + 2; i += kBulkBlock) s_hist[i] = 0;
+    if (!Src::kHasLabel && cx.cdf_u32)
+        for (int i = tid; i < B; i += kBulkBlock) s_cdf[i] = cx.cdf_u32[i];
+    __syncthreads();
+
+    const i64 per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const i64 t0 = (i64)blockIdx.x * per_cta;
+    const i64 t1 = t0 + per_cta < total_tiles ? t0 + per_cta : total_tiles;
+    const bool plain_labels = !Src::kHasLabel && B == 1 && !cx.has_mask; // every read is label 0
+    int cur_it = -1;
+    u64 acc_bases = 0, acc_reads = 0; // thread 0 only
+
+    for (i64 tl = t0; tl < t1; ++tl) {
+        const int it = (int)(tl / out.tiles_per_iter);
+        const i64 t = tl - (i64)it * out.tiles_per_iter;
+        if (it != cur_it) {
+            if (cur_it >= 0) {
+                __syncthreads();
+                for (int i = tid; i < B + 2; i += kBulkBlock)
+                    if (s_hist[i]) { atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, s_hist[i]); s_hist[i] = 0; }
+                if (tid == 0) {
+                    atomicAdd(out.n_bases + cur_it, acc_bases);
+                    atomicAdd(out.n_reads + cur_it, acc_reads);
+                    if (plain_labels) atomicAdd(out.label_counts + (i64)cur_it * (B + 2), acc_reads);
+                    acc_bases = acc_reads = 0;
+                }
+                __syncthreads();
+            }
+            cur_it = it;
+        }
+        i64 nb = n_bulk_arr ? n_bulk_arr[it] : n_bulk_const;
+        if (Src::kBounded) { const i64 c = src.count(it); nb = nb < c ? nb : c; }
+        const i64 base = t * kBulkTile;
+        if (base >= nb) { // tile beyond this iteration's bulk range (block-uniform)
+            if (tid == 0) out.tile_sum[tl] = 0;
+            continue;
+        }
+        uint32_t L[kBulkIpt];
+        C st[kBulkIpt];
+        int bc[kBulkIpt];
+        bool valid[kBulkIpt];
+#pragma unroll
+        for (int i = 0; i < kBulkIpt; ++i) { // phase 1: independent draws + table gathers in flight together
+            const i64 n = base + i * kBulkBlock + tid;
+            valid[i] = n < nb;
+            L[i] = 0; st[i] = 0; bc[i] = 0;
+            if (valid[i]) src.draw(cx, s_cdf, it, n, L[i], st[i], bc[i]);
+        }
+        u64 my = 0;
+        u64 *tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
+#pragma unroll
+        for (int i = 0; i < kBulkIpt; ++i) { // phase 2: blocked test, label, tally
+            if (!valid[i]) continue;
+            const i64 n = base + i * kBulkBlock + tid;
+            int label; uint32_t counted;
+            resolve_read(cx, src, it, n, L[i], st[i], bc[i], label, counted);
+            my += counted;
+            if (!plain_labels) atomicAdd(s_hist + label_slot(label, B), 1ull);
+            if (label >= 0 && label < B) tally_read(cx, src, tallies_it, it, n, st[i], (C)(st[i] + L[i]), label, 1);
+        }
+        my = warp_sum(my);
+        if (lane == 0) s_part[wid] = my;
+        __syncthreads();
+        if (tid == 0) {
+            u64 s = 0;
+#pragma unroll
+            for (int w = 0; w < kBulkBlock / 32; ++w) s += s_part[w];
+            out.tile_sum[tl] = s;
+            acc_bases += s;
+            const i64 left = nb - base;
+            acc_reads += (u64)(left < kBulkTile ? left : kBulkTile);
+        }
+        __syncthreads();
+    }
+    if (cur_it >= 0) {
+        __syncthreads();
+        for (int i = tid; i < B + 2; i += kBulkBlock)
+            if (s_hist[i]) atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, s_hist[i]);
+        if (tid == 0) {
+            atomicAdd(out.n_bases + cur_it, acc_bases);
+            atomicAdd(out.n_reads + cur_it, acc_reads);
+            if (plain_labels) atomicAdd(out.label_counts + (i64)cur_it * (B + 2), acc_reads);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- exact cut-off kernel (K5)
+
+// Block-wide exclusive scan of one u64 per thread; returns the exclusive prefix, *total = block sum.
+__device__ __forceinline__ u64 block_excl_scan(u64 v, u64 *s_warp, u64 *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u64 incl = warp_incl_scan(v, lane);
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const u64 w = s_warp[lane]; // kTailBlock / 32 == 32 warps
+        const u64 wi = warp_incl_scan(w, lane);
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    const u64 ex = s_warp[wid] + incl - v;
+    *total = s_warp[32];
+    __syncthreads();
+    return ex;
+}
+
+template <typename C, typename Src>
+__global__ void __launch_bounds__(kTailBlock)
+k_cutoff_tail(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__restrict__ n_bulk_arr,
+              const i64 n_bulk_const)
+{
+    extern __shared__ u64 smem[];
+    u64 *s_warp = smem;                         // [33]
+    u64 *s_hist = smem + 40;                    // [B + 2] (two's complement deltas)
+    uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2);
+    __shared__ i64 s_cut_tile;
+    __shared__ u64 s_cut_prefix;
+    const int tid = threadIdx.x;
+    const int B = cx.n_barcodes;
+    const int it = blockIdx.x;
+    for (int i = tid; i < B + 2; i += kTailBlock) s_hist[i] = 0;
+    if (!Src::kHasLabel && cx.cdf_u32)
+        for (int i = tid; i < B; i += kTailBlock) s_cdf[i] = cx.cdf_u32[i];
+    if (tid == 0) { s_cut_tile = -1; s_cut_prefix = 0; }
+    __syncthreads();
+
+    const i64 n_total = src.count(it);
+    i64 nb = n_bulk_arr ? n_bulk_arr[it] : n_bulk_const;
+    if (nb > n_total) nb = n_total;
+    const u64 bulk_sum = out.n_bases[it];
+    const i64 thr = cx.thr;
+    u64 *tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
+
+    i64 n, n_end;
+    u64 covered;
+    bool take_back; // true: the cut-off lies inside the bulk range; remove what bulk added beyond it
+    if ((i64)bulk_sum >= thr && nb > 0) {
+        take_back = true;
+        const i64 tiles = (nb + kBulkTile - 1) / kBulkTile;
+        const u64 *ts_it = out.tile_sum + (i64)it * out.tiles_per_iter;
+        u64 run = 0;
+        for (i64 b0 = 0; b0 < tiles; b0 += kTailBlock) { // first tile whose inclusive prefix reaches thr
+            const i64 ti = b0 + tid;
+            const u64 v = ti < tiles ? ts_it[ti] : 0;
+            u64 tot;
+            const u64 ex = block_excl_scan(v, s_warp, &tot);
+            const bool hit = ti < tiles && (i64)(run + ex) < thr && (i64)(run + ex + v) >= thr;
+            if (hit) { s_cut_tile = ti; s_cut_prefix = run + ex; }
+            __syncthreads();
+            if (s_cut_tile >= 0) break;
+            run += tot;
+        }
+        n = s_cut_tile * kBulkTile;
+        covered = s_cut_prefix;
+        n_end = nb;
+        if (tid == 0) atomicOr(out.status + it, 1);
+    } else {
+        take_back = false;
+        n = nb;
+        covered = bulk_sum;
+        n_end = n_total;
+    }
+
+    i64 d_bases = 0, d_reads = 0; // deltas to the bulk totals (uniform across the block)
+    bool exhausted = false;
+#pragma unroll 1
+    for (;;) {
+        if (n >= n_end) { exhausted = !take_back; break; }
+        uint32_t L[kTailIpt];
+        C st[kTailIpt];
+        int bc[kTailIpt], label[kTailIpt];
+        uint32_t counted[kTailIpt];
+        bool valid[kTailIpt];
+        u64 mine = 0;
+#pragma unroll
+        for (int i = 0; i < kTailIpt; ++i) { // thread-contiguous draw order so one scan orders the chunk
+            const i64 idx = n + (i64)tid * kTailIpt + i;
+            valid[i] = idx < n_end;
+            L[i] = 0; st[i] = 0; bc[i] = 0; label[i] = 0; counted[i] = 0;
+            if (valid[i]) {
+                src.draw(cx, s_cdf, it, idx, L[i], st[i], bc[i]);
+                resolve_read(cx, src, it, idx, L[i], st[i], bc[i], label[i], counted[i]);
+                mine += counted[i];
+            }
+        }
+        u64 chunk_total;
+        u64 pre = covered + block_excl_scan(mine, s_warp, &chunk_total);
+        u64 inc_bases = 0; // counted bases / reads of this thread on the acted-on side of the cut
+        int inc_reads = 0, excluded = 0;
+#pragma unroll
+        for (int i = 0; i < kTailIpt; ++i) {
+            if (!valid[i]) continue;
+            const bool included = (i64)pre < thr; // the while-condition seen by this draw (read_operations.py:100)
+            pre += counted[i];
+            excluded += !included;
+            const bool act = take_back ? !included : included;
+            if (!act) continue;
+            const i64 sign = take_back ? -1 : 1;
+            inc_bases += counted[i];
+            inc_reads += 1;
+            atomicAdd(s_hist + label_slot(label[i], B), (u64)sign);
+            if (label[i] >= 0 && label[i] < B)
+                tally_read(cx, src, tallies_it, it, n + (i64)tid * kTailIpt + i, st[i], (C)(st[i] + L[i]), label[i], sign);
+        }
+        u64 tot_b, tot_r, tot_x;
+        block_excl_scan(inc_bases, s_warp, &tot_b);
+        block_excl_scan((u64)inc_reads, s_warp, &tot_r);
+        block_excl_scan((u64)excluded, s_warp, &tot_x);
+        if (take_back) { d_bases -= (i64)tot_b; d_reads -= (i64)tot_r; }
+        else { d_bases += (i64)tot_b; d_reads += (i64)tot_r; }
+        covered += chunk_total;
+        n += kTailChunk;
+        if (!take_back && tot_x > 0) break; // the cut-off read was in this chunk
+    }
+    __syncthreads();
+    for (int i = tid; i < B + 2; i += kTailBlock)
+        if (s_hist[i]) out.label_counts[(i64)it * (B + 2) + i] += s_hist[i];
+    if (tid == 0) {
+        out.n_bases[it] = bulk_sum + (u64)d_bases;
+        out.n_reads[it] += (u64)d_reads;
+        if (exhausted && (i64)covered < thr) atomicOr(out.status + it, 2);
+    }
+}
+
+// ---------------------------------------------------------------- auxiliary kernels
+
+// Write the first n_reads draws of one native iteration in draw order (coverage track / overlap lists).
+template <typename C>
+__global__ void __launch_bounds__(256)
+k_materialize(const DevCtx<C> cx, const PhiloxSrc src, const i64 n_reads, i64 *__restrict__ o_start,
+              i64 *__restrict__ o_length, int32_t *__restrict__ o_label)
+{
+    extern __shared__ u64 smem[];
+    uint32_t *s_cdf = (uint32_t *)smem;
+    for (int i = threadIdx.x; i < cx.n_barcodes; i += blockDim.x) s_cdf[i] = cx.cdf_u32[i];
+    __syncthreads();
+    for (i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x; n < n_reads; n += (i64)gridDim.x * blockDim.x) {
+        uint32_t L, counted; C st; int bc, label;
+        src.draw(cx, s_cdf, 0, n, L, st, bc);
+        resolve_read(cx, src, 0, n, L, st, bc, label, counted);
+        o_start[n] = (i64)st;
+        o_length[n] = (i64)L;
+        o_label[n] = label;
+    }
+}
+
+// Per-target moment accumulators over the iterations of a batch (operand of the multi-GPU sum-reduce).
+__global__ void __launch_bounds__(256)
+k_moments(const i64 *__restrict__ tallies, const int n_iter, const i64 n_targets, i64 *__restrict__ mom)
+{
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_targets) return;
+    i64 sf = 0, sf2 = 0, sp = 0, sp2 = 0, sb = 0;
+    unsigned __int128 sb2 = 0;
+    for (int it = 0; it < n_iter; ++it) {
+        const i64 *r = tallies + ((i64)it * n_targets + t) * 3;
+        const i64 f = r[0], p = r[1], b = r[2];
+        sf += f; sf2 += f * f; sp += p; sp2 += p * p; sb += b;
+        sb2 += (unsigned __int128)(u64)b * (u64)b;
+    }
+    i64 *m = mom + t * 8;
+    m[0] += n_iter; m[1] += sf; m[2] += sf2; m[3] += sp; m[4] += sp2; m[5] += sb;
+    m[6] += (i64)(u64)(sb2 & 0xffffffffull);
+    m[7] += (i64)(u64)(sb2 >> 32);
+}
+
+} // namespace esl

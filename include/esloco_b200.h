@@ -1,0 +1,165 @@
+/*
+ * esloco_b200.h -- C ABI of the B200-native engine for esloco's Monte-Carlo hot path
+ * (read placement + per-target / per-barcode tally).
+ *
+ * The reference (aweich/esloco v1.0.6) is pure Python and has no FFI of its own; the seam this
+ * library sits behind is the Python call
+ *     run_simulation_iteration(iteration_id, param_dictionary, genome_size, target_regions,
+ *                              masked_tree, log_file)          src/esloco/combined_calculations.py:97-126
+ * and its two inner calls
+ *     generate_reads_based_on_coverage(...)                     src/esloco/read_operations.py:86-123
+ *     count_matches(insertion_dict, read_dir, scaling, min_overlap)   src/esloco/counting.py:7-61
+ * Each entry point below cites the reference lines whose work it takes over.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 (ESL_OK) or a negative esl_status; no exceptions cross;
+ *     esl_last_error(ctx) gives the message of the last failing call on that context.
+ *   - esl_set_* take HOST pointers (small, one-off inputs) and build device-resident index structures.
+ *   - esl_run_* / esl_replay_* / esl_moments take DEVICE pointers for bulk data and outputs, are
+ *     asynchronous on the given CUDA stream (a cudaStream_t passed as void*), and do not allocate.
+ *     Scratch is a caller-provided workspace of esl_workspace_bytes().
+ *   - one host thread per context at a time.
+ *   - there is no CPU fallback: esl_create fails if no sm_100 device is present.
+ *
+ * Read labels: barcode k >= 0, ESL_LABEL_BLOCKED_CONSUMING, ESL_LABEL_BLOCKED_NOTCONSUMING
+ * (the reference's "Blocked/Consuming" / "Blocked/NotConsuming" dict-key suffixes, read_operations.py:113,116).
+ *
+ * Output layouts (row-major, int64):
+ *   tallies      [n_iter][n_targets][3] = {full_matches, partial_matches, on_target_bases}  counting.py:54-57
+ *   label_counts [n_iter][n_barcodes+2] = reads per barcode, then Blocked/Consuming, Blocked/NotConsuming
+ *                                                                                 counting.py:63-71
+ *   n_bases      [n_iter]  covered_length ("N_bases", combined_calculations.py:81)
+ *   n_reads      [n_iter]  reads placed = entries of the reference's read dict (blocked ones included)
+ *   status       [n_iter]  int32 bit mask, see ESL_ITER_*
+ */
+#ifndef ESLOCO_B200_H
+#define ESLOCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct esl_ctx esl_ctx;
+
+typedef enum {
+    ESL_OK = 0,
+    ESL_ERR_INVALID = -1,    /* bad argument (message says which) */
+    ESL_ERR_CUDA = -2,       /* a CUDA runtime call failed */
+    ESL_ERR_NO_DEVICE = -3,  /* no CUDA device, or not compute capability 10.x */
+    ESL_ERR_STATE = -4,      /* a required esl_set_* call is missing */
+    ESL_ERR_WORKSPACE = -5,  /* workspace too small */
+    ESL_ERR_UNSUPPORTED = -6 /* valid in the reference but not supported here (message says what) */
+} esl_status;
+
+#define ESL_LABEL_BLOCKED_CONSUMING (-1)
+#define ESL_LABEL_BLOCKED_NOTCONSUMING (-2)
+
+/* per-iteration status bits */
+#define ESL_ITER_CUT_IN_BULK 1 /* informational: coverage was reached inside the bulk range; corrected on device */
+#define ESL_ITER_EXHAUSTED 2   /* replay only: the recorded draws ran out before coverage was reached */
+
+/* Version of this ABI (bumped on any signature change). */
+int esl_abi_version(void);
+
+/* Message of the last error raised by esl_create (ctx == NULL) or by a call on ctx. */
+const char *esl_last_error(const esl_ctx *ctx);
+
+/* One context per GPU.  Fails with ESL_ERR_NO_DEVICE when `device` is not a compute-capability-10.x GPU. */
+int esl_create(esl_ctx **ctx, int device);
+int esl_destroy(esl_ctx *ctx);
+
+/* genome_size of the concatenated coordinate space (fasta_operations.py:3-22 -> esloco.py:107,124).
+ * Genomes >= 2^32 switch every kernel to 64-bit coordinates. */
+int esl_set_genome(esl_ctx *ctx, uint64_t genome_size);
+
+/* Barcode CDF exactly as numpy's choice(p=) builds it from read_operations.py:96-97 (cumsum, /= last). */
+int esl_set_barcode_cdf(esl_ctx *ctx, const double *cdf, int32_t n_barcodes);
+
+/* Targets in the reference's dict order (row order of `tallies`): half-open [start, end), and the barcode a
+ * read must carry to match (key.split("_")[1], counting.py:37); barcode < 0 = matches nothing. */
+int esl_set_targets(esl_ctx *ctx, const int64_t *start, const int64_t *end, const int32_t *barcode,
+                    int64_t n_targets);
+
+/* Blocked intervals of build_mask_tree (utils.py:89-101): barcode >= 0 for that barcode's tree, -1 for "ALL".
+ * A read [s, s+L) hits interval k iff start[k] < s+L and end[k] > s (read_operations.py:63); each visited hit
+ * draws u and blocks when u < weight[k] (:65).  n = 0 clears the mask. */
+int esl_set_blocked(esl_ctx *ctx, const int64_t *start, const int64_t *end, const double *weight,
+                    const int32_t *barcode, int64_t n);
+
+/* Read-length pool: the source distribution after the `> min_read_length` filter (read_operations.py:24-25,
+ * config_handler.py:44).  A read length is a uniform pick from it (combined_calculations.py:57 +
+ * read_operations.py:102 collapse to that). */
+int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n);
+
+/* Scratch bytes esl_run_batch / esl_replay_draws need for n_iter iterations at `coverage`
+ * (for replay pass the largest per-iteration draw count in max_draws_per_iter, else 0). */
+int64_t esl_workspace_bytes(const esl_ctx *ctx, int32_t n_iter, double coverage, int64_t max_draws_per_iter);
+
+/* Native mode: run iterations [iter_begin, iter_begin + n_iter) of combination `combo` with the counter-based
+ * Philox4x32-10 stream keyed by `seed`; results do not depend on how iterations are split into batches or
+ * across GPUs.  Replaces run_simulation_iteration's per-combination body (combined_calculations.py:56-84):
+ * placement until covered_length >= coverage * genome_size (read_operations.py:100), blocked-region test,
+ * label histogram and target tally.  scaling < 1 thins qualifying (target, read) pairs (counting.py:46,51).
+ * Outputs are zeroed by the call. */
+int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_begin, int32_t n_iter,
+                  double coverage, int32_t consuming, int64_t min_overlap, double scaling, int64_t *d_tallies,
+                  int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status,
+                  void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Replay level 1: recorded reads (already cut off), iteration i owns reads [seg_offsets[i], seg_offsets[i+1]).
+ * count_matches + count_barcode_occurrences over them (counting.py:7-71).  seg_offsets is a DEVICE array of
+ * n_iter+1 int64; total_reads = seg_offsets[n_iter] (passed so the host need not read it back). */
+int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,
+                     const int64_t *d_seg_offsets, int64_t total_reads, int32_t n_iter, int64_t min_overlap,
+                     int64_t *d_tallies, int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads,
+                     int32_t *d_status, void *stream);
+
+/* Replay level 2: recorded RAW draws of an oversampled batch (read_operations.py:101-103,65): per draw the
+ * barcode uniform, the picked length and the start; per visited blocked hit one uniform
+ * (d_ublock[d_ublock_off[n] + j] for the j-th visited hit of draw n, hits visited in (start, end) order, the
+ * read's barcode tree first, then "ALL").  The device does the CDF lookup, the blocked search, the
+ * prefix-sum cut-off and the tally.  d_ublock_off may be NULL when no mask is set.  `bulk_draws` is how many
+ * leading draws of each iteration go through the order-free bulk kernel before the exact cut-off kernel
+ * takes over (any value gives the same result; 0 = everything through the cut-off kernel). */
+int esl_replay_draws(esl_ctx *ctx, const double *d_u_barcode, const int64_t *d_length, const int64_t *d_start,
+                     const int64_t *d_ublock_off, const double *d_ublock, const int64_t *d_seg_offsets,
+                     int64_t max_draws_per_iter, int64_t bulk_draws, int32_t n_iter, double coverage,
+                     int32_t consuming, int64_t min_overlap, int64_t *d_tallies, int64_t *d_label_counts,
+                     int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status, void *d_workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* Materialise the first n_reads draws of ONE native-mode iteration in draw order (start, length, label), for
+ * consumers that need the reads themselves (coverage track coverage.py:52-81, overlap lists counting.py:56).
+ * n_reads is the iteration's d_n_reads value from esl_run_batch with the same seed / combo / consuming. */
+int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iteration, int32_t consuming,
+                          int64_t n_reads, int64_t *d_start, int64_t *d_length, int32_t *d_label, void *stream);
+
+/* Per-target moment accumulators over iterations, the operand of the multi-GPU sum-reduce that replaces the
+ * joblib result gather + pandas groupby (esloco.py:149-158,183-195):
+ *   d_moments [n_targets][ESL_MOMENT_COLS] += {n, sum f, sum f^2, sum p, sum p^2, sum b, lo32(sum b^2), hi(sum b^2)}
+ * with f/p/b = full / partial / on_target_bases and sum b^2 split as hi * 2^32 + lo so every column stays an
+ * exact int64 under summation.  Accumulates (does not zero). */
+#define ESL_MOMENT_COLS 8
+int esl_moments(esl_ctx *ctx, const int64_t *d_tallies, int32_t n_iter, int64_t *d_moments, void *stream);
+
+/* Per-kernel device timing for bench.py's roofline: when on, the next esl_run_batch / esl_replay_* records CUDA
+ * events on its stream around the bulk kernel and around the cut-off kernel; esl_get_timing waits for them and
+ * returns the two durations of the last such call in milliseconds. */
+int esl_set_profiling(esl_ctx *ctx, int32_t on);
+int esl_get_timing(esl_ctx *ctx, float *bulk_ms, float *cutoff_ms);
+
+/* Introspection (for bench.py / DESIGN.md): number of kernel launches issued by this context so far. */
+int64_t esl_launch_count(const esl_ctx *ctx);
+/* Target index shape: total monotone layers over all barcodes (1 per barcode when targets do not nest). */
+int32_t esl_target_layers(const esl_ctx *ctx);
+/* Reads per iteration the bulk kernel processes before the exact cut-off kernel takes over. */
+int64_t esl_bulk_reads(const esl_ctx *ctx, double coverage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESLOCO_B200_H */

@@ -73,3 +73,24 @@ def test_barcode_probabilities(B, w):
     assert abs(p.sum() - 1) < 1e-12
     if w == {"0": 10} and B == 4:  # SURVEY.md Appendix A.1 probe
         assert np.allclose(p, [10 / 13, 1 / 13, 1 / 13, 1 / 13])
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (the engine's native stream)."""
+    from oracle import native_np as NN
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kat:
+        out = NN.philox4x32_10(*[np.array([c], np.uint64) for c in ctr], key[0], key[1])
+        assert tuple(int(o[0]) for o in out) == exp
+
+
+def test_mulhi64_restatement():
+    from oracle import native_np as NN
+    r = np.random.RandomState(3)
+    a = r.randint(0, 2**63, size=1000, dtype=np.int64).astype(np.uint64) * np.uint64(2) + np.uint64(1)
+    b = r.randint(1, 2**62, size=1000, dtype=np.int64).astype(np.uint64)
+    got = NN.mulhi64(a, b)
+    assert [int(x) for x in got] == [(int(x) * int(y)) >> 64 for x, y in zip(a, b)]
