@@ -26,9 +26,11 @@ def _length_pool_key_and_factory(seed, combo, mean_read_length, sequenced_data_p
 
 
 def run_simulation_batch(iteration_ids, param_dictionary, genome_size, target_regions, masked_tree, device=0,
-                         to_host=True):
+                         to_host=True, length_pools=None):
     """All combinations for a contiguous run of iterations.  Returns one BatchResult per combination (on the
-    host when to_host) plus the target keys; iteration i of the batch is iteration_ids[0] + i."""
+    host when to_host) plus the target keys; iteration i of the batch is iteration_ids[0] + i.
+    length_pools optionally maps a combination index to a ready-made host array of read lengths (already
+    filtered by min_read_length), bypassing the FASTQ scan / log-normal draw."""
     iteration_ids = list(iteration_ids)
     first, n_iter = iteration_ids[0], len(iteration_ids)
     if iteration_ids != list(range(first, first + n_iter)):
@@ -40,8 +42,11 @@ def run_simulation_batch(iteration_ids, param_dictionary, genome_size, target_re
     scaling = p["scaling"] if isinstance(p["scaling"], (int, float)) else 1
     out = []
     for combo, (mean_read_length, coverage) in enumerate(p["combinations"]):
-        key, factory = _length_pool_key_and_factory(seed, combo, mean_read_length, p.get("sequenced_data_path"),
-                                                    p["sigma"], p["min_read_length"])
+        if length_pools is not None and combo in length_pools:
+            key, factory = ("given", id(length_pools[combo])), (lambda c=combo: length_pools[c])
+        else:
+            key, factory = _length_pool_key_and_factory(seed, combo, mean_read_length, p.get("sequenced_data_path"),
+                                                        p["sigma"], p["min_read_length"])
         sess.set_pool(key, factory)
         res = sess.engine.run_batch(seed, combo, first, n_iter, coverage, p["consuming"],
                                     p["min_overlap_for_detection"], scaling)

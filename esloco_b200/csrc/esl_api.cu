@@ -255,8 +255,8 @@ i64 bulk_reads(const esl_ctx *ctx, double coverage)
     return n < 2 * esl::kBulkTile ? 0 : n;
 }
 
-size_t bulk_smem(int B) { return (size_t)(B + 2 + esl::kBulkBlock / 32) * 8 + (size_t)B * 4; }
-size_t tail_smem(int B) { return (size_t)(40 + B + 2) * 8 + (size_t)B * 4; }
+size_t bulk_smem(int B) { return (size_t)(esl::kBulkBlock / 32) * 8 + (size_t)(2 * B + 2) * 4; }
+size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4; }
 
 template <typename C, typename Src>
 int launch_pipeline(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, esl::DevOut out, const i64 *d_n_bulk,

@@ -95,8 +95,13 @@ struct PhiloxSrc {
     {
         const Philox4 r = philox4x32_10((uint32_t)n, 0u, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, k0, k1);
         L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool)); // uniform pick from the pool
-        const u64 range = cx.G - (u64)L;               // start ~ U{0 .. G-L-1}
-        start = (C)__umul64hi(((u64)r.x << 32) | r.y, range);
+        const u64 range = cx.G - (u64)L;               // start ~ U{0 .. G-L-1} = floor(u64 * range / 2^64)
+        if (sizeof(C) == 4) { // range < 2^32: two 32x32->64 products instead of a 64x64 high multiply
+            const uint32_t rg = (uint32_t)range;
+            start = (C)(((u64)r.x * rg + (((u64)r.y * rg) >> 32)) >> 32);
+        } else {
+            start = (C)__umul64hi(((u64)r.x << 32) | r.y, range);
+        }
         int k = 0;
         if (cx.n_barcodes > 1) { // searchsorted(cdf, u, side='right') on integer thresholds
             int lo = 0, hi = cx.n_barcodes - 1;
@@ -252,6 +257,15 @@ __device__ __forceinline__ void resolve_read(const DevCtx<C> &cx, const Src &src
 
 __device__ __forceinline__ int label_slot(int label, int B) { return label >= 0 ? label : (label == -1 ? B : B + 1); }
 
+// Shared-memory label histogram update, called by ALL lanes of a warp (slot < 0 = nothing to add).  Lanes with
+// the same slot are combined with match.any so one 32-bit ATOMS per distinct label is issued (64-bit shared
+// atomics are CAS loops and serialise badly when every lane hits the same counter).
+__device__ __forceinline__ void hist_add(int *s_hist, int slot, int delta)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, slot);
+    if (slot >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(s_hist + slot, delta * __popc(peers));
+}
+
 __device__ __forceinline__ u64 warp_sum(u64 v)
 {
 #pragma unroll
@@ -278,9 +292,9 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
                    const i64 n_bulk_const, const i64 total_tiles)
 {
     extern __shared__ u64 smem[];
-    u64 *s_hist = smem;                                   // [B + 2]
-    u64 *s_part = smem + cx.n_barcodes + 2;               // [kBulkBlock / 32]
-    uint32_t *s_cdf = (uint32_t *)(s_part + kBulkBlock / 32); // [B]
+    u64 *s_part = smem;                                   // [kBulkBlock / 32]
+    int *s_hist = (int *)(s_part + kBulkBlock / 32);      // [B + 2] reads per label since the last flush
+    uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2); // [B]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int B = cx.n_barcodes;
     for (int i = tid; i < B + 2; i += kBulkBlock) s_hist[i] = 0;
@@ -302,7 +316,7 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
             if (cur_it >= 0) {
                 __syncthreads();
                 for (int i = tid; i < B + 2; i += kBulkBlock)
-                    if (s_hist[i]) { atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, s_hist[i]); s_hist[i] = 0; }
+                    if (s_hist[i]) { atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
                 if (tid == 0) {
                     atomicAdd(out.n_bases + cur_it, acc_bases);
                     atomicAdd(out.n_reads + cur_it, acc_reads);
@@ -335,13 +349,12 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
         u64 *tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
 #pragma unroll
         for (int i = 0; i < kBulkIpt; ++i) { // phase 2: blocked test, label, tally
-            if (!valid[i]) continue;
             const i64 n = base + i * kBulkBlock + tid;
-            int label; uint32_t counted;
-            resolve_read(cx, src, it, n, L[i], st[i], bc[i], label, counted);
+            int label = 0; uint32_t counted = 0;
+            if (valid[i]) resolve_read(cx, src, it, n, L[i], st[i], bc[i], label, counted);
             my += counted;
-            if (!plain_labels) atomicAdd(s_hist + label_slot(label, B), 1ull);
-            if (label >= 0 && label < B) tally_read(cx, src, tallies_it, it, n, st[i], (C)(st[i] + L[i]), label, 1);
+            if (!plain_labels) hist_add(s_hist, valid[i] && label < B ? label_slot(label, B) : -1, 1);
+            if (valid[i] && label >= 0 && label < B) tally_read(cx, src, tallies_it, it, n, st[i], (C)(st[i] + L[i]), label, 1);
         }
         my = warp_sum(my);
         if (lane == 0) s_part[wid] = my;
@@ -360,7 +373,7 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
     if (cur_it >= 0) {
         __syncthreads();
         for (int i = tid; i < B + 2; i += kBulkBlock)
-            if (s_hist[i]) atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, s_hist[i]);
+            if (s_hist[i]) atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, (u64)(uint32_t)s_hist[i]);
         if (tid == 0) {
             atomicAdd(out.n_bases + cur_it, acc_bases);
             atomicAdd(out.n_reads + cur_it, acc_reads);
@@ -398,7 +411,7 @@ k_cutoff_tail(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__
 {
     extern __shared__ u64 smem[];
     u64 *s_warp = smem;                         // [33]
-    u64 *s_hist = smem + 40;                    // [B + 2] (two's complement deltas)
+    int *s_hist = (int *)(smem + 40);           // [B + 2] signed deltas to the label counts
     uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2);
     __shared__ i64 s_cut_tile;
     __shared__ u64 s_cut_prefix;
@@ -476,16 +489,15 @@ k_cutoff_tail(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__
         int inc_reads = 0, excluded = 0;
 #pragma unroll
         for (int i = 0; i < kTailIpt; ++i) {
-            if (!valid[i]) continue;
             const bool included = (i64)pre < thr; // the while-condition seen by this draw (read_operations.py:100)
             pre += counted[i];
-            excluded += !included;
-            const bool act = take_back ? !included : included;
+            excluded += valid[i] && !included;
+            const bool act = valid[i] && (take_back ? !included : included);
+            const int sign = take_back ? -1 : 1;
+            hist_add(s_hist, act && label[i] < B ? label_slot(label[i], B) : -1, sign);
             if (!act) continue;
-            const i64 sign = take_back ? -1 : 1;
             inc_bases += counted[i];
             inc_reads += 1;
-            atomicAdd(s_hist + label_slot(label[i], B), (u64)sign);
             if (label[i] >= 0 && label[i] < B)
                 tally_read(cx, src, tallies_it, it, n + (i64)tid * kTailIpt + i, st[i], (C)(st[i] + L[i]), label[i], sign);
         }
@@ -501,7 +513,7 @@ k_cutoff_tail(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__
     }
     __syncthreads();
     for (int i = tid; i < B + 2; i += kTailBlock)
-        if (s_hist[i]) out.label_counts[(i64)it * (B + 2) + i] += s_hist[i];
+        if (s_hist[i]) out.label_counts[(i64)it * (B + 2) + i] += (u64)(i64)s_hist[i];
     if (tid == 0) {
         out.n_bases[it] = bulk_sum + (u64)d_bases;
         out.n_reads[it] += (u64)d_reads;

@@ -190,13 +190,15 @@ static int blocked_test(eslo_rng *st, int barcode, int64_t rs, int64_t re, int64
  *   labels   : barcode k >= 0, -1 = "Blocked/Consuming", -2 = "Blocked/NotConsuming"
  * Records every draw up to and including the cut-off read (n_placed), then keeps drawing n_extra more
  * reads from the same stream (an oversampled tail for replay tests; NOT part of the reference's result
- * and not added to covered).  Optional outputs may be NULL.  ublock_off has cap+1 entries.
+ * and not added to covered; it stops early if a picked length is not shorter than the genome).
+ * Optional outputs may be NULL.  ublock_off has cap+1 entries.
  * Returns 0, -1 if cap is too small, -2 if a read is not shorter than the genome (numpy raises there). */
 int eslo_place(eslo_rng *st, int64_t G, double coverage, const int64_t *pool, int64_t npool, int n_barcodes,
                const double *cdf, int consuming, int64_t K, const int64_t *ms, const int64_t *me,
                const double *mw, const int32_t *mb, int64_t cap, int64_t n_extra, int64_t *start,
                int64_t *length, int32_t *label, double *u_barcode, int64_t *ublock_off, double *ublock,
-               int64_t ublock_cap, int64_t *covered_out, int64_t *n_placed_out, int64_t *n_ublock_out)
+               int64_t ublock_cap, int64_t *covered_out, int64_t *n_placed_out, int64_t *n_ublock_out,
+               int64_t *n_total_out)
 {
     const double thr = coverage * (double)G; /* `covered_length < coverage * genome_size`, :100 */
     int64_t covered = 0, n = 0, n_ublock = 0, placed = -1;
@@ -209,7 +211,10 @@ int eslo_place(eslo_rng *st, int64_t G, double coverage, const int64_t *pool, in
         while (k < n_barcodes && cdf[k] <= u) k++; /* searchsorted(cdf, u, side='right') */
         if (k >= n_barcodes) k = n_barcodes - 1;
         int64_t L = pool[eslo_bounded(st, (uint64_t)(npool - 1))]; /* :102 */
-        if (G - L <= 0) return -2;
+        if (G - L <= 0) {
+            if (placed >= 0) break; /* oversampled tail only: stop early instead of raising */
+            return -2;
+        }
         int64_t s = (int64_t)eslo_bounded(st, (uint64_t)(G - L - 1)); /* :103 */
         if (ublock_off) ublock_off[n] = n_ublock;
         int blocked = K > 0 ? blocked_test(st, k, s, s + L, K, ms, me, mw, mb, ublock, &n_ublock, ublock_cap) : 0;
@@ -233,6 +238,7 @@ int eslo_place(eslo_rng *st, int64_t G, double coverage, const int64_t *pool, in
     *covered_out = covered;
     *n_placed_out = placed;
     if (n_ublock_out) *n_ublock_out = n_ublock;
+    if (n_total_out) *n_total_out = n; /* placed + extras actually drawn */
     return 0;
 }
 

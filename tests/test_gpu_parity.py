@@ -91,13 +91,20 @@ def test_replay_draws_bit_exact(eng, name, bulk_mode):
     g = Golden(name)
     configure(eng, g)
     m = g.meta
-    rng = O.Rng(m["seed"])
     tb = O.target_barcodes(m["target_keys"], m["n_barcodes"])
+
+    def oracle_combo(rng, ci, **kw):
+        mrl, cov = m["combinations"][ci]
+        return O.process_combination(rng, mrl, cov, m["genome_size"], g["target_start"], g["target_end"], tb,
+                                     m["n_barcodes"], m["barcode_weights"], m["consuming"], g.mask, m["sigma"],
+                                     m["min_read_length"], m["scaling"], m["min_overlap"],
+                                     source_lengths=g.source_lengths, **kw)
+
     for ci, (mrl, cov) in enumerate(m["combinations"]):
-        out = O.process_combination(rng, mrl, cov, m["genome_size"], g["target_start"], g["target_end"], tb,
-                                    m["n_barcodes"], m["barcode_weights"], m["consuming"], g.mask, m["sigma"],
-                                    m["min_read_length"], m["scaling"], m["min_overlap"],
-                                    source_lengths=g.source_lengths, n_extra=3000, record_draws=True)
+        rng = O.Rng(m["seed"])
+        for prev in range(ci):  # earlier combinations advance the shared stream exactly as in the reference
+            oracle_combo(rng, prev)
+        out = oracle_combo(rng, ci, n_extra=3000, record_draws=True)
         pl = out["placement"]
         n_placed = pl["n_placed"]
         assert n_placed == g.combo(ci, "read_start").size
