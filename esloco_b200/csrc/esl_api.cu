@@ -70,7 +70,7 @@ struct esl_ctx {
     uint32_t n_pool = 0, pool_max = 0;
     double pool_mean = 0, pool_sd = 0;
 
-    DevBuf d_pool, d_cdf, d_cdf_u32, d_ts, d_te, d_trow, d_seg_off, d_bc_seg, d_ms, d_me, d_mpmax, d_mw, d_grp_off;
+    DevBuf d_pool, d_cdf, d_cdf_u32, d_ts, d_te, d_trow, d_seg, d_tgrid, d_bc_seg, d_ms, d_me, d_mpmax, d_mw, d_grp, d_mgrid;
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
 
     // optional per-kernel timing (esl_set_profiling): events around the bulk and the cut-off kernel
@@ -126,6 +126,28 @@ void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers)
 
 template <typename C> C clampc(i64 v, u64 G) { return (C)((u64)v > G + 1 ? G + 1 : (u64)v); }
 
+// Bucket grid over one sorted run: keys[lo..hi) ascending (target ends of a layer, or the running max of
+// blocked-interval ends).  About 4 buckets per interval (at least 64, at most 2^22), so a bucket rarely holds
+// more than one candidate.  Appends to `grid` and returns the descriptor.
+template <typename C>
+esl::SegDesc make_grid(const std::vector<C> &keys, int lo, int hi, u64 G, std::vector<int32_t> &grid)
+{
+    esl::SegDesc d;
+    d.lo = lo; d.hi = hi; d.grid_off = (int)grid.size();
+    const u64 want = std::min<u64>(std::max<u64>(64, 4ull * (u64)(hi - lo)), 1ull << 22);
+    int shift = 0;
+    while (((G + 1) >> shift) + 2 > want) ++shift;
+    d.shift = shift;
+    const u64 nb = ((G + 1) >> shift) + 2; // reads start below G, so bucket index <= G >> shift; +1 for the upper bound
+    int j = lo;
+    for (u64 b = 0; b < nb; ++b) {
+        const u64 edge = b << shift;
+        while (j < hi && (u64)keys[j] <= edge) ++j; // first key > bucket start
+        grid.push_back(j);
+    }
+    return d;
+}
+
 template <typename C>
 int upload_index(esl_ctx *ctx)
 {
@@ -133,7 +155,8 @@ int upload_index(esl_ctx *ctx)
     const u64 G = ctx->G;
     // targets
     std::vector<C> ts, te;
-    std::vector<int32_t> trow, seg_off(1, 0), bc_seg(B + 1, 0);
+    std::vector<int32_t> trow, bc_seg(B + 1, 0), tgrid;
+    std::vector<esl::SegDesc> seg;
     ctx->n_layers = 0;
     for (int b = 0; b < B; ++b) {
         std::vector<Rec> v;
@@ -142,22 +165,25 @@ int upload_index(esl_ctx *ctx)
         std::vector<std::vector<Rec>> layers;
         build_layers(v, layers);
         for (auto &ly : layers) {
+            const int lo = (int)ts.size();
             for (const Rec &r : ly) { ts.push_back(clampc<C>(r.s, G)); te.push_back(clampc<C>(r.e, G)); trow.push_back(r.row); }
-            seg_off.push_back((int32_t)ts.size());
+            seg.push_back(make_grid<C>(te, lo, (int)ts.size(), G, tgrid));
         }
         ctx->n_layers += (int)layers.size();
-        bc_seg[b + 1] = (int32_t)seg_off.size() - 1;
+        bc_seg[b + 1] = (int32_t)seg.size();
     }
     ctx->n_indexed = (i64)ts.size();
     CU(ctx->d_ts.upload(ts.data(), ts.size() * sizeof(C)));
     CU(ctx->d_te.upload(te.data(), te.size() * sizeof(C)));
     CU(ctx->d_trow.upload(trow.data(), trow.size() * sizeof(int32_t)));
-    CU(ctx->d_seg_off.upload(seg_off.data(), seg_off.size() * sizeof(int32_t)));
+    CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc)));
+    CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(int32_t)));
     CU(ctx->d_bc_seg.upload(bc_seg.data(), bc_seg.size() * sizeof(int32_t)));
     // blocked intervals: group g < B = barcode g, group B = "ALL"; (start, end) order, running max of ends
     std::vector<C> ms, me, mp;
     std::vector<double> mw;
-    std::vector<int32_t> grp_off(B + 2, 0);
+    std::vector<esl::SegDesc> grp;
+    std::vector<int32_t> mgrid;
     for (int g = 0; g <= B; ++g) {
         const int want = g < B ? g : -1;
         std::vector<size_t> idx;
@@ -168,19 +194,22 @@ int upload_index(esl_ctx *ctx)
             return ctx->m_end[a] < ctx->m_end[b2];
         });
         C run = 0;
+        const int glo = (int)ms.size();
         for (size_t i : idx) {
             const C s = clampc<C>(std::max<i64>(ctx->m_start[i], 0), G), e = clampc<C>(std::max<i64>(ctx->m_end[i], 0), G);
             run = std::max(run, e);
             ms.push_back(s); me.push_back(e); mp.push_back(run); mw.push_back(ctx->m_w[i]);
         }
-        grp_off[g + 1] = (int32_t)ms.size();
+        if ((int)ms.size() == glo) grp.push_back(esl::SegDesc{glo, glo, 0, 0}); // empty group: never dereferenced
+        else grp.push_back(make_grid<C>(mp, glo, (int)ms.size(), G, mgrid));
     }
     ctx->n_mask = (i64)ms.size();
     CU(ctx->d_ms.upload(ms.data(), ms.size() * sizeof(C)));
     CU(ctx->d_me.upload(me.data(), me.size() * sizeof(C)));
     CU(ctx->d_mpmax.upload(mp.data(), mp.size() * sizeof(C)));
     CU(ctx->d_mw.upload(mw.data(), mw.size() * sizeof(double)));
-    CU(ctx->d_grp_off.upload(grp_off.data(), grp_off.size() * sizeof(int32_t)));
+    CU(ctx->d_grp.upload(grp.data(), grp.size() * sizeof(esl::SegDesc)));
+    CU(ctx->d_mgrid.upload(mgrid.data(), mgrid.size() * sizeof(int32_t)));
     // barcode cdf
     std::vector<uint32_t> cu(B);
     for (int k = 0; k < B; ++k) {
@@ -228,14 +257,16 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.ts = ctx->d_ts.as<C>();
     d.te = ctx->d_te.as<C>();
     d.trow = ctx->d_trow.as<int32_t>();
-    d.seg_off = ctx->d_seg_off.as<int32_t>();
+    d.seg = ctx->d_seg.as<esl::SegDesc>();
+    d.tgrid = ctx->d_tgrid.as<int32_t>();
     d.bc_seg = ctx->d_bc_seg.as<int32_t>();
     d.n_targets = (i64)ctx->t_start.size();
     d.ms = ctx->d_ms.as<C>();
     d.me = ctx->d_me.as<C>();
     d.mpmax = ctx->d_mpmax.as<C>();
     d.mw = ctx->d_mw.as<double>();
-    d.grp_off = ctx->d_grp_off.as<int32_t>();
+    d.grp = ctx->d_grp.as<esl::SegDesc>();
+    d.mgrid = ctx->d_mgrid.as<int32_t>();
     return d;
 }
 

@@ -39,6 +39,22 @@ constexpr int kMaxBarcodes = 4096;
 constexpr int kLabelBlockedConsuming = -1;
 constexpr int kLabelBlockedNotConsuming = -2;
 
+// One sorted run of intervals plus its bucket grid.  grid[grid_off + b], b = position >> shift, is the first
+// index j of the run whose (running-max) end exceeds b << shift; so for a read starting at rs the first
+// overlapping candidate lies in [grid[b], grid[b+1]] -- usually an empty or one-element range, which turns the
+// O(log n) search into two adjacent loads.
+struct __align__(16) SegDesc {
+    int lo, hi;   // index range of the run
+    int grid_off; // offset of the run's grid
+    int shift;    // log2 of the bucket width
+};
+
+__device__ __forceinline__ SegDesc load_desc(const SegDesc *p)
+{
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(p)); // one LDG.128 through the read-only path
+    return SegDesc{v.x, v.y, v.z, v.w};
+}
+
 // Everything a kernel needs to resolve one read; passed by value.
 template <typename C>
 struct DevCtx {
@@ -58,7 +74,8 @@ struct DevCtx {
     const C *__restrict__ ts;
     const C *__restrict__ te;
     const int32_t *__restrict__ trow;    // original row of the sorted target
-    const int32_t *__restrict__ seg_off; // [n_seg + 1]
+    const SegDesc *__restrict__ seg;     // [n_seg] one descriptor per layer
+    const int32_t *__restrict__ tgrid;   // bucket grids of all layers
     const int32_t *__restrict__ bc_seg;  // [B + 1] layers of barcode b: bc_seg[b] .. bc_seg[b+1]
     i64 n_targets;
     // blocked index: group g < B is barcode g's tree, group B is "ALL"; inside a group sorted by
@@ -67,7 +84,8 @@ struct DevCtx {
     const C *__restrict__ me;
     const C *__restrict__ mpmax;
     const double *__restrict__ mw;
-    const int32_t *__restrict__ grp_off; // [B + 2]
+    const SegDesc *__restrict__ grp;     // [B + 1] one descriptor per group
+    const int32_t *__restrict__ mgrid;   // bucket grids of all groups (on the running max of ends)
 };
 
 struct DevOut {
@@ -188,10 +206,11 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
     int j = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        const int g = pass == 0 ? bc : cx.n_barcodes;
-        const int lo = __ldg(cx.grp_off + g), hi = __ldg(cx.grp_off + g + 1);
-        if (lo == hi) continue;
-        int a = lo, z = hi; // first interval whose running max of ends exceeds rs
+        const SegDesc d = load_desc(cx.grp + (pass == 0 ? bc : cx.n_barcodes));
+        const int hi = d.hi;
+        if (d.lo == hi) continue;
+        const int32_t *gp = cx.mgrid + d.grid_off + (int)(rs >> d.shift);
+        int a = __ldg(gp), z = __ldg(gp + 1); // first interval whose running max of ends exceeds rs
         while (a < z) {
             const int mid = (a + z) >> 1;
             if (__ldg(cx.mpmax + mid) <= rs) a = mid + 1; else z = mid;
@@ -215,8 +234,10 @@ __device__ __forceinline__ void tally_read(const DevCtx<C> &cx, const Src &src, 
     const int s0 = __ldg(cx.bc_seg + bc), s1 = __ldg(cx.bc_seg + bc + 1);
 #pragma unroll 1
     for (int sg = s0; sg < s1; ++sg) {
-        const int lo = __ldg(cx.seg_off + sg), hi = __ldg(cx.seg_off + sg + 1);
-        int a = lo, z = hi; // first target of the layer with end > rs (ends ascend inside a layer)
+        const SegDesc d = load_desc(cx.seg + sg);
+        const int hi = d.hi;
+        const int32_t *gp = cx.tgrid + d.grid_off + (int)(rs >> d.shift);
+        int a = __ldg(gp), z = __ldg(gp + 1); // first target of the layer with end > rs (ends ascend inside a layer)
         while (a < z) {
             const int mid = (a + z) >> 1;
             if (__ldg(cx.te + mid) <= rs) a = mid + 1; else z = mid;
