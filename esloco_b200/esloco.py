@@ -1,0 +1,176 @@
+#!/usr/bin/env python3
+"""`esloco --config <ini>` drop-in (mirrors src/esloco/esloco.py): same CLI, INI schema and output tables; the
+Monte-Carlo iterations run on the B200 engine.  Launch under torchrun to shard iterations over several GPUs."""
+import logging
+import os
+import sys
+import time
+
+import numpy as np
+
+from .bed_operations import global_to_chromosome_coordinates
+from .config_handler import parse_config
+from .genome_generation import create_barcoded_insertion_genome, create_barcoded_roi_genome
+from .utils import build_mask_tree
+
+BANNER = r"""
+             __
+  ___  _____/ /___  _________
+ / _ \/ ___/ / __ \/ ___/ __ \     b200
+/  __(__  ) / /_/ / /__/ /_/ /
+\___/____/_/\____/\___/\____/
+"""
+
+
+def print_help():
+    print("")
+    print("Usage: ")
+    print("         esloco --config <config_file>")
+    print("")
+    print("Run a simulation for local coverage estimation.")
+    print("")
+    print("Options:")
+    print("     --config  <config_file>    Path to the configuration file.")
+    print("     --help                     Show this help message.")
+    print("")
+    sys.exit(0)
+
+
+def setup_logging(filename):
+    root = logging.getLogger()
+    for handler in root.handlers[:]:
+        root.removeHandler(handler)
+    logging.basicConfig(filename=filename, level=logging.INFO, format="%(asctime)s - %(levelname)s - %(message)s", filemode="a")
+
+
+def iteration_chunks(iterations, n_targets, n_combos, budget_bytes=2 << 30):
+    """Split a range of iterations into batches whose tallies fit a device-memory budget."""
+    per_iter = max(1, n_targets * 24 * n_combos)
+    step = max(1, min(len(iterations), budget_bytes // per_iter))
+    for i in range(0, len(iterations), step):
+        yield iterations[i:i + step]
+
+
+def run(param_dictionary):
+    """Everything after config parsing; returns the three DataFrames on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    from .combined_calculations import run_simulation_batch
+    from .distributed import gather_iterations, reduce_moments, shard_iterations, world
+    from .session import get_session
+    from .tables import barcode_distribution_table, matches_table, summary_table, write_tables
+
+    p = param_dictionary
+    rank, ws, local = world()
+    if ws > 1 and not dist.is_initialized():
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode, output_path, experiment_name = p["mode"], p["output_path"], p["experiment_name"]
+    log_file = os.path.join(output_path, f"{experiment_name}_log.log")
+    setup_logging(log_file)
+    logging.info(f"Starting simulation: {experiment_name}")
+    logging.info(f"Running in mode: {mode}")
+    start_time = time.time()
+    np.random.seed(p["seed"])  # host set-up (insertion sites) draws from numpy's stream like the reference (esloco.py:100)
+    logging.info(f"Seed for reproducibility: {p['seed']}")
+    insertion_bed = None
+    if mode == "I":
+        genome_size, target_regions, masked_regions, chromosome_dir = create_barcoded_insertion_genome(
+            p["parallel_jobs"], p["reference_genome_path"], p["bedpath"], p["blocked_regions_bedpath"], p["chr_restriction"],
+            p["insertion_length"], p["insertion_numbers"], p["insertion_number_distribution"], p["n_barcodes"], log_file)
+        logging.info(f"Number of insertions: {len(target_regions)}")
+        insertion_bed = global_to_chromosome_coordinates(chromosome_dir, target_regions)
+    elif mode == "ROI":
+        target_regions, bed, masked_regions, genome_size, chromosome_dir = create_barcoded_roi_genome(
+            p["reference_genome_path"], p["chr_restriction"], p["roi_bedpath"], p["n_barcodes"], p["blocked_regions_bedpath"])
+        logging.info(f"Chromosome borders: {chromosome_dir}")
+    else:
+        logging.error("Error: Invalid mode selected.")
+        sys.exit(1)
+    masked_tree = build_mask_tree(masked_regions) if masked_regions else masked_regions
+    if not p["no_cov_plots"]:
+        logging.info("Coverage plots are produced by the reference's plotting layer and are not part of this engine.")
+
+    combos = p["combinations"]
+    mine = shard_iterations(p["iterations"], rank, ws)
+    sess = get_session(local)
+    n_targets = len(target_regions)
+    moments = [None] * len(combos)
+    tallies = [[] for _ in combos]; labels = [[] for _ in combos]; nbases = [[] for _ in combos]
+    t_gpu = time.time()
+    for chunk in iteration_chunks(mine, n_targets, len(combos)) if len(mine) else []:
+        batches, keys = run_simulation_batch(chunk, p, genome_size, target_regions, masked_tree, device=local, to_host=False)
+        for c, res in enumerate(batches):
+            if (res.status & 2).any().item():
+                raise RuntimeError("coverage not reached")
+            moments[c] = sess.engine.moments(res.tallies, moments[c])
+            tallies[c].append(res.tallies); labels[c].append(res.label_counts); nbases[c].append(res.n_bases)
+    if not len(mine):  # a rank without iterations still takes part in the collectives
+        sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"])
+        keys = sess.keys
+        dev = torch.device("cuda", local)
+        for c in range(len(combos)):
+            tallies[c].append(torch.zeros((0, n_targets, 3), dtype=torch.int64, device=dev))
+            labels[c].append(torch.zeros((0, p["n_barcodes"] + 2), dtype=torch.int64, device=dev))
+            nbases[c].append(torch.zeros((0,), dtype=torch.int64, device=dev))
+    for c in range(len(combos)):
+        if moments[c] is None:
+            moments[c] = torch.zeros((n_targets, 8), dtype=torch.int64, device=torch.device("cuda", local))
+        reduce_moments(moments[c])  # the one collective of the data path
+        tallies[c] = gather_iterations(torch.cat(tallies[c]), p["iterations"])
+        labels[c] = gather_iterations(torch.cat(labels[c]), p["iterations"])
+        nbases[c] = gather_iterations(torch.cat(nbases[c]), p["iterations"])
+    torch.cuda.synchronize()
+    logging.info(f"GPU iterations: {time.time() - t_gpu:.2f} seconds on {ws} GPU(s).")
+    out = None
+    if rank == 0:
+        its = list(range(p["iterations"]))
+        matches = matches_table(keys, mode, combos, its, [t.cpu().numpy() for t in tallies])
+        dist_df = barcode_distribution_table(p["n_barcodes"], combos, its, [x.cpu().numpy() for x in labels],
+                                             [x.cpu().numpy() for x in nbases])
+        summary = summary_table(keys, mode, combos, [m.cpu().numpy() for m in moments])
+        try:
+            write_tables(output_path, experiment_name, matches, dist_df, summary, insertion_bed if mode == "I" else None)
+            if mode == "I":
+                logging.info("Insertion locations saved.")
+        except Exception as e:
+            logging.error(f"Error writing output files: {e}")
+        logging.info("Simulation Parameters:")
+        for param, value in p.items():
+            logging.info(f"{param} = {value} ({type(value)})")
+        logging.info(f"Total execution time: {time.time() - start_time:.2f} seconds.")
+        logging.info("Simulation complete!")
+        out = (matches, dist_df, summary)
+    if ws > 1:
+        dist.barrier()
+    return out
+
+
+def main():
+    print(BANNER)
+    if len(sys.argv) != 3 or sys.argv[1] == "--help" or sys.argv[1] != "--config":
+        print_help()
+        sys.exit(1)
+    config_file = sys.argv[2]
+    if not os.path.exists(config_file):
+        print(f"Configuration file '{config_file}' does not exist.")
+        sys.exit(1)
+    print("Checking config...")
+    try:
+        param_dictionary = parse_config(config_file)
+    except Exception as e:
+        print(f"Error parsing config: {e}")
+        sys.exit(1)
+    print(f"Starting simulation: {param_dictionary.get('experiment_name')}")
+    print(f"Running in mode: {param_dictionary.get('mode')}")
+    run(param_dictionary)
+    print("Simulation complete!")
+    sys.exit()
+
+
+if __name__ == "__main__":
+    try:
+        main()
+    except ValueError as e:
+        print("Configuration error:", e)
+        sys.exit(1)

@@ -1,0 +1,116 @@
+"""Result assembly and table writing (mirrors src/esloco/esloco.py:155-216) -- SURVEY.md section 8(f) row 1.
+
+The reference builds one Python dict per (iteration, target) and splits strings per row with pandas; here the
+per-target name columns are derived once from the T keys and tiled over iterations, and the summary comes from the
+per-target moment accumulators (device kernel + NCCL reduce) instead of a groupby over all rows."""
+import numpy as np
+import pandas as pd
+
+from .counting import LABELS_BLOCKED
+from .distributed import summary_from_moments
+
+
+def split_target_keys(keys, mode):
+    """target / barcode / insertion columns from the target keys, exactly the rsplit logic of esloco.py:165-177
+    applied to "<key>_<iteration>"."""
+    cols = {"target": [], "barcode": []}
+    if mode != "ROI":
+        cols["insertion"] = []
+    for k in keys:
+        if mode == "ROI":  # {ROI}_{barcode}[_{iteration}]
+            parts = k.rsplit("_", 1)
+            cols["target"].append(parts[0]); cols["barcode"].append(parts[1] if len(parts) > 1 else None)
+        else:  # Barcode_{b}_insertion_{i}[_{iteration}]: rsplit n=4 on key+iteration == rsplit n=3 on key
+            parts = k.rsplit("_", 3)
+            parts = [None] * (4 - len(parts)) + parts
+            cols["target"].append("_".join(str(p) for p in parts))
+            cols["barcode"].append(parts[1])
+            cols["insertion"].append(f"{parts[2]}_{parts[3]}")
+    return cols
+
+
+def matches_table(keys, mode, combos, iteration_ids, tallies_per_combo, overlaps=None):
+    """DataFrame of `{exp}_matches_table.csv`: rows ordered iteration -> combination -> target (esloco.py:155-160).
+    tallies_per_combo[c] is an int64 array [n_iter, T, 3]."""
+    T, n_iter, n_combo = len(keys), len(iteration_ids), len(combos)
+    kcols = split_target_keys(keys, mode)
+    keys_arr = np.array(keys, dtype=object)
+    blocks = np.stack([np.asarray(t) for t in tallies_per_combo], axis=1)  # [n_iter, n_combo, T, 3]
+    flat = blocks.reshape(n_iter * n_combo * T, 3)
+    it_col = np.repeat(np.array([str(i) for i in iteration_ids], dtype=object), n_combo * T)
+    df = pd.DataFrame({"target_region": np.tile(keys_arr, n_iter * n_combo) + "_" + it_col,
+                       "full_matches": flat[:, 0], "partial_matches": flat[:, 1]})
+    if overlaps is None:
+        df["overlap"] = [[] for _ in range(len(df))]
+    else:
+        df["overlap"] = overlaps
+    df["on_target_bases"] = flat[:, 2]
+    df["mean_read_length"] = np.tile(np.repeat(np.array([c[0] for c in combos], dtype=object), T), n_iter)
+    df["coverage"] = np.tile(np.repeat(np.array([c[1] for c in combos], dtype=object), T), n_iter)
+    for name, vals in kcols.items():
+        df[name] = np.tile(np.array(vals, dtype=object), n_iter * n_combo)
+    df["iteration"] = it_col
+    return df
+
+
+def barcode_distribution_table(n_barcodes, combos, iteration_ids, label_counts_per_combo, n_bases_per_combo):
+    """DataFrame of `{exp}_barcode_distribution_table.csv` (esloco.py:161-180): one row per (iteration,
+    combination); label columns, coverage, mean_read_length, iteration, N_bases, total_Reads.  All barcode columns
+    are always present (the reference drops barcodes without reads, which shifts its total_Reads sum onto other
+    columns); blocked columns appear only when such reads exist."""
+    rows = []
+    lc = [np.asarray(x) for x in label_counts_per_combo]
+    any_blocked = [any(x[:, n_barcodes + j].any() for x in lc) for j in range(2)]
+    for i, it in enumerate(iteration_ids):
+        for c, (mrl, cov) in enumerate(combos):
+            row = {str(k): int(lc[c][i, k]) for k in range(n_barcodes)}
+            for j, name in enumerate(LABELS_BLOCKED):
+                if any_blocked[j]:
+                    row[name] = int(lc[c][i, n_barcodes + j])
+            row.update(coverage=cov, mean_read_length=mrl, iteration=it, N_bases=int(np.asarray(n_bases_per_combo[c])[i]))
+            rows.append(row)
+    df = pd.DataFrame(rows)
+    df["total_Reads"] = df.iloc[:, :n_barcodes].sum(axis=1)
+    return df
+
+
+def summary_table(keys, mode, combos, moments_per_combo):
+    """DataFrame of `{exp}_summary.csv` from per-target moment accumulators [T, 8] per combination
+    (esloco.py:183-195): groups are (target, mean_read_length, coverage), sorted like pandas groupby; in ROI mode a
+    target's rows of all barcodes fall into one group, so their accumulators are added."""
+    names = split_target_keys(keys, mode)["target"]
+    frames = []
+    for (mrl, cov), mom in zip(combos, moments_per_combo):
+        mom = np.asarray(mom).astype(object)
+        order, index = [], {}
+        for i, nm in enumerate(names):
+            if nm not in index:
+                index[nm] = len(order); order.append(nm)
+        grouped = np.zeros((len(order), 8), dtype=object)
+        for i, nm in enumerate(names):
+            grouped[index[nm]] += mom[i]
+        lo_hi = grouped[:, 7] * (1 << 32) + grouped[:, 6]  # re-normalise the split square sum after adding rows
+        grouped[:, 6] = [int(x) & 0xFFFFFFFF for x in lo_hi]
+        grouped[:, 7] = [int(x) >> 32 for x in lo_hi]
+        cols = summary_from_moments(grouped)
+        df = pd.DataFrame({"target": order, "mean_read_length": mrl, "coverage": cov})
+        for k in ("mean_full_matches", "sd_full_matches", "mean_partial_matches", "sd_partial_matches",
+                  "mean_bases_on_target", "sd_bases_on_target", "sem_bases_on_target",
+                  "ci_lower_bases_on_target", "ci_upper_bases_on_target"):
+            df[k] = cols[k]
+        frames.append(df)
+    out = pd.concat(frames, ignore_index=True)
+    return out.sort_values(["target", "mean_read_length", "coverage"], kind="stable").reset_index(drop=True)
+
+
+def write_tables(output_path, experiment_name, matches=None, barcode_distribution=None, summary=None, insertion_bed=None):
+    """Tab-separated, header, no index (esloco.py:198-216)."""
+    base = f"{output_path}{experiment_name}"
+    if insertion_bed is not None:
+        insertion_bed.to_csv(f"{base}_insertion_locations.bed", sep="\t", header=True, index=False)
+    if barcode_distribution is not None:
+        barcode_distribution.to_csv(f"{base}_barcode_distribution_table.csv", sep="\t", header=True, index=False)
+    if matches is not None:
+        matches.to_csv(f"{base}_matches_table.csv", sep="\t", header=True, index=False)
+    if summary is not None:
+        summary.to_csv(f"{base}_summary.csv", sep="\t", header=True, index=False)

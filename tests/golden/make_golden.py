@@ -330,7 +330,8 @@ def main():
             min_overlap=case["min_overlap"], seed=case["seed"], setup_seed=case.get("setup_seed"),
             iteration=case["iteration"], insertion_length=case.get("insertion_length"),
             insertion_numbers=case.get("insertion_numbers"), contigs=case.get("contigs"),
-            combos=[])
+            roi_rows=case.get("roi_rows"), blocked_rows=case.get("blocked_rows"),
+            blocked_header=case.get("blocked_header"), combos=[])
         for ci, c in enumerate(combos):
             meta["combos"].append(dict(covered_length=c["covered_length"], label_order=c["label_order"],
                                        target_region=c["target_region"], pool_len=c["pool_len"],

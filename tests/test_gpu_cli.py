@@ -1,0 +1,116 @@
+"""End-to-end drop-in check on the GPU: `esloco --config` writes the reference's tables (format pinned by
+tests/golden/cli_format.json, recorded from the unmodified reference CLI) and run_simulation_iteration keeps the
+reference's return shape."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from test_host_setup import write_bed, write_fasta
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+CONTIGS = [("chr1", 300_000), ("chr2", 200_000), ("chrX", 100_000), ("chr1_alt", 50_000), ("chrM", 16_000)]
+
+
+def make_config(tmp, mode):
+    fmt = json.load(open(os.path.join(HERE, "golden", "cli_format.json")))[mode]
+    fasta = os.path.join(tmp, "ref.fa"); write_fasta(fasta, CONTIGS)
+    write_bed(os.path.join(tmp, "blocked.bed"), ["chrom", "start", "end", "id", "barcode", "weight"], [("chr2", 1000, 90_000, "b1", "[]", 1)])
+    write_bed(os.path.join(tmp, "roi.bed"), ["chrom", "start", "end", "id"],
+              [("chr1", 1000, 5000, "RA"), ("chrX", 0, 0, "RX"), ("chr2", 100_000, 120_000, "RB")])
+    os.makedirs(os.path.join(tmp, "out_" + mode), exist_ok=True)
+    ini = os.path.join(tmp, mode + ".ini")
+    open(ini, "w").write(fmt["ini"].replace("{tmp}", tmp))
+    return ini, fmt
+
+
+@pytest.mark.parametrize("mode", ["ROI", "I"])
+def test_cli_tables_have_reference_format(tmp_path, mode):
+    from esloco_b200.config_handler import parse_config
+    from esloco_b200.esloco import run
+    tmp = str(tmp_path)
+    ini, fmt = make_config(tmp, mode)
+    p = parse_config(ini)
+    run(p)
+    out = os.path.join(tmp, "out_" + mode)
+    m = pd.read_csv(os.path.join(out, f"exp{mode}_matches_table.csv"), sep="\t", dtype=str)
+    ref = fmt["matches_table.csv"]
+    assert list(m.columns) == ref["columns"] and len(m) == ref["rows"]
+    cols = ("target_region", "target", "barcode", "iteration", "mean_read_length", "coverage") + (("insertion",) if mode == "I" else ())
+    for c in cols:
+        assert m[c].tolist() == ref[c], c
+    s = pd.read_csv(os.path.join(out, f"exp{mode}_summary.csv"), sep="\t", dtype=str)
+    refs = fmt["summary.csv"]
+    assert list(s.columns) == refs["columns"] and len(s) == refs["rows"]
+    for c in ("target", "mean_read_length", "coverage"):
+        assert s[c].tolist() == refs[c], c
+    d = pd.read_csv(os.path.join(out, f"exp{mode}_barcode_distribution_table.csv"), sep="\t")
+    refd = fmt["barcode_distribution_table.csv"]
+    assert set(d.columns) == set(refd["columns"]) and len(d) == refd["rows"]  # label columns: barcode order here
+    assert list(d.columns)[-5:] == refd["columns"][-5:]
+    for c in ("coverage", "mean_read_length", "iteration"):
+        assert d[c].astype(str).tolist() == refd[c], c
+    G = 600_000
+    assert (d["N_bases"] >= d["coverage"] * G).all()
+    assert (d["total_Reads"] == d["0"] + d["1"]).all()
+    assert (d["Blocked/NotConsuming"] > 0).all()
+    share0 = d["0"].sum() / d["total_Reads"].sum()  # barcode_weights {"0": 3} -> 3/4 of the unblocked reads
+    assert abs(share0 - 0.75) < 0.05
+    # the summary agrees with a groupby over the matches table (what the reference computes)
+    mm = pd.read_csv(os.path.join(out, f"exp{mode}_matches_table.csv"), sep="\t")
+    g = mm.groupby(["target", "mean_read_length", "coverage"], as_index=False).agg(
+        mean_bases_on_target=("on_target_bases", "mean"), sd_bases_on_target=("on_target_bases", "std"),
+        mean_full_matches=("full_matches", "mean"), sd_partial_matches=("partial_matches", "std"))
+    ss = pd.read_csv(os.path.join(out, f"exp{mode}_summary.csv"), sep="\t")
+    for c in ("mean_bases_on_target", "sd_bases_on_target", "mean_full_matches", "sd_partial_matches"):
+        assert np.allclose(ss[c], g[c], rtol=1e-9, equal_nan=True), c
+    if mode == "I":
+        b = pd.read_csv(os.path.join(out, "expI_insertion_locations.bed"), sep="\t")
+        assert list(b.columns) == fmt["insertion_locations.bed"]["columns"]
+    assert os.path.exists(os.path.join(out, f"exp{mode}_log.log"))
+
+
+def test_run_simulation_iteration_shape_and_determinism(tmp_path):
+    from esloco_b200.combined_calculations import run_simulation_batch, run_simulation_iteration
+    from esloco_b200.synthetic import random_insertions
+    from esloco_b200.utils import build_mask_tree
+    G = 2_000_000
+    targets = random_insertions(G, 6, 2000, 2, seed=1)
+    tree = build_mask_tree({"m": {"start": 100_000, "end": 300_000, "weight": "0.5", "barcode": '["1"]'}})
+    p = dict(n_barcodes=2, barcode_weights={"1": 2}, seed=42, scaling=1.0, combinations=[(4000, 3), (8000, 1.5)],
+             sequenced_data_path=None, sigma=1, min_read_length=100, consuming=True, min_overlap_for_detection=50)
+    results, dists = run_simulation_iteration(5, p, G, targets, tree, None)
+    assert len(results) == 2 and len(dists) == 2
+    keys = list(targets)
+    for c, (mrl, cov) in enumerate(p["combinations"]):
+        assert [r["target_region"] for r in results[c]] == [k + "_5" for k in keys]
+        assert set(results[c][0]) == {"target_region", "full_matches", "partial_matches", "on_target_bases", "mean_read_length", "coverage"}
+        assert dists[c]["coverage"] == cov and dists[c]["mean_read_length"] == mrl and dists[c]["iteration"] == 5
+        assert dists[c]["N_bases"] >= cov * G
+        assert "Blocked/Consuming" in dists[c] and "0" in dists[c] and "1" in dists[c]
+    again, _ = run_simulation_iteration(5, p, G, targets, tree, None)
+    assert again == results  # seed + iteration id fix the result, whatever the call pattern
+    batch, _ = run_simulation_batch(range(4, 7), p, G, targets, tree)
+    assert [int(x) for x in batch[0].tallies[1, :, 2]] == [r["on_target_bases"] for r in results[0]]
+
+
+def test_count_matches_mirror(tmp_path):
+    from esloco_b200.counting import count_barcode_occurrences, count_matches
+    from golden_util import Golden
+    from oracle import oracle as O
+    g = Golden("dense_adversarial")
+    m = g.meta
+    targets = {k: {"start": int(s), "end": int(e)} for k, s, e in zip(m["target_keys"], g["target_start"], g["target_end"])}
+    names = {-1: "Blocked/Consuming", -2: "Blocked/NotConsuming"}
+    reads = {f"Read_{n}_{names.get(int(l), 'Barcode_%d' % l)}": (int(s), int(e)) for n, (s, e, l) in
+             enumerate(zip(g.combo(0, "read_start"), g.combo(0, "read_end"), g.combo(0, "read_label")))}
+    out = count_matches(targets, reads, 1.0, m["min_overlap"], genome_size=m["genome_size"], n_barcodes=m["n_barcodes"])
+    assert [d["target_region"] for d in out] == m["target_keys"]
+    assert [d["full_matches"] for d in out] == g.combo(0, "full").tolist()
+    assert [d["partial_matches"] for d in out] == g.combo(0, "partial").tolist()
+    assert [d["on_target_bases"] for d in out] == g.combo(0, "otb").tolist()
+    hist = count_barcode_occurrences(reads)
+    assert list(hist) == m["combos"][0]["label_order"] and list(hist.values()) == g.combo(0, "label_counts").tolist()

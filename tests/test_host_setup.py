@@ -1,0 +1,101 @@
+"""Host set-up (FASTA / BED / insertion generator / mask tree) against what the unmodified reference produced
+for the same files and numpy seed (golden fixtures)."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import Golden, case_names
+
+CASES = [c for c in case_names() if Golden(c).meta.get("contigs")]
+
+
+def write_fasta(path, contigs, width=70):
+    with open(path, "w") as fh:
+        for name, n in contigs:
+            fh.write(f">{name} some description\n")
+            line = "ACGT" * 25000
+            full, rest = divmod(n, len(line))
+            for _ in range(full):
+                fh.write(line + "\n")
+            if rest:
+                fh.write(line[:rest] + "\n")
+
+
+def write_bed(path, header, rows):
+    with open(path, "w") as fh:
+        if header:
+            fh.write("\t".join(header) + "\n")
+        for r in rows:
+            fh.write("\t".join(str(x) for x in r) + "\n")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_setup_matches_reference(name, tmp_path):
+    from esloco_b200.genome_generation import create_barcoded_insertion_genome, create_barcoded_roi_genome
+    from esloco_b200.utils import build_mask_tree, mask_tree_to_arrays, targets_to_arrays
+    g = Golden(name)
+    m = g.meta
+    fasta = str(tmp_path / "ref.fa")
+    write_fasta(fasta, m["contigs"])
+    blocked = None
+    if m.get("blocked_rows"):
+        blocked = str(tmp_path / "blocked.bed")
+        write_bed(blocked, m["blocked_header"], m["blocked_rows"])
+    np.random.seed(m["setup_seed"])
+    if m["mode"] == "I":
+        G, targets, masked, cdir = create_barcoded_insertion_genome(
+            1, fasta, None, blocked, None, m["insertion_length"], m["insertion_numbers"], None, m["n_barcodes"])
+    else:
+        roi = str(tmp_path / "roi.bed")
+        write_bed(roi, ["chrom", "start", "end", "id"], m["roi_rows"])
+        targets, _bed, masked, G, cdir = create_barcoded_roi_genome(fasta, None, roi, m["n_barcodes"], blocked)
+    assert G == m["genome_size"]
+    assert {k: list(v) for k, v in cdir.items()} == m["chromosome_dir"]
+    keys, ts, te, tb = targets_to_arrays(targets, m["n_barcodes"])
+    assert keys == m["target_keys"]
+    assert np.array_equal(ts, g["target_start"]) and np.array_equal(te, g["target_end"])
+    tree = build_mask_tree(masked) if masked else None
+    ms, me, mw, mb = mask_tree_to_arrays(tree, m["n_barcodes"])
+    order = np.lexsort((mb, me, ms)); gorder = np.lexsort((g["mask_barcode"], g["mask_end"], g["mask_start"]))
+    assert np.array_equal(ms[order], g["mask_start"][gorder]) and np.array_equal(me[order], g["mask_end"][gorder])
+    assert np.array_equal(mw[order], g["mask_weight"][gorder]) and np.array_equal(mb[order], g["mask_barcode"][gorder])
+
+
+def test_fasta_filters_and_unrestricted(tmp_path):
+    from esloco_b200.fasta_operations import pseudo_fasta_coordinates
+    p = str(tmp_path / "x.fa")
+    write_fasta(p, [("chr1", 1000), ("chr1_alt", 500), ("chrM", 300), ("chr2", 700)])
+    assert pseudo_fasta_coordinates(p) == (1700, {"chr1": [0, 1000], "chr2": [1000, 1700]})
+    total, d = pseudo_fasta_coordinates(p, "unrestricted")
+    assert total == 2500 and list(d) == ["chr1", "chr1-alt", "chrM", "chr2"]
+
+
+def test_seq_read_data(tmp_path):
+    from esloco_b200.config_handler import seq_read_data
+    fq = tmp_path / "r.fastq"
+    lens = [10, 250, 3000, 5, 777]
+    fq.write_text("".join(f"@r{i}\n{'A' * n}\n+\n{'I' * n}\n" for i, n in enumerate(lens)))
+    assert seq_read_data(str(fq), distribution=True, min_read_length=9).tolist() == [10, 250, 3000, 777]
+    assert seq_read_data(str(fq), min_read_length=0) == np.mean(lens)
+    fa = tmp_path / "r.fa"
+    fa.write_text(">a\nACGT\nAC\n>b\nA\n")
+    assert seq_read_data(str(fa), distribution=True).tolist() == [6, 1]
+    (tmp_path / "r.txt").write_text("x\n")
+    with pytest.raises(ValueError):
+        seq_read_data(str(tmp_path / "r.txt"))
+
+
+def test_weighted_probabilities_and_mask_keys():
+    from esloco_b200.read_operations import barcode_probabilities, get_weighted_probabilities
+    from esloco_b200.utils import build_mask_tree, mask_tree_to_arrays
+    from oracle import oracle as O
+    for B, w in [(4, {"0": 10}), (4, None), (3, {"1": 2}), (24, {"0": 10, "1": 5}), (2, {"Barcode": 3})]:
+        assert np.array_equal(barcode_probabilities(B, w), O.barcode_probabilities(B, w))
+    assert get_weighted_probabilities("Barcode_1", 4, {"0": 10}) == 4 / ((10 + 4 - 1) * 4)
+    tree = build_mask_tree({"a": {"start": 5, "end": 9, "weight": "0.5", "barcode": '["0","1"]'},
+                            "b": {"start": 1, "end": 2, "weight": 1, "barcode": []},
+                            "c": {"start": 3, "end": 4, "weight": 1, "barcode": [0]}})  # int key: unreachable in the reference
+    assert set(tree) == {"0", "1", "ALL", 0}
+    ms, me, mw, mb = mask_tree_to_arrays(tree, 2)
+    assert sorted(zip(ms, me, mw, mb)) == [(1, 2, 1.0, -1), (5, 9, 0.5, 0), (5, 9, 0.5, 1)]

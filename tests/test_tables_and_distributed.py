@@ -1,0 +1,132 @@
+"""Host-side result assembly and the multi-rank logic (gloo, world_size 2) -- no GPU needed."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fake_tallies(n_iter, T, seed, big=False):
+    r = np.random.RandomState(seed)
+    t = np.zeros((n_iter, T, 3), np.int64)
+    t[:, :, 0] = r.poisson(3, (n_iter, T)); t[:, :, 1] = r.poisson(5, (n_iter, T))
+    t[:, :, 2] = r.randint(0, 7_500_000_000 if big else 200_000, (n_iter, T))
+    return t
+
+
+def reference_style_tables(keys, mode, combos, its, tallies):
+    """What esloco.py:155-195 computes, written with the same pandas calls (rows -> DataFrame -> rsplit -> groupby)."""
+    rows = []
+    for i, it in enumerate(its):
+        for c, (mrl, cov) in enumerate(combos):
+            for j, k in enumerate(keys):
+                rows.append({"target_region": f"{k}_{it}", "full_matches": tallies[c][i, j, 0], "partial_matches": tallies[c][i, j, 1],
+                             "overlap": [], "on_target_bases": tallies[c][i, j, 2], "mean_read_length": mrl, "coverage": cov})
+    df = pd.DataFrame(rows)
+    if mode == "ROI":
+        df[["target", "barcode", "iteration"]] = df["target_region"].str.rsplit("_", n=2, expand=True)
+    else:
+        sp = df["target_region"].str.rsplit("_", n=4, expand=True)
+        df["target"] = sp.iloc[:, :4].agg("_".join, axis=1)
+        df["barcode"] = sp.iloc[:, 1]
+        df["insertion"] = sp.iloc[:, 2] + "_" + sp.iloc[:, 3]
+        df["iteration"] = sp.iloc[:, 4]
+    summ = df.groupby(["target", "mean_read_length", "coverage"], as_index=False).agg(
+        mean_full_matches=("full_matches", "mean"), sd_full_matches=("full_matches", "std"),
+        mean_partial_matches=("partial_matches", "mean"), sd_partial_matches=("partial_matches", "std"),
+        mean_bases_on_target=("on_target_bases", "mean"), sd_bases_on_target=("on_target_bases", "std"),
+        sem_bases_on_target=("on_target_bases", "sem"))
+    summ["ci_lower_bases_on_target"] = summ["mean_bases_on_target"] - 1.96 * summ["sem_bases_on_target"]
+    summ["ci_upper_bases_on_target"] = summ["mean_bases_on_target"] + 1.96 * summ["sem_bases_on_target"]
+    return df, summ
+
+
+@pytest.mark.parametrize("mode", ["I", "ROI"])
+def test_tables_match_reference_style_pandas(mode):
+    from esloco_b200.distributed import moments_from_tallies
+    from esloco_b200.tables import matches_table, summary_table
+    if mode == "I":
+        keys = [f"Barcode_{b}_insertion_{i}" for b in range(3) for i in range(11)]
+    else:
+        keys = [f"R{i}_{b}" for b in range(3) for i in range(11)]
+    combos = [(15000, 10), (15000, 30), (5000, 10)]
+    its = list(range(7))
+    tallies = [fake_tallies(len(its), len(keys), s, big=(s == 2)) for s in range(len(combos))]
+    ref_df, ref_sum = reference_style_tables(keys, mode, combos, its, tallies)
+    df = matches_table(keys, mode, combos, its, tallies)
+    assert list(df.columns) == list(ref_df.columns)
+    for col in df.columns:
+        assert df[col].astype(str).tolist() == ref_df[col].astype(str).tolist(), col
+    summ = summary_table(keys, mode, combos, [moments_from_tallies(t) for t in tallies])
+    assert list(summ.columns) == list(ref_sum.columns)
+    assert summ["target"].tolist() == ref_sum["target"].tolist()
+    for col in summ.columns[1:]:
+        assert np.allclose(summ[col].astype(float), ref_sum[col].astype(float), rtol=1e-9, atol=0), col
+
+
+def test_barcode_distribution_table():
+    from esloco_b200.tables import barcode_distribution_table
+    lc = np.array([[5, 0, 7, 0, 2], [6, 1, 8, 0, 0]])
+    df = barcode_distribution_table(3, [(1000, 2)], [0, 1], [lc], [np.array([111, 222])])
+    assert list(df.columns) == ["0", "1", "2", "Blocked/NotConsuming", "coverage", "mean_read_length", "iteration", "N_bases", "total_Reads"]
+    assert df["total_Reads"].tolist() == [12, 15] and df["N_bases"].tolist() == [111, 222]
+
+
+def test_shard_iterations_partition():
+    from esloco_b200.distributed import shard_iterations
+    for n in (0, 1, 7, 8, 1000):
+        for ws in (1, 2, 3, 8):
+            parts = [list(shard_iterations(n, r, ws)) for r in range(ws)]
+            assert sum(parts, []) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, ws, port, n_iter, T, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    import torch
+    import torch.distributed as dist
+    from esloco_b200.distributed import gather_iterations, moments_from_tallies, reduce_moments, shard_iterations
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    full = fake_tallies(n_iter, T, 99, big=True)
+    mine = shard_iterations(n_iter, rank, ws)
+    local = full[mine.start:mine.stop]
+    acc = torch.from_numpy(moments_from_tallies(local))
+    reduce_moments(acc, dst=0)
+    gathered = gather_iterations(torch.from_numpy(local.copy()), n_iter, dst=0)
+    if rank == 0:
+        q.put((acc.numpy(), gathered.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_iter", [9, 1])
+def test_world_size_2_gloo_reduce_and_gather(n_iter):
+    """Two ranks shard the iterations, reduce moment accumulators, gather tallies: rank 0 must end up with exactly
+    the single-process result (an odd count and a rank with zero iterations included)."""
+    import torch.multiprocessing as mp
+    from esloco_b200.distributed import moments_from_tallies
+    T = 13
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_iter, T, q)) for r in range(2)]
+    for p in procs: p.start()
+    acc, gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = fake_tallies(n_iter, T, 99, big=True)
+    assert np.array_equal(gathered, full)
+    exp = moments_from_tallies(full).astype(object)
+    got = acc.astype(object)
+    assert np.array_equal(got[:, :6], exp[:, :6])
+    assert [int(h) * 2**32 + int(l) for h, l in zip(got[:, 7], got[:, 6])] == [int(h) * 2**32 + int(l) for h, l in zip(exp[:, 7], exp[:, 6])]
