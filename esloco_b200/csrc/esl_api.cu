@@ -289,36 +289,91 @@ i64 bulk_reads(const esl_ctx *ctx, double coverage)
 size_t bulk_smem(int B) { return (size_t)(esl::kBulkBlock / 32) * 8 + (size_t)(2 * B + 2) * 4; }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4; }
 
-template <typename C, typename Src>
-int launch_pipeline(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, esl::DevOut out, const i64 *d_n_bulk,
-                    i64 n_bulk_const, i64 max_bulk, int n_iter, bool run_tail, cudaStream_t st)
+// Upper bound on the draws per iteration any bulk pass may cover.  Without a mask (or with consuming = True)
+// every draw counts and the first-pass bound n1 is already tight.  With a mask a blocked draw may count nothing,
+// so a second pass can extend up to this cap; the blocked fraction is bounded from above by the union bound
+// sum_k w_k (len_k + mean read length) / G.  The cap only sizes scratch and grids -- the per-iteration extent of
+// the second pass is decided on the device from the measured counted mean, and k_cutoff_tail finishes exactly.
+i64 bulk_cap(const esl_ctx *ctx, double coverage)
 {
-    const int tiles_per_iter = (int)((max_bulk + esl::kBulkTile - 1) / esl::kBulkTile);
-    out.tiles_per_iter = tiles_per_iter;
-    const i64 total_tiles = (i64)tiles_per_iter * n_iter;
+    const i64 n1 = bulk_reads(ctx, coverage);
+    if (ctx->m_start.empty() || n1 == 0) return n1;
+    long double blocked = 0;
+    for (size_t k = 0; k < ctx->m_start.size(); ++k) {
+        const long double len = (long double)std::max<i64>(0, ctx->m_end[k] - ctx->m_start[k]);
+        blocked += std::min<long double>(1.0L, std::max<long double>(0.0L, ctx->m_w[k])) * (len + ctx->pool_mean);
+    }
+    const double f = (double)std::min<long double>(0.9L, blocked / (long double)ctx->G);
+    const double expect = coverage * (double)ctx->G / ctx->pool_mean / (1.0 - f);
+    i64 cap = (i64)(expect * 1.02) + 4 * esl::kBulkTile;
+    cap = std::max(cap, n1);
+    cap = std::min<i64>(cap, 0xFFFF0000ll);
+    cap += (esl::kBulkTile - cap % esl::kBulkTile) % esl::kBulkTile;
+    return cap;
+}
+
+struct BulkRange {
+    const i64 *lo_arr; i64 lo_const;
+    const i64 *hi_arr; i64 hi_const;
+    i64 tile0, tiles; // absolute tile window of the launch (per iteration)
+};
+
+template <typename C, typename Src>
+int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const esl::DevOut &out, const BulkRange &r,
+                int n_iter, cudaStream_t st)
+{
+    const i64 total_tiles = r.tiles * n_iter;
+    if (total_tiles <= 0) return ESL_OK;
+    auto kern = esl::k_place_tally_bulk<C, Src>;
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx->B)));
+    if (occ < 1) occ = 1;
+    const i64 grid = std::min<i64>(total_tiles, (i64)ctx->sm_count * occ);
+    kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx->B), st>>>(dc, src, out, r.lo_arr, r.lo_const, r.hi_arr, r.hi_const,
+                                                                      (int)r.tile0, (int)r.tiles, total_tiles);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return ESL_OK;
+}
+
+// Bulk pass(es) + exact cut-off kernel.  n1 = draws per iteration of the first pass; n_cap >= n1 = bound of the
+// optional second pass (needs d_range = 2 * n_iter i64 of scratch); out.tile_sum must be zeroed and hold
+// ceil(n_cap / tile) entries per iteration.
+template <typename C, typename Src>
+int launch_pipeline(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, esl::DevOut out, i64 n1, i64 n_cap,
+                    i64 *d_range, int n_iter, bool run_tail, cudaStream_t st)
+{
+    const i64 T = esl::kBulkTile;
+    out.tiles_per_iter = (int)((std::max(n1, n_cap) + T - 1) / T);
     const bool prof = ctx->profiling && ctx->ev[0];
     ctx->ev_valid = false;
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
-    if (total_tiles > 0) {
-        auto kern = esl::k_place_tally_bulk<C, Src>;
-        int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx->B)));
-        if (occ < 1) occ = 1;
-        const i64 grid = std::min<i64>(total_tiles, (i64)ctx->sm_count * occ);
-        kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx->B), st>>>(dc, src, out, d_n_bulk, n_bulk_const, total_tiles);
+    int rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{nullptr, 0, nullptr, n1, 0, (n1 + T - 1) / T}, n_iter, st);
+    if (rc) return rc;
+    const i64 *d_hi = nullptr;
+    if (n_cap > n1 && d_range && n1 > 0) {
+        i64 *d_lo = d_range, *d_hi2 = d_range + n_iter;
+        const double m2 = ctx->pool_sd * ctx->pool_sd + ctx->pool_mean * ctx->pool_mean;
+        esl::k_plan_second_pass<<<(n_iter + 127) / 128, 128, 0, st>>>(out.n_bases, n_iter, dc.thr, n1, n_cap, m2, 8.0, d_lo, d_hi2);
         CU(cudaGetLastError());
         ctx->launches++;
+        rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{d_lo, 0, d_hi2, 0, n1 / T, (n_cap - n1) / T}, n_iter, st);
+        if (rc) return rc;
+        d_hi = d_hi2;
     }
     if (prof) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); }
     if (run_tail) {
         auto kern = esl::k_cutoff_tail<C, Src>;
-        kern<<<(unsigned)n_iter, esl::kTailBlock, tail_smem(ctx->B), st>>>(dc, src, out, d_n_bulk, n_bulk_const);
+        kern<<<(unsigned)n_iter, esl::kTailBlock, tail_smem(ctx->B), st>>>(dc, src, out, d_hi, n1);
         CU(cudaGetLastError());
         ctx->launches++;
     }
     if (prof) { CU(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid = true; }
     return ESL_OK;
 }
+
+// Workspace layout: [tile sums: tiles * n_iter u64][second-pass ranges: 2 * n_iter i64]
+size_t ws_tile_bytes(i64 cap, int n_iter) { return (size_t)((cap + esl::kBulkTile - 1) / esl::kBulkTile) * (size_t)n_iter * sizeof(u64); }
 
 int zero_outputs(esl_ctx *ctx, int n_iter, int64_t *d_tallies, int64_t *d_label_counts, int64_t *d_n_bases,
                  int64_t *d_n_reads, int32_t *d_status, cudaStream_t st)
@@ -464,9 +519,8 @@ int64_t esl_bulk_reads(const esl_ctx *ctx, double coverage) { return ctx ? bulk_
 int64_t esl_workspace_bytes(const esl_ctx *ctx, int32_t n_iter, double coverage, int64_t max_draws_per_iter)
 {
     if (!ctx || n_iter < 0) return ESL_ERR_INVALID;
-    const i64 nb = max_draws_per_iter > 0 ? max_draws_per_iter : bulk_reads(ctx, coverage);
-    const i64 tiles = (nb + esl::kBulkTile - 1) / esl::kBulkTile;
-    return (int64_t)(((size_t)tiles * n_iter + n_iter + 2) * sizeof(u64)) + 256;
+    const i64 cap = max_draws_per_iter > 0 ? max_draws_per_iter : bulk_cap(ctx, coverage);
+    return (int64_t)(ws_tile_bytes(cap, n_iter) + (size_t)(2 * n_iter + 2) * sizeof(i64)) + 256;
 }
 
 int esl_set_profiling(esl_ctx *ctx, int32_t on)
@@ -515,14 +569,19 @@ int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_beg
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
     esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0};
     esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iter_begin};
-    const i64 nb = bulk_reads(ctx, coverage);
+    const i64 n1 = bulk_reads(ctx, coverage);
+    const i64 cap = (ctx->n_mask > 0 && !consuming) ? bulk_cap(ctx, coverage) : n1;
+    const size_t tile_bytes = ws_tile_bytes(std::max(cap, n1), n_iter);
+    CU(cudaMemsetAsync(d_ws, 0, tile_bytes, st));
+    i64 *d_range = (i64 *)((char *)d_ws + ((tile_bytes + 15) & ~(size_t)15));
     if (ctx->wide)
-        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, nullptr, nb, nb, n_iter, true, st);
-    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, nullptr, nb, nb, n_iter, true, st);
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, n1, cap, d_range, n_iter, true, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, n1, cap, d_range, n_iter, true, st);
 }
 
 int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,
-                     const int64_t *d_seg, int64_t total_reads, int32_t n_iter, int64_t min_overlap, int64_t *d_tallies,
+                     const int64_t *d_seg, int64_t total_reads, int64_t max_reads_per_iter, int32_t n_iter,
+                     int64_t min_overlap, int64_t *d_tallies,
                      int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status, void *stream)
 {
     if (!ctx) return ESL_ERR_INVALID;
@@ -536,14 +595,15 @@ int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_leng
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
     // the bulk kernel also records per-tile sums; replay level 1 has no cut-off, so they go to a private scratch
-    const i64 tiles = (total_reads + esl::kBulkTile - 1) / esl::kBulkTile + 1;
-    CU(ctx->d_scratch.reserve((size_t)tiles * n_iter * sizeof(u64)));
+    if (total_reads >= 0xFFFF0000ll) return ctx->fail(ESL_ERR_UNSUPPORTED, "more than 2^32 reads in one replay call");
+    if (max_reads_per_iter <= 0 || max_reads_per_iter > total_reads) max_reads_per_iter = total_reads;
+    CU(ctx->d_scratch.reserve(ws_tile_bytes(max_reads_per_iter, n_iter) + 64));
     esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, ctx->d_scratch.as<u64>(), 0};
     esl::ReadSrc src{d_start, d_length, d_label, d_seg};
-    const i64 big = total_reads; // every iteration's reads are all "bulk" (clipped to its own count on device)
+    const i64 big = max_reads_per_iter; // every iteration's reads are all "bulk" (clipped to its own count on device)
     if (ctx->wide)
-        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, nullptr, big, big, n_iter, false, st);
-    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, nullptr, big, big, n_iter, false, st);
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, big, big, nullptr, n_iter, false, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, big, big, nullptr, n_iter, false, st);
 }
 
 int esl_replay_draws(esl_ctx *ctx, const double *d_ubc, const int64_t *d_length, const int64_t *d_start,
@@ -567,11 +627,13 @@ int esl_replay_draws(esl_ctx *ctx, const double *d_ubc, const int64_t *d_length,
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
+    if (max_draws >= 0xFFFF0000ll) return ctx->fail(ESL_ERR_UNSUPPORTED, "more than 2^32 draws per iteration");
+    CU(cudaMemsetAsync(d_ws, 0, ws_tile_bytes(std::max<i64>(bulk_draws, 1), n_iter), st));
     esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0};
     esl::DrawSrc src{d_ubc, d_length, d_start, d_uoff, d_ublock, d_seg};
     if (ctx->wide)
-        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, nullptr, bulk_draws, bulk_draws, n_iter, true, st);
-    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, nullptr, bulk_draws, bulk_draws, n_iter, true, st);
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, bulk_draws, bulk_draws, nullptr, n_iter, true, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, bulk_draws, bulk_draws, nullptr, n_iter, true, st);
 }
 
 int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iteration, int32_t consuming,

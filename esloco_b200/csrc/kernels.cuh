@@ -306,11 +306,14 @@ __device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
 // ---------------------------------------------------------------- bulk kernel
 
 // Persistent flat grid; CTA c owns a contiguous run of (iteration, tile) pairs so the per-iteration
-// counters are flushed once per iteration change, not once per tile.
+// counters are flushed once per iteration change, not once per tile.  One launch covers the absolute tiles
+// [tile0, tile0 + tiles_launch) of every iteration; inside that window iteration `it` owns the draws
+// [lo(it), hi(it)) (lo is a multiple of the tile size).  Draw indices are < 2^32 (checked on the host).
 template <typename C, typename Src>
 __global__ void __launch_bounds__(kBulkBlock)
-k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__restrict__ n_bulk_arr,
-                   const i64 n_bulk_const, const i64 total_tiles)
+k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__restrict__ lo_arr,
+                   const i64 lo_const, const i64 *__restrict__ hi_arr, const i64 hi_const, const int tile0,
+                   const int tiles_launch, const i64 total_tiles)
 {
     extern __shared__ u64 smem[];
     u64 *s_part = smem;                                   // [kBulkBlock / 32]
@@ -329,10 +332,12 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
     const bool plain_labels = !Src::kHasLabel && B == 1 && !cx.has_mask; // every read is label 0
     int cur_it = -1;
     u64 acc_bases = 0, acc_reads = 0; // thread 0 only
+    uint32_t lo = 0, hi = 0;
+    u64 *tallies_it = nullptr;
 
     for (i64 tl = t0; tl < t1; ++tl) {
-        const int it = (int)(tl / out.tiles_per_iter);
-        const i64 t = tl - (i64)it * out.tiles_per_iter;
+        const int it = (int)(tl / tiles_launch);
+        const int t = (int)(tl - (i64)it * tiles_launch) + tile0; // absolute tile of this iteration
         if (it != cur_it) {
             if (cur_it >= 0) {
                 __syncthreads();
@@ -347,35 +352,33 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
                 __syncthreads();
             }
             cur_it = it;
+            i64 l = lo_arr ? lo_arr[it] : lo_const, h = hi_arr ? hi_arr[it] : hi_const;
+            if (Src::kBounded) { const i64 c = src.count(it); h = h < c ? h : c; }
+            lo = (uint32_t)l;
+            hi = (uint32_t)(h > l ? h : l);
+            tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
         }
-        i64 nb = n_bulk_arr ? n_bulk_arr[it] : n_bulk_const;
-        if (Src::kBounded) { const i64 c = src.count(it); nb = nb < c ? nb : c; }
-        const i64 base = t * kBulkTile;
-        if (base >= nb) { // tile beyond this iteration's bulk range (block-uniform)
-            if (tid == 0) out.tile_sum[tl] = 0;
-            continue;
-        }
+        const uint32_t base = (uint32_t)t * kBulkTile;
+        if (base < lo || base >= hi) continue; // tile outside this iteration's range (block-uniform)
         uint32_t L[kBulkIpt];
         C st[kBulkIpt];
         int bc[kBulkIpt];
-        bool valid[kBulkIpt];
 #pragma unroll
         for (int i = 0; i < kBulkIpt; ++i) { // phase 1: independent draws + table gathers in flight together
-            const i64 n = base + i * kBulkBlock + tid;
-            valid[i] = n < nb;
+            const uint32_t n = base + i * kBulkBlock + tid;
             L[i] = 0; st[i] = 0; bc[i] = 0;
-            if (valid[i]) src.draw(cx, s_cdf, it, n, L[i], st[i], bc[i]);
+            if (n < hi) src.draw(cx, s_cdf, it, (i64)n, L[i], st[i], bc[i]);
         }
         u64 my = 0;
-        u64 *tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
 #pragma unroll
         for (int i = 0; i < kBulkIpt; ++i) { // phase 2: blocked test, label, tally
-            const i64 n = base + i * kBulkBlock + tid;
+            const uint32_t n = base + i * kBulkBlock + tid;
+            const bool valid = n < hi;
             int label = 0; uint32_t counted = 0;
-            if (valid[i]) resolve_read(cx, src, it, n, L[i], st[i], bc[i], label, counted);
+            if (valid) resolve_read(cx, src, it, (i64)n, L[i], st[i], bc[i], label, counted);
             my += counted;
-            if (!plain_labels) hist_add(s_hist, valid[i] && label < B ? label_slot(label, B) : -1, 1);
-            if (valid[i] && label >= 0 && label < B) tally_read(cx, src, tallies_it, it, n, st[i], (C)(st[i] + L[i]), label, 1);
+            if (!plain_labels) hist_add(s_hist, valid && label < B ? label_slot(label, B) : -1, 1);
+            if (valid && label >= 0 && label < B) tally_read(cx, src, tallies_it, it, (i64)n, st[i], (C)(st[i] + L[i]), label, 1);
         }
         my = warp_sum(my);
         if (lane == 0) s_part[wid] = my;
@@ -384,10 +387,10 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
             u64 s = 0;
 #pragma unroll
             for (int w = 0; w < kBulkBlock / 32; ++w) s += s_part[w];
-            out.tile_sum[tl] = s;
+            out.tile_sum[(i64)it * out.tiles_per_iter + t] = s;
             acc_bases += s;
-            const i64 left = nb - base;
-            acc_reads += (u64)(left < kBulkTile ? left : kBulkTile);
+            const uint32_t left = hi - base;
+            acc_reads += left < (uint32_t)kBulkTile ? left : (uint32_t)kBulkTile;
         }
         __syncthreads();
     }
@@ -401,6 +404,32 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
             if (plain_labels) atomicAdd(out.label_counts + (i64)cur_it * (B + 2), acc_reads);
         }
     }
+}
+
+// With blocked regions and consuming = False a blocked draw adds nothing to the covered length
+// (read_operations.py:116-117), so the cut-off moves out by the unknown blocked fraction.  After the first bulk
+// pass the per-iteration mean counted length per draw is known from n_bases; this kernel sizes a second bulk
+// pass [n1, n2(it)) with the same z-sigma rule on the REMAINING coverage (sd bound: counted is 0 or L, so
+// E[c^2] <= E[L^2]).  Any overshoot is again corrected exactly by k_cutoff_tail.
+__global__ void k_plan_second_pass(const u64 *__restrict__ n_bases, const int n_iter, const i64 thr, const i64 n1,
+                                   const i64 n_cap, const double pool_m2, const double z, i64 *__restrict__ lo_out,
+                                   i64 *__restrict__ hi_out)
+{
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_iter) return;
+    i64 n2 = n1;
+    const double S = (double)n_bases[it], rem = (double)thr - S;
+    if (n1 > 0 && rem > 0 && S > 0) {
+        const double m = S / (double)n1;
+        const double var = pool_m2 - m * m, sd = var > 0 ? sqrt(var) : 0.0;
+        const double r = (-z * sd + sqrt(z * z * sd * sd + 4.0 * m * rem)) / (2.0 * m);
+        i64 extra = (i64)floor(r * r) - 1;
+        extra -= extra % kBulkTile;
+        if (extra > 0) n2 = n1 + extra;
+        if (n2 > n_cap) n2 = n_cap;
+    }
+    lo_out[it] = n1;
+    hi_out[it] = n2;
 }
 
 // ---------------------------------------------------------------- exact cut-off kernel (K5)

@@ -143,7 +143,8 @@ class Engine:
         dseg = self._dev(seg, t.int64)
         self._keep = (ds, dl, dlab, dseg)
         self._check(self.lib.esl_replay_reads(
-            self.ctx, ds.data_ptr(), dl.data_ptr(), dlab.data_ptr(), dseg.data_ptr(), int(seg[-1]), n_iter,
+            self.ctx, ds.data_ptr(), dl.data_ptr(), dlab.data_ptr(), dseg.data_ptr(), int(seg[-1]),
+            int(np.max(np.diff(seg))) if n_iter else 0, n_iter,
             int(min_overlap), out.tallies.data_ptr(), out.label_counts.data_ptr(), out.n_bases.data_ptr(),
             out.n_reads.data_ptr(), out.status.data_ptr(), self._stream()))
         return out

@@ -112,9 +112,11 @@ int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_beg
 
 /* Replay level 1: recorded reads (already cut off), iteration i owns reads [seg_offsets[i], seg_offsets[i+1]).
  * count_matches + count_barcode_occurrences over them (counting.py:7-71).  seg_offsets is a DEVICE array of
- * n_iter+1 int64; total_reads = seg_offsets[n_iter] (passed so the host need not read it back). */
+ * n_iter+1 int64; total_reads = seg_offsets[n_iter] and max_reads_per_iter = the largest segment (passed so the
+ * host need not read them back; max_reads_per_iter <= 0 means "unknown", which only costs empty tiles). */
 int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,
-                     const int64_t *d_seg_offsets, int64_t total_reads, int32_t n_iter, int64_t min_overlap,
+                     const int64_t *d_seg_offsets, int64_t total_reads, int64_t max_reads_per_iter, int32_t n_iter,
+                     int64_t min_overlap,
                      int64_t *d_tallies, int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads,
                      int32_t *d_status, void *stream);
 

@@ -196,6 +196,41 @@ def test_native_mode_matches_cpu_restatement(eng, name):
     assert int(solo.n_reads[0]) == int(res.n_reads[1])
 
 
+@pytest.mark.parametrize("consuming", [False, True])
+def test_native_masked_second_bulk_pass(eng, consuming):
+    """Large enough for the bulk kernel to run, 35 % of the genome blocked: with consuming=False the cut-off moves
+    out by the blocked fraction and the device-planned second bulk pass covers most of the extension.  Exact
+    against the CPU restatement of the same Philox draws."""
+    G = 20_000_000
+    rng = np.random.RandomState(12)
+    ts = np.sort(rng.randint(0, G - 5000, 60)); te = ts + rng.randint(200, 5000, 60)
+    tb = (np.arange(60) % 2).astype(np.int32)
+    mask = (np.array([1_000_000, 9_000_000, 9_500_000, 15_000_000]), np.array([5_000_000, 10_000_000, 11_000_000, 17_000_000]),
+            np.array([1.0, 0.5, 1.0, 1.0]), np.array([-1, 0, -1, 1], np.int32))
+    eng.set_genome(G)
+    cdf = O.barcode_cdf(O.barcode_probabilities(2, {"0": 2}))
+    eng.set_barcode_cdf(cdf)
+    eng.set_targets(ts, te, tb)
+    eng.set_blocked(*mask)
+    pool = O.lognormal_pool(O.Rng(21), 2000, 1, 50, n=100000)
+    eng.set_length_table(pool)
+    cov, seed = 6.0, 4242
+    n1 = eng.bulk_reads(cov)
+    assert n1 > 20000
+    res = eng.run_batch(seed, 1, 10, 2, cov, consuming, 1, 1.0).cpu()
+    for i in range(2):
+        it = NN.native_iteration(seed, 1, 10 + i, G, cov, pool, cdf, consuming=consuming, mask=mask)
+        exp = O.count_matches(None, ts, te, tb, it["start"], it["start"] + it["length"], it["label"], 1.0, 1)
+        counts, _ = O.label_hist(it["label"], 2)
+        t = res.tallies[i].numpy()
+        assert int(res.n_reads[i]) == it["n_placed"] and int(res.n_bases[i]) == it["covered"]
+        assert np.array_equal(res.label_counts[i].numpy(), counts)
+        assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+        if not consuming:
+            assert it["n_placed"] > 1.2 * n1  # the second pass had real work to do
+    assert not (res.status.numpy() & 2).any()
+
+
 def test_native_materialize_reads(eng):
     g = Golden("blocked_fractional_multihit")
     configure(eng, g)
