@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libesloco_b200.so")
+LIB_PATH = os.environ.get("ESL_LIB") or os.path.join(_HERE, "libesloco_b200.so")  # ESL_LIB: tuning builds only
 
 ESL_OK = 0
 ESL_ITER_CUT_IN_BULK = 1

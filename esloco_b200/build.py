@@ -29,7 +29,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("ESL_NVCC_EXTRA", "").split()  # e.g. -DESL_BULK_MIN_BLOCKS=5 for tuning experiments
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

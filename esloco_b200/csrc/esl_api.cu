@@ -63,14 +63,14 @@ struct esl_ctx {
     bool have_targets = false, have_pool = false;
     bool index_dirty = true;
     bool wide = false; // 64-bit coordinates
-    int n_layers = 0;
+    int n_layers = 0, n_first_layers = 0;
     i64 n_indexed = 0, n_mask = 0;
 
     // pool statistics
     uint32_t n_pool = 0, pool_max = 0;
     double pool_mean = 0, pool_sd = 0;
 
-    DevBuf d_pool, d_cdf, d_cdf_u32, d_ts, d_te, d_trow, d_seg, d_tgrid, d_bc_seg, d_ms, d_me, d_mpmax, d_mw, d_grp, d_mgrid;
+    DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_ts, d_te, d_trow, d_seg, d_tgrid, d_extra_off, d_ms, d_me, d_mpmax, d_mw, d_grp, d_mgrid;
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
 
     // optional per-kernel timing (esl_set_profiling): events around the bulk and the cut-off kernel
@@ -127,24 +127,44 @@ void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers)
 template <typename C> C clampc(i64 v, u64 G) { return (C)((u64)v > G + 1 ? G + 1 : (u64)v); }
 
 // Bucket grid over one sorted run: keys[lo..hi) ascending (target ends of a layer, or the running max of
-// blocked-interval ends).  About 4 buckets per interval (at least 64, at most 2^22), so a bucket rarely holds
-// more than one candidate.  Appends to `grid` and returns the descriptor.
+// blocked-interval ends), starts[lo..hi) the interval starts.  At least 8 buckets per interval, so a bucket
+// rarely holds more than one interval end; runs where some bucket holds more than
+// kCrowdedBucket ends are flagged so the device bisects inside the bucket.  Appends to `grid`.
 template <typename C>
-esl::SegDesc make_grid(const std::vector<C> &keys, int lo, int hi, u64 G, std::vector<int32_t> &grid)
+esl::SegDesc make_grid(const std::vector<C> &keys, const std::vector<C> &starts, int lo, int hi, u64 G,
+                       std::vector<esl::GridEntry<C>> &grid)
 {
     esl::SegDesc d;
     d.lo = lo; d.hi = hi; d.grid_off = (int)grid.size();
-    const u64 want = std::min<u64>(std::max<u64>(64, 4ull * (u64)(hi - lo)), 1ull << 22);
+    // bucket width ~ min(G / (8 * intervals), 64 kb): fine enough that "first candidate starts before the read
+    // ends" is rarely a false alarm even for sparse runs, yet at most 2^21 entries (16 MB) per run
+    const u64 want = std::min<u64>(std::max<u64>(std::max<u64>(64, 8ull * (u64)(hi - lo)), (G >> 16) + 1), 1ull << 21);
     int shift = 0;
     while (((G + 1) >> shift) + 2 > want) ++shift;
-    d.shift = shift;
-    const u64 nb = ((G + 1) >> shift) + 2; // reads start below G, so bucket index <= G >> shift; +1 for the upper bound
-    int j = lo;
+    const u64 nb = ((G + 1) >> shift) + 2; // reads start below G: bucket index <= G >> shift; one more for the bound
+    int j = lo, crowded = 0, prev = lo;
     for (u64 b = 0; b < nb; ++b) {
         const u64 edge = b << shift;
         while (j < hi && (u64)keys[j] <= edge) ++j; // first key > bucket start
-        grid.push_back(j);
+        if (j - prev > esl::kCrowdedBucket) crowded = 1;
+        prev = j;
+        esl::GridEntry<C> e{};
+        e.j = j;
+        e.s = j < hi ? starts[j] : (C) ~(C)0;
+        grid.push_back(e);
     }
+    d.flags = shift | (crowded << 8);
+    return d;
+}
+
+// Grid of an empty run: two entries that reject every read; any position maps to bucket 0 (shift 63).
+template <typename C>
+esl::SegDesc empty_run(std::vector<esl::GridEntry<C>> &grid)
+{
+    esl::SegDesc d{0, 0, (int)grid.size(), 63};
+    esl::GridEntry<C> e{};
+    e.j = 0; e.s = (C) ~(C)0;
+    grid.push_back(e); grid.push_back(e);
     return d;
 }
 
@@ -153,37 +173,46 @@ int upload_index(esl_ctx *ctx)
 {
     const int B = ctx->B;
     const u64 G = ctx->G;
-    // targets
+    // targets: seg[b] = first layer of barcode b, extra layers appended behind the B first-layer descriptors
     std::vector<C> ts, te;
-    std::vector<int32_t> trow, bc_seg(B + 1, 0), tgrid;
-    std::vector<esl::SegDesc> seg;
+    std::vector<int32_t> trow, extra_off(B, 0);
+    std::vector<esl::GridEntry<C>> tgrid;
+    std::vector<esl::SegDesc> first(B), extra;
     ctx->n_layers = 0;
+    ctx->n_first_layers = 0;
     for (int b = 0; b < B; ++b) {
         std::vector<Rec> v;
         for (size_t i = 0; i < ctx->t_start.size(); ++i)
             if (ctx->t_bc[i] == b && ctx->t_end[i] > ctx->t_start[i]) v.push_back(Rec{ctx->t_start[i], ctx->t_end[i], (int32_t)i});
         std::vector<std::vector<Rec>> layers;
         build_layers(v, layers);
-        for (auto &ly : layers) {
+        if (layers.size() > 0xFFFF) return ctx->fail(ESL_ERR_UNSUPPORTED, "barcode %d needs %zu nesting layers (max 65535)", b, layers.size());
+        extra_off[b] = (int32_t)extra.size();
+        for (size_t l = 0; l < layers.size(); ++l) {
             const int lo = (int)ts.size();
-            for (const Rec &r : ly) { ts.push_back(clampc<C>(r.s, G)); te.push_back(clampc<C>(r.e, G)); trow.push_back(r.row); }
-            seg.push_back(make_grid<C>(te, lo, (int)ts.size(), G, tgrid));
+            for (const Rec &r : layers[l]) { ts.push_back(clampc<C>(r.s, G)); te.push_back(clampc<C>(r.e, G)); trow.push_back(r.row); }
+            esl::SegDesc d = make_grid<C>(te, ts, lo, (int)ts.size(), G, tgrid);
+            if (l == 0) { d.flags |= (int)((layers.size() - 1) << 16); first[b] = d; }
+            else extra.push_back(d);
         }
+        if (layers.empty()) first[b] = empty_run<C>(tgrid);
         ctx->n_layers += (int)layers.size();
-        bc_seg[b + 1] = (int32_t)seg.size();
+        ctx->n_first_layers += layers.empty() ? 0 : 1;
     }
+    std::vector<esl::SegDesc> seg(first);
+    seg.insert(seg.end(), extra.begin(), extra.end());
     ctx->n_indexed = (i64)ts.size();
     CU(ctx->d_ts.upload(ts.data(), ts.size() * sizeof(C)));
     CU(ctx->d_te.upload(te.data(), te.size() * sizeof(C)));
     CU(ctx->d_trow.upload(trow.data(), trow.size() * sizeof(int32_t)));
     CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc)));
-    CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(int32_t)));
-    CU(ctx->d_bc_seg.upload(bc_seg.data(), bc_seg.size() * sizeof(int32_t)));
+    CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(esl::GridEntry<C>)));
+    CU(ctx->d_extra_off.upload(extra_off.data(), extra_off.size() * sizeof(int32_t)));
     // blocked intervals: group g < B = barcode g, group B = "ALL"; (start, end) order, running max of ends
     std::vector<C> ms, me, mp;
     std::vector<double> mw;
     std::vector<esl::SegDesc> grp;
-    std::vector<int32_t> mgrid;
+    std::vector<esl::GridEntry<C>> mgrid;
     for (int g = 0; g <= B; ++g) {
         const int want = g < B ? g : -1;
         std::vector<size_t> idx;
@@ -200,8 +229,8 @@ int upload_index(esl_ctx *ctx)
             run = std::max(run, e);
             ms.push_back(s); me.push_back(e); mp.push_back(run); mw.push_back(ctx->m_w[i]);
         }
-        if ((int)ms.size() == glo) grp.push_back(esl::SegDesc{glo, glo, 0, 0}); // empty group: never dereferenced
-        else grp.push_back(make_grid<C>(mp, glo, (int)ms.size(), G, mgrid));
+        if ((int)ms.size() == glo) grp.push_back(empty_run<C>(mgrid));
+        else grp.push_back(make_grid<C>(mp, ms, glo, (int)ms.size(), G, mgrid));
     }
     ctx->n_mask = (i64)ms.size();
     CU(ctx->d_ms.upload(ms.data(), ms.size() * sizeof(C)));
@@ -209,15 +238,23 @@ int upload_index(esl_ctx *ctx)
     CU(ctx->d_mpmax.upload(mp.data(), mp.size() * sizeof(C)));
     CU(ctx->d_mw.upload(mw.data(), mw.size() * sizeof(double)));
     CU(ctx->d_grp.upload(grp.data(), grp.size() * sizeof(esl::SegDesc)));
-    CU(ctx->d_mgrid.upload(mgrid.data(), mgrid.size() * sizeof(int32_t)));
-    // barcode cdf
+    CU(ctx->d_mgrid.upload(mgrid.data(), mgrid.size() * sizeof(esl::GridEntry<C>)));
+    // barcode cdf: doubles (replay), integer thresholds and a 1024-slice start table (native)
     std::vector<uint32_t> cu(B);
     for (int k = 0; k < B; ++k) {
         const double v = std::ceil(ctx->cdf[k] * 4294967296.0);
         cu[k] = v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
     }
+    std::vector<uint16_t> lut(esl::kCdfLut);
+    int k = 0;
+    for (int q = 0; q < esl::kCdfLut; ++q) {
+        const uint32_t w = (uint32_t)q << 22; // lowest draw of the slice
+        while (k < B - 1 && cu[k] <= w) ++k;
+        lut[q] = (uint16_t)k;
+    }
     CU(ctx->d_cdf.upload(ctx->cdf.data(), B * sizeof(double)));
     CU(ctx->d_cdf_u32.upload(cu.data(), B * sizeof(uint32_t)));
+    CU(ctx->d_cdf_lut.upload(lut.data(), lut.size() * sizeof(uint16_t)));
     return ESL_OK;
 }
 
@@ -254,19 +291,21 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.pool = ctx->d_pool.as<uint32_t>();
     d.cdf = ctx->d_cdf.as<double>();
     d.cdf_u32 = ctx->d_cdf_u32.as<uint32_t>();
+    d.cdf_lut = ctx->d_cdf_lut.as<uint16_t>();
     d.ts = ctx->d_ts.as<C>();
     d.te = ctx->d_te.as<C>();
     d.trow = ctx->d_trow.as<int32_t>();
     d.seg = ctx->d_seg.as<esl::SegDesc>();
-    d.tgrid = ctx->d_tgrid.as<int32_t>();
-    d.bc_seg = ctx->d_bc_seg.as<int32_t>();
+    d.tgrid = ctx->d_tgrid.as<esl::GridEntry<C>>();
+    d.extra_off = ctx->d_extra_off.as<int32_t>();
+    d.any_extra = ctx->n_layers > ctx->n_first_layers;
     d.n_targets = (i64)ctx->t_start.size();
     d.ms = ctx->d_ms.as<C>();
     d.me = ctx->d_me.as<C>();
     d.mpmax = ctx->d_mpmax.as<C>();
     d.mw = ctx->d_mw.as<double>();
     d.grp = ctx->d_grp.as<esl::SegDesc>();
-    d.mgrid = ctx->d_mgrid.as<int32_t>();
+    d.mgrid = ctx->d_mgrid.as<esl::GridEntry<C>>();
     return d;
 }
 
@@ -286,8 +325,8 @@ i64 bulk_reads(const esl_ctx *ctx, double coverage)
     return n < 2 * esl::kBulkTile ? 0 : n;
 }
 
-size_t bulk_smem(int B) { return (size_t)(esl::kBulkBlock / 32) * 8 + (size_t)(2 * B + 2) * 4; }
-size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4; }
+size_t bulk_smem(int B) { return (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
+size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
 
 // Upper bound on the draws per iteration any bulk pass may cover.  Without a mask (or with consuming = True)
 // every draw counts and the first-pass bound n1 is already tight.  With a mask a blocked draw may count nothing,
@@ -324,7 +363,7 @@ int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const es
 {
     const i64 total_tiles = r.tiles * n_iter;
     if (total_tiles <= 0) return ESL_OK;
-    auto kern = esl::k_place_tally_bulk<C, Src>;
+    auto kern = dc.has_mask ? esl::k_place_tally_bulk<C, Src, true> : esl::k_place_tally_bulk<C, Src, false>;
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx->B)));
     if (occ < 1) occ = 1;
@@ -648,7 +687,7 @@ int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t 
     cudaStream_t st = (cudaStream_t)stream;
     esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iteration};
     const unsigned grid = (unsigned)std::min<i64>((n_reads + 255) / 256, (i64)ctx->sm_count * 8);
-    const size_t sm = (size_t)ctx->B * 4 + 8;
+    const size_t sm = (size_t)ctx->B * 4 + (size_t)esl::kCdfLut * 2 + 16;
     if (ctx->wide)
         esl::k_materialize<uint64_t><<<grid, 256, sm, st>>>(make_devctx<uint64_t>(ctx, 0.0, consuming, 1, 1.0), src, n_reads, d_start, d_length, d_label);
     else

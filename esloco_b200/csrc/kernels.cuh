@@ -31,6 +31,10 @@ typedef int64_t i64;
 constexpr int kBulkBlock = 256;
 constexpr int kBulkIpt = 4;
 constexpr int kBulkTile = kBulkBlock * kBulkIpt;
+#ifndef ESL_BULK_MIN_BLOCKS
+#define ESL_BULK_MIN_BLOCKS 4
+#endif
+constexpr int kBulkMinBlocks = ESL_BULK_MIN_BLOCKS; // register cap: 65536 / (256 * min blocks)
 constexpr int kTailBlock = 1024;
 constexpr int kTailIpt = 2;
 constexpr int kTailChunk = kTailBlock * kTailIpt;
@@ -38,21 +42,41 @@ constexpr int kMaxBarcodes = 4096;
 
 constexpr int kLabelBlockedConsuming = -1;
 constexpr int kLabelBlockedNotConsuming = -2;
+constexpr int kLabelInvalid = -1000; // slot of a tile that holds no draw
 
-// One sorted run of intervals plus its bucket grid.  grid[grid_off + b], b = position >> shift, is the first
-// index j of the run whose (running-max) end exceeds b << shift; so for a read starting at rs the first
-// overlapping candidate lies in [grid[b], grid[b+1]] -- usually an empty or one-element range, which turns the
-// O(log n) search into two adjacent loads.
+// One sorted run of intervals (a monotone target layer, or one blocked group) plus its bucket grid.
+// Grid entry b (b = position >> shift) holds j = first index of the run whose (running-max) end exceeds
+// b << shift, together with the START of that interval.  For a read [rs, re) with bucket b = rs >> shift:
+//   * every interval before j ends at or before the bucket start <= rs, so it cannot overlap;
+//   * if start[j] >= re nothing overlaps at all (starts ascend) -- the common case, decided by ONE 8-byte load;
+//   * otherwise the candidates are j, j+1, ... while start < re, each checked exactly (end > rs).
+// A bucket normally holds at most a few interval ends; for crowded runs (flag) the candidate scan first
+// bisects inside [j, j of the next bucket].
 struct __align__(16) SegDesc {
     int lo, hi;   // index range of the run
     int grid_off; // offset of the run's grid
-    int shift;    // log2 of the bucket width
+    int flags;    // bits 0-7 log2(bucket width), bit 8 crowded, bits 16-31 number of EXTRA layers (targets only)
 };
+constexpr int kCrowdedBucket = 8;
+
+template <typename C> struct GridEntry;
+template <> struct __align__(8) GridEntry<uint32_t> { int j; uint32_t s; };
+template <> struct __align__(16) GridEntry<uint64_t> { int j; int pad; uint64_t s; };
 
 __device__ __forceinline__ SegDesc load_desc(const SegDesc *p)
 {
     const int4 v = __ldg(reinterpret_cast<const int4 *>(p)); // one LDG.128 through the read-only path
     return SegDesc{v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ GridEntry<uint32_t> load_entry(const GridEntry<uint32_t> *p)
+{
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+    return GridEntry<uint32_t>{(int)v.x, v.y};
+}
+__device__ __forceinline__ GridEntry<uint64_t> load_entry(const GridEntry<uint64_t> *p)
+{
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    return GridEntry<uint64_t>{(int)(uint32_t)v.x, 0, v.y};
 }
 
 // Everything a kernel needs to resolve one read; passed by value.
@@ -66,27 +90,31 @@ struct DevCtx {
     int consuming;
     int has_mask;
     uint32_t n_pool;
-    const uint32_t *__restrict__ pool;   // length table (K2)
-    const double *__restrict__ cdf;      // numpy-style cdf, replay path
+    const uint32_t *__restrict__ pool;    // length table (K2)
+    const double *__restrict__ cdf;       // numpy-style cdf, replay path
     const uint32_t *__restrict__ cdf_u32; // ceil(cdf * 2^32) saturated, native path
-    // target index: per barcode a run of "monotone layers" (starts AND ends ascending inside a layer), so
-    // the targets a read overlaps are one contiguous range per layer.
+    const uint16_t *__restrict__ cdf_lut; // [kCdfLut] barcode of the lowest u32 in each of kCdfLut equal slices
+    // target index: per barcode a run of "monotone layers" (starts AND ends ascending inside a layer), so the
+    // targets a read overlaps are one contiguous range per layer.  seg[b], b < B, is barcode b's first layer;
+    // its extra layers (nesting targets only) are seg[B + extra_off[b] ...].
     const C *__restrict__ ts;
     const C *__restrict__ te;
-    const int32_t *__restrict__ trow;    // original row of the sorted target
-    const SegDesc *__restrict__ seg;     // [n_seg] one descriptor per layer
-    const int32_t *__restrict__ tgrid;   // bucket grids of all layers
-    const int32_t *__restrict__ bc_seg;  // [B + 1] layers of barcode b: bc_seg[b] .. bc_seg[b+1]
+    const int32_t *__restrict__ trow;     // original row of the sorted target
+    const SegDesc *__restrict__ seg;
+    const GridEntry<C> *__restrict__ tgrid;
+    const int32_t *__restrict__ extra_off; // [B]
+    int any_extra;                         // some barcode has more than one layer
     i64 n_targets;
     // blocked index: group g < B is barcode g's tree, group B is "ALL"; inside a group sorted by
-    // (start, end) with a running max of ends for the lower bound.
+    // (start, end) with a running max of ends (pmax) as the grid key.
     const C *__restrict__ ms;
     const C *__restrict__ me;
     const C *__restrict__ mpmax;
     const double *__restrict__ mw;
-    const SegDesc *__restrict__ grp;     // [B + 1] one descriptor per group
-    const int32_t *__restrict__ mgrid;   // bucket grids of all groups (on the running max of ends)
+    const SegDesc *__restrict__ grp;      // [B + 1]
+    const GridEntry<C> *__restrict__ mgrid;
 };
+constexpr int kCdfLut = 1024;
 
 struct DevOut {
     u64 *tallies;      // [n_iter][T][3]
@@ -94,7 +122,7 @@ struct DevOut {
     u64 *n_bases;      // [n_iter]
     u64 *n_reads;      // [n_iter]
     int *status;       // [n_iter]
-    u64 *tile_sum;     // [n_iter][tiles_per_iter] counted-length sum of each bulk tile
+    u64 *tile_sum;     // [n_iter][tiles_per_iter] counted-length sum of each bulk tile (zeroed by the host call)
     int tiles_per_iter;
 };
 
@@ -108,8 +136,8 @@ struct PhiloxSrc {
     __device__ __forceinline__ i64 count(int) const { return 0x7fffffffffffffffLL; }
 
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *s_cdf, int it, i64 n, uint32_t &L,
-                                         C &start, int &bc) const
+    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint16_t *s_lut, int it, i64 n,
+                                         uint32_t &L, C &start, int &bc) const
     {
         const Philox4 r = philox4x32_10((uint32_t)n, 0u, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, k0, k1);
         L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool)); // uniform pick from the pool
@@ -121,13 +149,9 @@ struct PhiloxSrc {
             start = (C)__umul64hi(((u64)r.x << 32) | r.y, range);
         }
         int k = 0;
-        if (cx.n_barcodes > 1) { // searchsorted(cdf, u, side='right') on integer thresholds
-            int lo = 0, hi = cx.n_barcodes - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (s_cdf[mid] <= r.w) lo = mid + 1; else hi = mid;
-            }
-            k = lo;
+        if (cx.n_barcodes > 1) { // searchsorted(cdf, u, side='right') on integer thresholds: table start + short walk
+            k = s_lut[r.w >> 22];
+            while (k < cx.n_barcodes - 1 && s_cdf[k] <= r.w) ++k;
         }
         bc = k;
     }
@@ -158,8 +182,8 @@ struct DrawSrc {
     __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
 
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *, int it, i64 n, uint32_t &L, C &st,
-                                         int &bc) const
+    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *, const uint16_t *, int it, i64 n, uint32_t &L,
+                                         C &st, int &bc) const
     {
         const i64 g = seg[it] + n;
         L = (uint32_t)length[g];
@@ -184,8 +208,8 @@ struct ReadSrc {
     __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
 
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &, const uint32_t *, int it, i64 n, uint32_t &L, C &st,
-                                         int &bc) const
+    __device__ __forceinline__ void draw(const DevCtx<C> &, const uint32_t *, const uint16_t *, int it, i64 n, uint32_t &L,
+                                         C &st, int &bc) const
     {
         const i64 g = seg[it] + n;
         L = (uint32_t)length[g];
@@ -198,6 +222,34 @@ struct ReadSrc {
 
 // ---------------------------------------------------------------- per-read pipeline
 
+// First candidate of a run for a read starting at rs: one descriptor load (L1-resident) + one grid-entry load.
+template <typename C>
+struct Probe {
+    int a; // first candidate index
+    C s;   // its start (all ones when there is none)
+};
+template <typename C>
+__device__ __forceinline__ Probe<C> probe(const SegDesc *descs, int idx, const GridEntry<C> *grid, C rs)
+{
+    const SegDesc d = load_desc(descs + idx);
+    const GridEntry<C> e = load_entry(grid + d.grid_off + (int)((u64)rs >> (d.flags & 0xff)));
+    return Probe<C>{e.j, e.s};
+}
+
+// Index of the first interval in [a, next bucket's j] whose key exceeds rs, for crowded runs only.
+template <typename C>
+__device__ __forceinline__ int skip_crowded(const SegDesc &d, const GridEntry<C> *grid, const C *__restrict__ keys, int a, C rs)
+{
+    if (!(d.flags & 0x100)) return a;
+    int z = load_entry(grid + d.grid_off + (int)((u64)rs >> (d.flags & 0xff)) + 1).j;
+    if (z - a <= kCrowdedBucket) return a;
+    while (a < z) {
+        const int mid = (a + z) >> 1;
+        if (__ldg(keys + mid) <= rs) a = mid + 1; else z = mid;
+    }
+    return a;
+}
+
 // K4: is [rs, re) blocked for barcode bc?  Trees: the barcode's own, then "ALL"; hits in (start, end)
 // order; one uniform per visited hit; u < weight blocks (read_operations.py:59-67).
 template <typename C, typename Src>
@@ -206,16 +258,11 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
     int j = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        const SegDesc d = load_desc(cx.grp + (pass == 0 ? bc : cx.n_barcodes));
-        const int hi = d.hi;
-        if (d.lo == hi) continue;
-        const int32_t *gp = cx.mgrid + d.grid_off + (int)(rs >> d.shift);
-        int a = __ldg(gp), z = __ldg(gp + 1); // first interval whose running max of ends exceeds rs
-        while (a < z) {
-            const int mid = (a + z) >> 1;
-            if (__ldg(cx.mpmax + mid) <= rs) a = mid + 1; else z = mid;
-        }
-        for (int k = a; k < hi; ++k) {
+        const int g = pass == 0 ? bc : cx.n_barcodes;
+        const Probe<C> p = probe(cx.grp, g, cx.mgrid, rs);
+        if (p.s >= re) continue;
+        const SegDesc d = load_desc(cx.grp + g);
+        for (int k = skip_crowded(d, cx.mgrid, cx.mpmax, p.a, rs); k < d.hi; ++k) {
             if (__ldg(cx.ms + k) >= re) break;
             if (__ldg(cx.me + k) > rs) {
                 const double u = src.block_u(it, n, j++);
@@ -226,37 +273,54 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
     return false;
 }
 
-// K6 + K7: add (sign = +1) or take back (sign = -1) the read's contribution to every target it overlaps.
+// K6 + K7 for one layer whose first candidate starts before the read's end: walk the candidates and add
+// (sign = +1) or take back (sign = -1) the read's contribution (counting.py:40-57).
 template <typename C, typename Src>
-__device__ __forceinline__ void tally_read(const DevCtx<C> &cx, const Src &src, u64 *__restrict__ tallies_it, int it,
-                                           i64 n, C rs, C re, int bc, i64 sign)
+__device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src, u64 *__restrict__ tallies_it, int it, i64 n,
+                                         int sg, int a, C rs, C re, i64 sign)
 {
-    const int s0 = __ldg(cx.bc_seg + bc), s1 = __ldg(cx.bc_seg + bc + 1);
-#pragma unroll 1
-    for (int sg = s0; sg < s1; ++sg) {
-        const SegDesc d = load_desc(cx.seg + sg);
-        const int hi = d.hi;
-        const int32_t *gp = cx.tgrid + d.grid_off + (int)(rs >> d.shift);
-        int a = __ldg(gp), z = __ldg(gp + 1); // first target of the layer with end > rs (ends ascend inside a layer)
-        while (a < z) {
-            const int mid = (a + z) >> 1;
-            if (__ldg(cx.te + mid) <= rs) a = mid + 1; else z = mid;
-        }
-        for (int j = a; j < hi; ++j) {
-            const C s = __ldg(cx.ts + j);
-            if (s >= re) break; // starts ascend: nothing further overlaps
-            const C e = __ldg(cx.te + j);
-            const C ov = (e < re ? e : re) - (s > rs ? s : rs);
-            if ((i64)ov >= cx.min_overlap) {
-                const int row = __ldg(cx.trow + j);
-                if (cx.scaling < 1.0 && !(src.scale_u(it, n, row) <= cx.scaling)) continue;
-                const bool full = rs <= s && e <= re;
-                u64 *t = tallies_it + (i64)row * 3;
-                atomicAdd(t + (full ? 0 : 1), (u64)sign);
-                atomicAdd(t + 2, (u64)(sign * (i64)ov));
-            }
+    const SegDesc d = load_desc(cx.seg + sg);
+    for (int j = skip_crowded(d, cx.tgrid, cx.te, a, rs); j < d.hi; ++j) {
+        const C s = __ldg(cx.ts + j);
+        if (s >= re) break; // starts ascend: nothing further overlaps
+        const C e = __ldg(cx.te + j);
+        if (e <= rs) continue; // ends inside the bucket but before the read
+        const C ov = (e < re ? e : re) - (s > rs ? s : rs);
+        if ((i64)ov >= cx.min_overlap) {
+            const int row = __ldg(cx.trow + j);
+            if (cx.scaling < 1.0 && !(src.scale_u(it, n, row) <= cx.scaling)) continue;
+            const bool full = rs <= s && e <= re;
+            u64 *t = tallies_it + (i64)row * 3;
+            atomicAdd(t + (full ? 0 : 1), (u64)sign);
+            atomicAdd(t + 2, (u64)(sign * (i64)ov));
         }
     }
+}
+
+// Extra layers of barcode bc (only when its targets nest).
+template <typename C, typename Src>
+__device__ __forceinline__ void tally_extra_layers(const DevCtx<C> &cx, const Src &src, u64 *__restrict__ tallies_it, int it,
+                                                i64 n, int bc, int n_extra, C rs, C re, i64 sign)
+{
+    const int s0 = cx.n_barcodes + __ldg(cx.extra_off + bc);
+    for (int sg = s0; sg < s0 + n_extra; ++sg) {
+        const Probe<C> p = probe(cx.seg, sg, cx.tgrid, rs);
+        if (p.s < re) tally_layer(cx, src, tallies_it, it, n, sg, p.a, rs, re, sign);
+    }
+}
+
+// All layers of the read's barcode: probe each layer, walk its candidates when the first one starts before
+// the read's end.  Out of line: the bulk kernel only calls it for the few reads whose first-layer probe says
+// "maybe" (or when some barcode has nesting targets), the cut-off kernel for every read.
+template <typename C, typename Src>
+__device__ __forceinline__ void tally_read(const DevCtx<C> &cx, const Src &src, u64 *__restrict__ tallies_it, int it,
+                                        i64 n, C rs, C re, int bc, i64 sign)
+{
+    const SegDesc d = load_desc(cx.seg + bc);
+    const GridEntry<C> e = load_entry(cx.tgrid + d.grid_off + (int)((u64)rs >> (d.flags & 0xff)));
+    if (e.s < re) tally_layer(cx, src, tallies_it, it, n, bc, e.j, rs, re, sign);
+    const int n_extra = (int)((uint32_t)d.flags >> 16);
+    if (n_extra) tally_extra_layers(cx, src, tallies_it, it, n, bc, n_extra, rs, re, sign);
 }
 
 // Resolve label + counted length of one drawn read (read_operations.py:104-121).
@@ -305,33 +369,41 @@ __device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
 
 // ---------------------------------------------------------------- bulk kernel
 
-// Persistent flat grid; CTA c owns a contiguous run of (iteration, tile) pairs so the per-iteration
-// counters are flushed once per iteration change, not once per tile.  One launch covers the absolute tiles
-// [tile0, tile0 + tiles_launch) of every iteration; inside that window iteration `it` owns the draws
+// Persistent flat grid; CTA c owns a contiguous run of (iteration, tile) pairs.  One launch covers the absolute
+// tiles [tile0, tile0 + tiles_launch) of every iteration; inside that window iteration `it` owns the draws
 // [lo(it), hi(it)) (lo is a multiple of the tile size).  Draw indices are < 2^32 (checked on the host).
-template <typename C, typename Src>
-__global__ void __launch_bounds__(kBulkBlock)
-k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__restrict__ lo_arr,
+//
+// A thread resolves kBulkIpt reads per tile in PHASES, each phase running over all its reads before the next
+// starts, so the dependent memory accesses of different reads overlap (pool gather -> start -> grid entry are
+// two L2 round trips per read; four reads in flight hide them):
+//   1 draw  2 blocked probes / slow path  3 label histogram  4 target probes / slow path  5 tile sum
+// There is no block barrier inside the tile loop: warps only meet when the CTA moves to the next iteration and
+// flushes its shared label histogram.
+template <typename C, typename Src, bool kMask>
+__global__ void __launch_bounds__(kBulkBlock, kBulkMinBlocks)
+k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src src, const DevOut out, const i64 *__restrict__ lo_arr,
                    const i64 lo_const, const i64 *__restrict__ hi_arr, const i64 hi_const, const int tile0,
                    const int tiles_launch, const i64 total_tiles)
 {
     extern __shared__ u64 smem[];
-    u64 *s_part = smem;                                   // [kBulkBlock / 32]
-    int *s_hist = (int *)(s_part + kBulkBlock / 32);      // [B + 2] reads per label since the last flush
+    int *s_hist = (int *)smem;                                  // [B + 2] reads per label since the last flush
     uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2); // [B]
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint16_t *s_lut = (uint16_t *)(s_cdf + cx.n_barcodes);      // [kCdfLut]
+    const int tid = threadIdx.x, lane = tid & 31;
     const int B = cx.n_barcodes;
     for (int i = tid; i < B + 2; i += kBulkBlock) s_hist[i] = 0;
-    if (!Src::kHasLabel && cx.cdf_u32)
+    if (!Src::kHasLabel && cx.cdf_u32 && B > 1) {
         for (int i = tid; i < B; i += kBulkBlock) s_cdf[i] = cx.cdf_u32[i];
+        for (int i = tid; i < kCdfLut; i += kBulkBlock) s_lut[i] = cx.cdf_lut[i];
+    }
     __syncthreads();
 
     const i64 per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
     const i64 t0 = (i64)blockIdx.x * per_cta;
     const i64 t1 = t0 + per_cta < total_tiles ? t0 + per_cta : total_tiles;
-    const bool plain_labels = !Src::kHasLabel && B == 1 && !cx.has_mask; // every read is label 0
+    const bool plain_labels = !Src::kHasLabel && B == 1 && !kMask; // every read is label 0
     int cur_it = -1;
-    u64 acc_bases = 0, acc_reads = 0; // thread 0 only
+    u64 acc_bases = 0, acc_reads = 0; // lane 0 of each warp / thread 0
     uint32_t lo = 0, hi = 0;
     u64 *tallies_it = nullptr;
 
@@ -343,12 +415,12 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
                 __syncthreads();
                 for (int i = tid; i < B + 2; i += kBulkBlock)
                     if (s_hist[i]) { atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
+                if (lane == 0 && acc_bases) atomicAdd(out.n_bases + cur_it, acc_bases);
                 if (tid == 0) {
-                    atomicAdd(out.n_bases + cur_it, acc_bases);
                     atomicAdd(out.n_reads + cur_it, acc_reads);
                     if (plain_labels) atomicAdd(out.label_counts + (i64)cur_it * (B + 2), acc_reads);
-                    acc_bases = acc_reads = 0;
                 }
+                acc_bases = acc_reads = 0;
                 __syncthreads();
             }
             cur_it = it;
@@ -360,46 +432,81 @@ k_place_tally_bulk(const DevCtx<C> cx, const Src src, const DevOut out, const i6
         }
         const uint32_t base = (uint32_t)t * kBulkTile;
         if (base < lo || base >= hi) continue; // tile outside this iteration's range (block-uniform)
+        const bool full_tile = hi - base >= (uint32_t)kBulkTile;
+
         uint32_t L[kBulkIpt];
         C st[kBulkIpt];
-        int bc[kBulkIpt];
+        int label[kBulkIpt];
 #pragma unroll
-        for (int i = 0; i < kBulkIpt; ++i) { // phase 1: independent draws + table gathers in flight together
+        for (int i = 0; i < kBulkIpt; ++i) { // phase 1: draws (Philox, pool gather, start, barcode)
             const uint32_t n = base + i * kBulkBlock + tid;
-            L[i] = 0; st[i] = 0; bc[i] = 0;
-            if (n < hi) src.draw(cx, s_cdf, it, (i64)n, L[i], st[i], bc[i]);
+            L[i] = 0; st[i] = 0; label[i] = kLabelInvalid;
+            if (full_tile || n < hi) src.draw(cx, s_cdf, s_lut, it, (i64)n, L[i], st[i], label[i]);
         }
         u64 my = 0;
+        if (!Src::kHasLabel && kMask) { // phase 2: blocked regions -- probe both trees for all reads, then the slow path
+            C first[kBulkIpt]; // smallest start among the first candidates of the barcode tree and the "ALL" tree
 #pragma unroll
-        for (int i = 0; i < kBulkIpt; ++i) { // phase 2: blocked test, label, tally
-            const uint32_t n = base + i * kBulkBlock + tid;
-            const bool valid = n < hi;
-            int label = 0; uint32_t counted = 0;
-            if (valid) resolve_read(cx, src, it, (i64)n, L[i], st[i], bc[i], label, counted);
-            my += counted;
-            if (!plain_labels) hist_add(s_hist, valid && label < B ? label_slot(label, B) : -1, 1);
-            if (valid && label >= 0 && label < B) tally_read(cx, src, tallies_it, it, (i64)n, st[i], (C)(st[i] + L[i]), label, 1);
+            for (int i = 0; i < kBulkIpt; ++i) {
+                const Probe<C> pa = probe(cx.grp, label[i] >= 0 ? label[i] : 0, cx.mgrid, st[i]);
+                const Probe<C> pb = probe(cx.grp, B, cx.mgrid, st[i]);
+                first[i] = pa.s < pb.s ? pa.s : pb.s;
+            }
+#pragma unroll
+            for (int i = 0; i < kBulkIpt; ++i) {
+                const C re = (C)(st[i] + L[i]);
+                uint32_t counted = L[i];
+                if (label[i] >= 0 && first[i] < re &&
+                    is_blocked(cx, src, it, (i64)(base + i * kBulkBlock + tid), label[i], st[i], re)) {
+                    label[i] = cx.consuming ? kLabelBlockedConsuming : kLabelBlockedNotConsuming;
+                    counted = cx.consuming ? L[i] : 0u;
+                }
+                my += counted;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kBulkIpt; ++i) my += (Src::kHasLabel && label[i] == kLabelBlockedNotConsuming) ? 0u : L[i];
         }
-        my = warp_sum(my);
-        if (lane == 0) s_part[wid] = my;
-        __syncthreads();
-        if (tid == 0) {
-            u64 s = 0;
+        if (!plain_labels) { // phase 3: label histogram
 #pragma unroll
-            for (int w = 0; w < kBulkBlock / 32; ++w) s += s_part[w];
-            out.tile_sum[(i64)it * out.tiles_per_iter + t] = s;
-            acc_bases += s;
+            for (int i = 0; i < kBulkIpt; ++i)
+                hist_add(s_hist, label[i] != kLabelInvalid && label[i] < B ? label_slot(label[i], B) : -1, 1);
+        }
+        { // phase 4: targets -- first layer probed for all reads, then the candidate walks of the few "maybe"s
+            Probe<C> pt[kBulkIpt];
+#pragma unroll
+            for (int i = 0; i < kBulkIpt; ++i) {
+                const bool ok = label[i] >= 0 && label[i] < B;
+                pt[i] = probe(cx.seg, ok ? label[i] : 0, cx.tgrid, st[i]);
+                if (!ok) pt[i].s = (C) ~(C)0;
+            }
+#pragma unroll
+            for (int i = 0; i < kBulkIpt; ++i) {
+                const C re = (C)(st[i] + L[i]);
+                const i64 n = (i64)(base + i * kBulkBlock + tid);
+                if (pt[i].s < re) tally_layer(cx, src, tallies_it, it, n, label[i], pt[i].a, st[i], re, 1);
+                if (cx.any_extra && label[i] >= 0 && label[i] < B) {
+                    const int n_extra = (int)((uint32_t)__ldg(&cx.seg[label[i]].flags) >> 16);
+                    if (n_extra) tally_extra_layers(cx, src, tallies_it, it, n, label[i], n_extra, st[i], re, 1);
+                }
+            }
+        }
+        my = warp_sum(my); // phase 5: tile sum (read only when the cut-off has to be taken back)
+        if (lane == 0) {
+            if (my) atomicAdd(out.tile_sum + (i64)it * out.tiles_per_iter + t, my);
+            acc_bases += my;
+        }
+        if (tid == 0) {
             const uint32_t left = hi - base;
             acc_reads += left < (uint32_t)kBulkTile ? left : (uint32_t)kBulkTile;
         }
-        __syncthreads();
     }
     if (cur_it >= 0) {
         __syncthreads();
         for (int i = tid; i < B + 2; i += kBulkBlock)
             if (s_hist[i]) atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, (u64)(uint32_t)s_hist[i]);
+        if (lane == 0 && acc_bases) atomicAdd(out.n_bases + cur_it, acc_bases);
         if (tid == 0) {
-            atomicAdd(out.n_bases + cur_it, acc_bases);
             atomicAdd(out.n_reads + cur_it, acc_reads);
             if (plain_labels) atomicAdd(out.label_counts + (i64)cur_it * (B + 2), acc_reads);
         }
@@ -456,21 +563,24 @@ __device__ __forceinline__ u64 block_excl_scan(u64 v, u64 *s_warp, u64 *total)
 
 template <typename C, typename Src>
 __global__ void __launch_bounds__(kTailBlock)
-k_cutoff_tail(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__restrict__ n_bulk_arr,
+k_cutoff_tail(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src src, const DevOut out, const i64 *__restrict__ n_bulk_arr,
               const i64 n_bulk_const)
 {
     extern __shared__ u64 smem[];
     u64 *s_warp = smem;                         // [33]
     int *s_hist = (int *)(smem + 40);           // [B + 2] signed deltas to the label counts
     uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2);
+    uint16_t *s_lut = (uint16_t *)(s_cdf + cx.n_barcodes);
     __shared__ i64 s_cut_tile;
     __shared__ u64 s_cut_prefix;
     const int tid = threadIdx.x;
     const int B = cx.n_barcodes;
     const int it = blockIdx.x;
     for (int i = tid; i < B + 2; i += kTailBlock) s_hist[i] = 0;
-    if (!Src::kHasLabel && cx.cdf_u32)
+    if (!Src::kHasLabel && cx.cdf_u32 && B > 1) {
         for (int i = tid; i < B; i += kTailBlock) s_cdf[i] = cx.cdf_u32[i];
+        for (int i = tid; i < kCdfLut; i += kTailBlock) s_lut[i] = cx.cdf_lut[i];
+    }
     if (tid == 0) { s_cut_tile = -1; s_cut_prefix = 0; }
     __syncthreads();
 
@@ -528,7 +638,7 @@ k_cutoff_tail(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__
             valid[i] = idx < n_end;
             L[i] = 0; st[i] = 0; bc[i] = 0; label[i] = 0; counted[i] = 0;
             if (valid[i]) {
-                src.draw(cx, s_cdf, it, idx, L[i], st[i], bc[i]);
+                src.draw(cx, s_cdf, s_lut, it, idx, L[i], st[i], bc[i]);
                 resolve_read(cx, src, it, idx, L[i], st[i], bc[i], label[i], counted[i]);
                 mine += counted[i];
             }
@@ -576,16 +686,18 @@ k_cutoff_tail(const DevCtx<C> cx, const Src src, const DevOut out, const i64 *__
 // Write the first n_reads draws of one native iteration in draw order (coverage track / overlap lists).
 template <typename C>
 __global__ void __launch_bounds__(256)
-k_materialize(const DevCtx<C> cx, const PhiloxSrc src, const i64 n_reads, i64 *__restrict__ o_start,
+k_materialize(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ PhiloxSrc src, const i64 n_reads, i64 *__restrict__ o_start,
               i64 *__restrict__ o_length, int32_t *__restrict__ o_label)
 {
     extern __shared__ u64 smem[];
     uint32_t *s_cdf = (uint32_t *)smem;
+    uint16_t *s_lut = (uint16_t *)(s_cdf + cx.n_barcodes);
     for (int i = threadIdx.x; i < cx.n_barcodes; i += blockDim.x) s_cdf[i] = cx.cdf_u32[i];
+    for (int i = threadIdx.x; i < kCdfLut; i += blockDim.x) s_lut[i] = cx.cdf_lut[i];
     __syncthreads();
     for (i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x; n < n_reads; n += (i64)gridDim.x * blockDim.x) {
         uint32_t L, counted; C st; int bc, label;
-        src.draw(cx, s_cdf, 0, n, L, st, bc);
+        src.draw(cx, s_cdf, s_lut, 0, n, L, st, bc);
         resolve_read(cx, src, 0, n, L, st, bc, label, counted);
         o_start[n] = (i64)st;
         o_length[n] = (i64)L;
