@@ -607,7 +607,7 @@ int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_beg
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
     esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0};
-    esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iter_begin};
+    esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iter_begin, philox_keys((uint32_t)seed, (uint32_t)(seed >> 32))};
     const i64 n1 = bulk_reads(ctx, coverage);
     const i64 cap = (ctx->n_mask > 0 && !consuming) ? bulk_cap(ctx, coverage) : n1;
     const size_t tile_bytes = ws_tile_bytes(std::max(cap, n1), n_iter);
@@ -685,7 +685,7 @@ int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t 
     if (n_reads == 0) return ESL_OK;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iteration};
+    esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iteration, philox_keys((uint32_t)seed, (uint32_t)(seed >> 32))};
     const unsigned grid = (unsigned)std::min<i64>((n_reads + 255) / 256, (i64)ctx->sm_count * 8);
     const size_t sm = (size_t)ctx->B * 4 + (size_t)esl::kCdfLut * 2 + 16;
     if (ctx->wide)

@@ -131,6 +131,7 @@ struct DevOut {
 // Native stream.
 struct PhiloxSrc {
     uint32_t k0, k1, combo, iter_begin;
+    PhiloxKeys keys; // round keys of (k0, k1), filled by the host
     static constexpr bool kHasLabel = false;
     static constexpr bool kBounded = false;
     __device__ __forceinline__ i64 count(int) const { return 0x7fffffffffffffffLL; }
@@ -139,7 +140,7 @@ struct PhiloxSrc {
     __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint16_t *s_lut, int it, i64 n,
                                          uint32_t &L, C &start, int &bc) const
     {
-        const Philox4 r = philox4x32_10((uint32_t)n, 0u, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, k0, k1);
+        const Philox4 r = philox4x32_10((uint32_t)n, 0u, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, keys);
         L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool)); // uniform pick from the pool
         const u64 range = cx.G - (u64)L;               // start ~ U{0 .. G-L-1} = floor(u64 * range / 2^64)
         if (sizeof(C) == 4) { // range < 2^32: two 32x32->64 products instead of a 64x64 high multiply
@@ -265,8 +266,10 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
         for (int k = skip_crowded(d, cx.mgrid, cx.mpmax, p.a, rs); k < d.hi; ++k) {
             if (__ldg(cx.ms + k) >= re) break;
             if (__ldg(cx.me + k) > rs) {
+                const double w = __ldg(cx.mw + k);
+                if (!Src::kBounded && w >= 1.0) return true; // u < 1 <= w for every u: no need to draw it
                 const double u = src.block_u(it, n, j++);
-                if (u < __ldg(cx.mw + k)) return true;
+                if (u < w) return true;
             }
         }
     }

@@ -36,6 +36,33 @@ ESL_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     return Philox4{c0, c1, c2, c3};
 }
 
+// Round keys of one Philox key, computed once per kernel so the ten key bumps are not redone for every draw.
+struct PhiloxKeys {
+    uint32_t a[10], b[10];
+};
+ESL_HD PhiloxKeys philox_keys(uint32_t k0, uint32_t k1)
+{
+    PhiloxKeys k;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { k.a[r] = k0 + (uint32_t)r * 0x9E3779B9u; k.b[r] = k1 + (uint32_t)r * 0xBB67AE85u; }
+    return k;
+}
+ESL_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.a[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.b[r];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
 // 53-bit uniform in [0,1) from two words, the same construction numpy's legacy stream uses.
 ESL_HD double u53(uint32_t a, uint32_t b)
 {
