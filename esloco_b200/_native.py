@@ -34,6 +34,8 @@ SYMBOLS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "esl_materialize_reads": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esl_coverage_bins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p]),
     "esl_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "esl_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "esl_get_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

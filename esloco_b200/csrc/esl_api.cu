@@ -534,20 +534,25 @@ int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n)
 {
     if (!ctx) return ESL_ERR_INVALID;
     if (!lengths || n < 1 || n > 0xFFFFFFFFll) return ctx->fail(ESL_ERR_INVALID, "length table must hold 1 .. 2^32-1 entries");
-    long double s = 0, s2 = 0;
-    uint32_t mx = 0;
+    // exact integer moments of the pool: sum in u64, sum of squares in 128 bits (n < 2^32, L < 2^32)
+    u64 s = 0;
+    unsigned __int128 s2 = 0;
+    uint32_t mx = 0, mn = 0xFFFFFFFFu;
     for (int64_t i = 0; i < n; ++i) {
-        if (lengths[i] == 0) return ctx->fail(ESL_ERR_INVALID, "length table entry %lld is 0", (long long)i);
-        s += lengths[i];
-        s2 += (long double)lengths[i] * lengths[i];
+        const u64 v = lengths[i];
+        s += v;
+        s2 += v * v;
         mx = std::max(mx, lengths[i]);
+        mn = std::min(mn, lengths[i]);
     }
+    if (mn == 0) return ctx->fail(ESL_ERR_INVALID, "length table holds a zero-length read");
     CU(cudaSetDevice(ctx->device));
     CU(ctx->d_pool.upload(lengths, (size_t)n * sizeof(uint32_t)));
     ctx->n_pool = (uint32_t)n;
     ctx->pool_max = mx;
-    ctx->pool_mean = (double)(s / n);
-    const long double var = s2 / n - (s / n) * (s / n);
+    const long double mean = (long double)s / (long double)n;
+    const long double var = (long double)s2 / (long double)n - mean * mean;
+    ctx->pool_mean = (double)mean;
     ctx->pool_sd = var > 0 ? (double)sqrtl(var) : 0.0;
     ctx->have_pool = true;
     return ESL_OK;
@@ -692,6 +697,24 @@ int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t 
         esl::k_materialize<uint64_t><<<grid, 256, sm, st>>>(make_devctx<uint64_t>(ctx, 0.0, consuming, 1, 1.0), src, n_reads, d_start, d_length, d_label);
     else
         esl::k_materialize<uint32_t><<<grid, 256, sm, st>>>(make_devctx<uint32_t>(ctx, 0.0, consuming, 1, 1.0), src, n_reads, d_start, d_length, d_label);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return ESL_OK;
+}
+
+int esl_coverage_bins(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,
+                      int64_t n_reads, int64_t bin_size, int64_t n_bins, int64_t *d_bins, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n_reads < 0 || bin_size < 1 || n_bins < 1 || !d_bins || (n_reads && (!d_start || !d_length || !d_label)))
+        return ctx->fail(ESL_ERR_INVALID, "bad arguments");
+    if (ctx->B <= 0) return ctx->fail(ESL_ERR_STATE, "esl_set_barcode_cdf has not been called");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(d_bins, 0, (size_t)(ctx->B + 2) * (size_t)n_bins * sizeof(int64_t), st));
+    if (n_reads == 0) return ESL_OK;
+    const unsigned grid = (unsigned)std::min<i64>((n_reads + 255) / 256, (i64)ctx->sm_count * 8);
+    esl::k_coverage_bins<<<grid, 256, 0, st>>>(d_start, d_length, d_label, n_reads, bin_size, n_bins, ctx->B, (u64 *)d_bins);
     CU(cudaGetLastError());
     ctx->launches++;
     return ESL_OK;

@@ -708,6 +708,26 @@ k_materialize(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Phil
     }
 }
 
+// Binned coverage track of materialised reads (coverage.py:52-64,76-81 without the genome-length arrays): bins
+// [label slot][bin] accumulate the number of read bases falling into each bin; the host divides by the bin
+// width to get the reference's per-bin mean coverage.  One read per thread, a read spans few bins.
+__global__ void __launch_bounds__(256)
+k_coverage_bins(const i64 *__restrict__ start, const i64 *__restrict__ length, const int32_t *__restrict__ label,
+                const i64 n_reads, const i64 bin_size, const i64 n_bins, const int n_barcodes, u64 *__restrict__ bins)
+{
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (i64)gridDim.x * blockDim.x) {
+        const int lab = label[r];
+        if (lab >= n_barcodes) continue;
+        const i64 s = start[r], e = s + length[r];
+        u64 *row = bins + (i64)label_slot(lab, n_barcodes) * n_bins;
+        for (i64 b = s / bin_size; b < n_bins && b * bin_size < e; ++b) {
+            const i64 lo = b * bin_size > s ? b * bin_size : s;
+            const i64 hi = (b + 1) * bin_size < e ? (b + 1) * bin_size : e;
+            if (hi > lo) atomicAdd(row + b, (u64)(hi - lo));
+        }
+    }
+}
+
 // Per-target moment accumulators over the iterations of a batch (operand of the multi-GPU sum-reduce).
 __global__ void __launch_bounds__(256)
 k_moments(const i64 *__restrict__ tallies, const int n_iter, const i64 n_targets, i64 *__restrict__ mom)

@@ -182,6 +182,15 @@ class Engine:
                                                    lab.data_ptr(), self._stream()))
         return s, ln, lab
 
+    def coverage_bins(self, start, length, label, bin_size):
+        """[n_barcodes+2, n_bins] int64 read bases per bin and label slot for device-resident reads."""
+        t = self.torch
+        n_bins = -(-self.genome_size // int(bin_size))
+        bins = t.empty((self.n_barcodes + 2, n_bins), dtype=t.int64, device=self.tdev)
+        self._check(self.lib.esl_coverage_bins(self.ctx, start.data_ptr(), length.data_ptr(), label.data_ptr(),
+                                               int(start.numel()), int(bin_size), n_bins, bins.data_ptr(), self._stream()))
+        return bins
+
     def moments(self, tallies, acc=None):
         """acc[T, 8] += per-target moment sums over the iterations in `tallies` (operand of the NCCL reduce)."""
         t = self.torch

@@ -88,8 +88,6 @@ def run(param_dictionary):
         logging.error("Error: Invalid mode selected.")
         sys.exit(1)
     masked_tree = build_mask_tree(masked_regions) if masked_regions else masked_regions
-    if not p["no_cov_plots"]:
-        logging.info("Coverage plots are produced by the reference's plotting layer and are not part of this engine.")
 
     combos = p["combinations"]
     mine = shard_iterations(p["iterations"], rank, ws)
@@ -103,6 +101,17 @@ def run(param_dictionary):
         for c, res in enumerate(batches):
             if (res.status & 2).any().item():
                 raise RuntimeError("coverage not reached")
+            if chunk[0] == 0 and not p["no_cov_plots"]:
+                # first iteration of every combination (combined_calculations.py:66-74): the binned track behind the
+                # reference's coverage plot, written as a table; drawing it is left to the plotting layer
+                from .coverage import binned_coverage, write_coverage_track
+                from .combined_calculations import _length_pool_key_and_factory
+                mrl, cov = combos[c]
+                key, factory = _length_pool_key_and_factory(int(p.get("seed", 0)), c, mrl, p.get("sequenced_data_path"),
+                                                            p["sigma"], p["min_read_length"])
+                sess.set_pool(key, factory)
+                track = binned_coverage(sess.engine, int(p.get("seed", 0)), c, 0, p["consuming"], int(res.n_reads[0]))
+                write_coverage_track(os.path.join(p["output_path_plots"], f"{mrl}_{cov}_coverage.tsv"), *track)
             moments[c] = sess.engine.moments(res.tallies, moments[c])
             tallies[c].append(res.tallies); labels[c].append(res.label_counts); nbases[c].append(res.n_bases)
     if not len(mine):  # a rank without iterations still takes part in the collectives

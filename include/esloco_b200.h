@@ -140,6 +140,13 @@ int esl_replay_draws(esl_ctx *ctx, const double *d_u_barcode, const int64_t *d_l
 int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iteration, int32_t consuming,
                           int64_t n_reads, int64_t *d_start, int64_t *d_length, int32_t *d_label, void *stream);
 
+/* Binned coverage track of materialised reads, replacing the genome-length float64 arrays of the first-iteration
+ * coverage plot (coverage.py:52-64,76-81), which cannot be allocated at hg38 size: d_bins [n_barcodes+2][n_bins]
+ * receives the number of read bases per bin and label slot (barcodes, Blocked/Consuming, Blocked/NotConsuming);
+ * bin b covers [b*bin_size, (b+1)*bin_size).  Zeroes d_bins first. */
+int esl_coverage_bins(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,
+                      int64_t n_reads, int64_t bin_size, int64_t n_bins, int64_t *d_bins, void *stream);
+
 /* Per-target moment accumulators over iterations, the operand of the multi-GPU sum-reduce that replaces the
  * joblib result gather + pandas groupby (esloco.py:149-158,183-195):
  *   d_moments [n_targets][ESL_MOMENT_COLS] += {n, sum f, sum f^2, sum p, sum p^2, sum b, lo32(sum b^2), hi(sum b^2)}

@@ -114,3 +114,36 @@ def test_count_matches_mirror(tmp_path):
     assert [d["on_target_bases"] for d in out] == g.combo(0, "otb").tolist()
     hist = count_barcode_occurrences(reads)
     assert list(hist) == m["combos"][0]["label_order"] and list(hist.values()) == g.combo(0, "label_counts").tolist()
+
+
+def test_binned_coverage_track_matches_per_base_arrays(tmp_path):
+    """Binned coverage (device) == the reference's per-base array + bin means (coverage.py:52-64,76-81), small genome."""
+    from esloco_b200.coverage import binned_coverage
+    from esloco_b200.session import get_session
+    from esloco_b200.utils import build_mask_tree
+    G, bin_size = 203_000, 10_000  # last bin is truncated
+    sess = get_session(0)
+    tree = build_mask_tree({"m": {"start": 50_000, "end": 80_000, "weight": 1, "barcode": []}})
+    sess.invalidate()
+    sess.configure(G, {"T_0": {"start": 10, "end": 20}}, tree, 2, {"0": 3})
+    rng = np.random.RandomState(3)
+    pool = rng.randint(200, 30_000, 5000)
+    sess.set_pool(("covtest",), lambda: pool)
+    eng = sess.engine
+    res = eng.run_batch(11, 0, 0, 1, 8.0, consuming=True).cpu()
+    n = int(res.n_reads[0])
+    pos, raw, smoothed = binned_coverage(eng, 11, 0, 0, True, n, bin_size)
+    s, ln, lab = (x.cpu().numpy() for x in eng.materialize_reads(11, 0, 0, True, n))
+    names = {0: "0", 1: "1", -1: "Blocked/Consuming"}
+    n_bins = -(-G // bin_size)
+    for key in ["Combined"] + list(names.values()):
+        cov = np.zeros(G)
+        for a, l_, b in zip(s, ln, lab):
+            if key == "Combined" or names[int(b)] == key:
+                cov[a:a + l_] += 1
+        ref = np.array([cov[i * bin_size:(i + 1) * bin_size].mean() for i in range(n_bins)])
+        assert np.allclose(raw[key], ref, rtol=1e-12, atol=1e-12), key
+    assert set(raw) == {"Combined", "0", "1", "Blocked/Consuming"}
+    from scipy.ndimage import gaussian_filter1d
+    assert np.allclose(smoothed["Combined"], gaussian_filter1d(raw["Combined"], 3))
+    assert abs(raw["Combined"].mean() - 8.0) < 1.0

@@ -130,3 +130,11 @@ def test_world_size_2_gloo_reduce_and_gather(n_iter):
     got = acc.astype(object)
     assert np.array_equal(got[:, :6], exp[:, :6])
     assert [int(h) * 2**32 + int(l) for h, l in zip(got[:, 7], got[:, 6])] == [int(h) * 2**32 + int(l) for h, l in zip(exp[:, 7], exp[:, 6])]
+
+
+def test_gaussian_filter_matches_scipy():
+    from scipy.ndimage import gaussian_filter1d as ref
+    from esloco_b200.coverage import gaussian_filter1d
+    for n in (1, 4, 13, 500, 3100):
+        x = np.random.RandomState(n).rand(n) * 30
+        assert np.allclose(gaussian_filter1d(x, 3), ref(x, 3))
