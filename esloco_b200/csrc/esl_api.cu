@@ -70,7 +70,7 @@ struct esl_ctx {
     uint32_t n_pool = 0, pool_max = 0;
     double pool_mean = 0, pool_sd = 0;
 
-    DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_ts, d_te, d_trow, d_seg, d_tgrid, d_extra_off, d_ms, d_me, d_mpmax, d_mw, d_grp, d_mgrid;
+    DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_ms, d_me, d_mpmax, d_mw, d_grp, d_mgrid;
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
 
     // optional per-kernel timing (esl_set_profiling): events around the bulk and the cut-off kernel
@@ -202,9 +202,19 @@ int upload_index(esl_ctx *ctx)
     std::vector<esl::SegDesc> seg(first);
     seg.insert(seg.end(), extra.begin(), extra.end());
     ctx->n_indexed = (i64)ts.size();
-    CU(ctx->d_ts.upload(ts.data(), ts.size() * sizeof(C)));
+    std::vector<esl::TargetRec<C>> trec(ts.size());
+    {
+        size_t j = 0;
+        for (const esl::SegDesc &d : seg)
+            for (int k = d.lo; k < d.hi; ++k, ++j) {
+                esl::TargetRec<C> r{};
+                r.s = ts[k]; r.e = te[k]; r.row = trow[k];
+                r.s_next = k + 1 < d.hi ? ts[k + 1] : (C) ~(C)0;
+                trec[k] = r;
+            }
+    }
+    CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>)));
     CU(ctx->d_te.upload(te.data(), te.size() * sizeof(C)));
-    CU(ctx->d_trow.upload(trow.data(), trow.size() * sizeof(int32_t)));
     CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc)));
     CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(esl::GridEntry<C>)));
     CU(ctx->d_extra_off.upload(extra_off.data(), extra_off.size() * sizeof(int32_t)));
@@ -292,9 +302,8 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.cdf = ctx->d_cdf.as<double>();
     d.cdf_u32 = ctx->d_cdf_u32.as<uint32_t>();
     d.cdf_lut = ctx->d_cdf_lut.as<uint16_t>();
-    d.ts = ctx->d_ts.as<C>();
+    d.trec = ctx->d_trec.as<esl::TargetRec<C>>();
     d.te = ctx->d_te.as<C>();
-    d.trow = ctx->d_trow.as<int32_t>();
     d.seg = ctx->d_seg.as<esl::SegDesc>();
     d.tgrid = ctx->d_tgrid.as<esl::GridEntry<C>>();
     d.extra_off = ctx->d_extra_off.as<int32_t>();

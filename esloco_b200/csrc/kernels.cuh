@@ -63,6 +63,23 @@ template <typename C> struct GridEntry;
 template <> struct __align__(8) GridEntry<uint32_t> { int j; uint32_t s; };
 template <> struct __align__(16) GridEntry<uint64_t> { int j; int pad; uint64_t s; };
 
+// One indexed target: start, end, original row and the start of the next target of the layer (all ones at the
+// end), so a candidate walk needs one 16-byte load per candidate and none to find out that it is over.
+template <typename C> struct TargetRec;
+template <> struct __align__(16) TargetRec<uint32_t> { uint32_t s, e; int row; uint32_t s_next; };
+template <> struct __align__(16) TargetRec<uint64_t> { uint64_t s, e, s_next; int row; int pad; };
+__device__ __forceinline__ TargetRec<uint32_t> load_rec(const TargetRec<uint32_t> *p)
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return TargetRec<uint32_t>{v.x, v.y, (int)v.z, v.w};
+}
+__device__ __forceinline__ TargetRec<uint64_t> load_rec(const TargetRec<uint64_t> *p)
+{
+    const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(p) + 1);
+    return TargetRec<uint64_t>{a.x, a.y, b.x, (int)(uint32_t)b.y, 0};
+}
+
 __device__ __forceinline__ SegDesc load_desc(const SegDesc *p)
 {
     const int4 v = __ldg(reinterpret_cast<const int4 *>(p)); // one LDG.128 through the read-only path
@@ -97,9 +114,8 @@ struct DevCtx {
     // target index: per barcode a run of "monotone layers" (starts AND ends ascending inside a layer), so the
     // targets a read overlaps are one contiguous range per layer.  seg[b], b < B, is barcode b's first layer;
     // its extra layers (nesting targets only) are seg[B + extra_off[b] ...].
-    const C *__restrict__ ts;
-    const C *__restrict__ te;
-    const int32_t *__restrict__ trow;     // original row of the sorted target
+    const TargetRec<C> *__restrict__ trec; // targets in layer order
+    const C *__restrict__ te;              // their ends again, contiguous (bisect key of crowded buckets)
     const SegDesc *__restrict__ seg;
     const GridEntry<C> *__restrict__ tgrid;
     const int32_t *__restrict__ extra_off; // [B]
@@ -284,19 +300,17 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
 {
     const SegDesc d = load_desc(cx.seg + sg);
     for (int j = skip_crowded(d, cx.tgrid, cx.te, a, rs); j < d.hi; ++j) {
-        const C s = __ldg(cx.ts + j);
-        if (s >= re) break; // starts ascend: nothing further overlaps
-        const C e = __ldg(cx.te + j);
-        if (e <= rs) continue; // ends inside the bucket but before the read
-        const C ov = (e < re ? e : re) - (s > rs ? s : rs);
-        if ((i64)ov >= cx.min_overlap) {
-            const int row = __ldg(cx.trow + j);
-            if (cx.scaling < 1.0 && !(src.scale_u(it, n, row) <= cx.scaling)) continue;
-            const bool full = rs <= s && e <= re;
-            u64 *t = tallies_it + (i64)row * 3;
-            atomicAdd(t + (full ? 0 : 1), (u64)sign);
-            atomicAdd(t + 2, (u64)(sign * (i64)ov));
+        const TargetRec<C> r = load_rec(cx.trec + j);
+        if (r.s >= re) break; // starts ascend: nothing further overlaps
+        if (r.e > rs) {       // (an end inside the bucket but before the read does not overlap)
+            const C ov = (r.e < re ? r.e : re) - (r.s > rs ? r.s : rs);
+            if ((i64)ov >= cx.min_overlap && !(cx.scaling < 1.0 && !(src.scale_u(it, n, r.row) <= cx.scaling))) {
+                u64 *t = tallies_it + (i64)r.row * 3;
+                atomicAdd(t + ((rs <= r.s && r.e <= re) ? 0 : 1), (u64)sign);
+                atomicAdd(t + 2, (u64)(sign * (i64)ov));
+            }
         }
+        if (r.s_next >= re) break; // known without touching the next record
     }
 }
 

@@ -334,3 +334,40 @@ def test_error_behaviour(eng):
         eng.set_targets([-5], [10], [0])
     with pytest.raises(EngineError):
         eng.set_barcode_cdf([0.5, 0.2])
+
+
+def test_full_size_config2_consistency(eng):
+    """BASELINE.json configs[1] at FULL size (hg38-size genome, 30x, 100 insertions, ~6.2 M reads per iteration).
+    Size-independent properties: the native kernels, a level-1 replay of the materialised reads and the oracle's
+    indexed CPU tally of the same reads agree bit for bit; the cut-off is tight; batch splitting is invisible."""
+    from esloco_b200 import synthetic as S
+    from esloco_b200.utils import targets_to_arrays
+    G, _ = S.chromosome_dir(S.HG38)
+    targets = S.random_insertions(G, 100, 5000, 1, seed=2)
+    keys, ts, te, tb = targets_to_arrays(targets, 1)
+    pool = S.lognormal_lengths(15000, 1, 1, seed=1)
+    eng.set_genome(G)
+    eng.set_barcode_cdf([1.0])
+    eng.set_targets(ts, te, tb)
+    eng.set_blocked()
+    eng.set_length_table(pool)
+    cov, seed = 30, 20261019
+    res = eng.run_batch(seed, 0, 7, 3, cov).cpu()
+    thr = cov * G
+    nb, nr = res.n_bases.numpy(), res.n_reads.numpy()
+    assert (nb >= thr).all() and (nb - thr < pool.max()).all() and (res.status.numpy() == 0).all()
+    assert abs(nr.mean() - thr / pool.mean()) < 6 * pool.std() / pool.mean() * np.sqrt(thr / pool.mean())
+    assert np.array_equal(res.label_counts[:, 0].numpy(), nr)
+    solo = eng.run_batch(seed, 0, 8, 1, cov).cpu()
+    assert np.array_equal(solo.tallies[0].numpy(), res.tallies[1].numpy()) and int(solo.n_bases[0]) == int(nb[1])
+    # the same reads through the other two implementations
+    s, ln, lab = eng.materialize_reads(seed, 0, 8, False, int(nr[1]))
+    assert int(ln.sum().item()) == int(nb[1])
+    rep = eng.replay_reads(s, ln, lab, [0, int(nr[1])]).cpu()
+    assert np.array_equal(rep.tallies[0].numpy(), res.tallies[1].numpy())
+    sh, lh, labh = s.cpu().numpy(), ln.cpu().numpy(), lab.cpu().numpy()
+    exp = O.count_matches_indexed(ts, te, tb, 1, sh, sh + lh, labh, 1)
+    t = res.tallies[1].numpy()
+    assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+    depth = t[:, 2] / 5000.0
+    assert abs(depth.mean() - cov) < 5 * depth.std(ddof=1) / np.sqrt(depth.size)  # ~30x on the targets
