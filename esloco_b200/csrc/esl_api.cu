@@ -70,7 +70,7 @@ struct esl_ctx {
     uint32_t n_pool = 0, pool_max = 0;
     double pool_mean = 0, pool_sd = 0;
 
-    DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_ms, d_me, d_mpmax, d_mw, d_grp, d_mgrid;
+    DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_mrec, d_mpmax, d_grp, d_mgrid;
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
 
     // optional per-kernel timing (esl_set_profiling): events around the bulk and the cut-off kernel
@@ -243,10 +243,10 @@ int upload_index(esl_ctx *ctx)
         else grp.push_back(make_grid<C>(mp, ms, glo, (int)ms.size(), G, mgrid));
     }
     ctx->n_mask = (i64)ms.size();
-    CU(ctx->d_ms.upload(ms.data(), ms.size() * sizeof(C)));
-    CU(ctx->d_me.upload(me.data(), me.size() * sizeof(C)));
+    std::vector<esl::MaskRec<C>> mrec(ms.size());
+    for (size_t k = 0; k < ms.size(); ++k) { mrec[k] = esl::MaskRec<C>{}; mrec[k].s = ms[k]; mrec[k].e = me[k]; mrec[k].w = mw[k]; }
+    CU(ctx->d_mrec.upload(mrec.data(), mrec.size() * sizeof(esl::MaskRec<C>)));
     CU(ctx->d_mpmax.upload(mp.data(), mp.size() * sizeof(C)));
-    CU(ctx->d_mw.upload(mw.data(), mw.size() * sizeof(double)));
     CU(ctx->d_grp.upload(grp.data(), grp.size() * sizeof(esl::SegDesc)));
     CU(ctx->d_mgrid.upload(mgrid.data(), mgrid.size() * sizeof(esl::GridEntry<C>)));
     // barcode cdf: doubles (replay), integer thresholds and a 1024-slice start table (native)
@@ -309,10 +309,8 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.extra_off = ctx->d_extra_off.as<int32_t>();
     d.any_extra = ctx->n_layers > ctx->n_first_layers;
     d.n_targets = (i64)ctx->t_start.size();
-    d.ms = ctx->d_ms.as<C>();
-    d.me = ctx->d_me.as<C>();
+    d.mrec = ctx->d_mrec.as<esl::MaskRec<C>>();
     d.mpmax = ctx->d_mpmax.as<C>();
-    d.mw = ctx->d_mw.as<double>();
     d.grp = ctx->d_grp.as<esl::SegDesc>();
     d.mgrid = ctx->d_mgrid.as<esl::GridEntry<C>>();
     return d;

@@ -80,6 +80,22 @@ __device__ __forceinline__ TargetRec<uint64_t> load_rec(const TargetRec<uint64_t
     return TargetRec<uint64_t>{a.x, a.y, b.x, (int)(uint32_t)b.y, 0};
 }
 
+// One blocked interval: start, end and blocking probability in one 16-byte (u32) record.
+template <typename C> struct MaskRec;
+template <> struct __align__(16) MaskRec<uint32_t> { uint32_t s, e; double w; };
+template <> struct __align__(16) MaskRec<uint64_t> { uint64_t s, e; double w; double pad; };
+__device__ __forceinline__ MaskRec<uint32_t> load_rec(const MaskRec<uint32_t> *p)
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return MaskRec<uint32_t>{v.x, v.y, __hiloint2double((int)v.w, (int)v.z)};
+}
+__device__ __forceinline__ MaskRec<uint64_t> load_rec(const MaskRec<uint64_t> *p)
+{
+    const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    const double w = __ldg(reinterpret_cast<const double *>(p) + 2);
+    return MaskRec<uint64_t>{a.x, a.y, w, 0.0};
+}
+
 __device__ __forceinline__ SegDesc load_desc(const SegDesc *p)
 {
     const int4 v = __ldg(reinterpret_cast<const int4 *>(p)); // one LDG.128 through the read-only path
@@ -123,10 +139,8 @@ struct DevCtx {
     i64 n_targets;
     // blocked index: group g < B is barcode g's tree, group B is "ALL"; inside a group sorted by
     // (start, end) with a running max of ends (pmax) as the grid key.
-    const C *__restrict__ ms;
-    const C *__restrict__ me;
+    const MaskRec<C> *__restrict__ mrec;
     const C *__restrict__ mpmax;
-    const double *__restrict__ mw;
     const SegDesc *__restrict__ grp;      // [B + 1]
     const GridEntry<C> *__restrict__ mgrid;
 };
@@ -280,12 +294,12 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
         if (p.s >= re) continue;
         const SegDesc d = load_desc(cx.grp + g);
         for (int k = skip_crowded(d, cx.mgrid, cx.mpmax, p.a, rs); k < d.hi; ++k) {
-            if (__ldg(cx.ms + k) >= re) break;
-            if (__ldg(cx.me + k) > rs) {
-                const double w = __ldg(cx.mw + k);
-                if (!Src::kBounded && w >= 1.0) return true; // u < 1 <= w for every u: no need to draw it
+            const MaskRec<C> r = load_rec(cx.mrec + k);
+            if (r.s >= re) break;
+            if (r.e > rs) {
+                if (!Src::kBounded && r.w >= 1.0) return true; // u < 1 <= w for every u: no need to draw it
                 const double u = src.block_u(it, n, j++);
-                if (u < w) return true;
+                if (u < r.w) return true;
             }
         }
     }
