@@ -75,12 +75,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi needs a few hundred ms to start: make sure it is already sampling when the timed region begins."""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.01)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.06]
+        if not rows and self.rows:  # region shorter than one sampling period: take the sample nearest to it
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[1]]
         sm, smax, reasons = [], None, set()
         for r in rows:
             try:
@@ -200,14 +208,15 @@ def run_ours(args, w):
             eng.moments(out.tallies, acc)
             dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample()  # before the warm-up, so the GPU does not idle between warm-up and timing
     for k in range(args.warmup):
         step(k)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     eng.set_profiling(True)
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
