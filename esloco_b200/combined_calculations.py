@@ -25,12 +25,22 @@ def _length_pool_key_and_factory(seed, combo, mean_read_length, sequenced_data_p
             lambda: lognormal_pool(seed, combo, mean_read_length, sigma, min_read_length))
 
 
+def group_hits(hits, n_iter, n_targets):
+    """Sorted hit records [k, 4] -> per-iteration list of per-target overlap lists (counting.py:56 `overlap`)."""
+    out = [[[] for _ in range(n_targets)] for _ in range(n_iter)]
+    for it, row, _n, ov in hits.tolist():
+        out[it][row].append(ov)
+    return out
+
+
 def run_simulation_batch(iteration_ids, param_dictionary, genome_size, target_regions, masked_tree, device=0,
-                         to_host=True, length_pools=None):
+                         to_host=True, length_pools=None, overlap_lists=False, hit_capacity=None):
     """All combinations for a contiguous run of iterations.  Returns one BatchResult per combination (on the
     host when to_host) plus the target keys; iteration i of the batch is iteration_ids[0] + i.
     length_pools optionally maps a combination index to a ready-made host array of read lengths (already
-    filtered by min_read_length), bypassing the FASTQ scan / log-normal draw."""
+    filtered by min_read_length), bypassing the FASTQ scan / log-normal draw.  With overlap_lists=True each
+    BatchResult gets an `overlaps` attribute: per iteration, per target, the list of overlaps in read order (the
+    reference's `overlap` column); hit_capacity bounds the number of (target, read) pairs per combination."""
     iteration_ids = list(iteration_ids)
     first, n_iter = iteration_ids[0], len(iteration_ids)
     if iteration_ids != list(range(first, first + n_iter)):
@@ -48,9 +58,18 @@ def run_simulation_batch(iteration_ids, param_dictionary, genome_size, target_re
             key, factory = _length_pool_key_and_factory(seed, combo, mean_read_length, p.get("sequenced_data_path"),
                                                         p["sigma"], p["min_read_length"])
         sess.set_pool(key, factory)
-        res = sess.engine.run_batch(seed, combo, first, n_iter, coverage, p["consuming"],
-                                    p["min_overlap_for_detection"], scaling)
-        out.append(res.cpu() if to_host else res)
+        if overlap_lists:
+            sess.engine.set_hit_buffer(hit_capacity or max(1 << 20, 64 * len(target_regions) * n_iter))
+        try:
+            res = sess.engine.run_batch(seed, combo, first, n_iter, coverage, p["consuming"],
+                                        p["min_overlap_for_detection"], scaling)
+            overlaps = group_hits(sess.engine.take_hits(res.n_reads), n_iter, len(target_regions)) if overlap_lists else None
+        finally:
+            if overlap_lists:
+                sess.engine.set_hit_buffer(0)
+        res = res.cpu() if to_host else res
+        res.overlaps = overlaps
+        out.append(res)
     return out, sess.keys
 
 
@@ -59,9 +78,14 @@ def format_iteration(res, i, keys, iteration_id, mean_read_length, coverage, n_b
     (combined_calculations.py:76-89)."""
     t = res.tallies[i].numpy()
     suffix = "_" + str(iteration_id)
-    detected = [{"target_region": k + suffix, "full_matches": int(t[j, 0]), "partial_matches": int(t[j, 1]),
-                 "on_target_bases": int(t[j, 2]), "mean_read_length": mean_read_length, "coverage": coverage}
-                for j, k in enumerate(keys)]
+    ov = getattr(res, "overlaps", None)
+    detected = []
+    for j, k in enumerate(keys):
+        d = {"target_region": k + suffix, "full_matches": int(t[j, 0]), "partial_matches": int(t[j, 1])}
+        if ov is not None:
+            d["overlap"] = ov[i][j]
+        d.update(on_target_bases=int(t[j, 2]), mean_read_length=mean_read_length, coverage=coverage)
+        detected.append(d)
     dist = label_counts_to_dict(res.label_counts[i].numpy(), n_barcodes)
     dist["coverage"] = coverage
     dist["mean_read_length"] = mean_read_length
@@ -71,11 +95,16 @@ def format_iteration(res, i, keys, iteration_id, mean_read_length, coverage, n_b
 
 
 def run_simulation_iteration(iteration_id, param_dictionary, genome_size, target_regions, masked_tree, log_file=None,
-                             device=0):
+                             device=0, overlap_lists=None):
     """run_simulation_iteration(iteration_id, param_dictionary, genome_size, target_regions, masked_tree,
     log_file) -> (results, barcode_distributions) with the reference's shapes (combined_calculations.py:97-126):
-    results[c] is the per-target list of dicts of combination c, barcode_distributions[c] its label histogram."""
-    batches, keys = run_simulation_batch([iteration_id], param_dictionary, genome_size, target_regions, masked_tree, device)
+    results[c] is the per-target list of dicts of combination c, barcode_distributions[c] its label histogram.
+    The per-read `overlap` list of each dict is filled when overlap_lists (or param_dictionary["overlap_lists"]) is
+    true; it is off by default because it is the only output whose size grows with the number of hits."""
+    if overlap_lists is None:
+        overlap_lists = bool(param_dictionary.get("overlap_lists", False))
+    batches, keys = run_simulation_batch([iteration_id], param_dictionary, genome_size, target_regions, masked_tree, device,
+                                         overlap_lists=overlap_lists)
     results, dists = [], []
     for res, (mean_read_length, coverage) in zip(batches, param_dictionary["combinations"]):
         if int(res.status[0]) & 2:

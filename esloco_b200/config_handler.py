@@ -105,6 +105,7 @@ def parse_config(config_file):
             mrl = int(seq_read_data(sequenced_data_path, min_read_length=min_read_length))
             logging.info(f"Mean read length set to: {mrl}")
             mean_read_lengths = [mrl]
+        overlap_lists = config.getboolean("COMMON", "overlap_lists", fallback=False)  # extension: fill the `overlap` column
         blocked_regions_bedpath = config.get("COMMON", "blocked_regions_bedpath", fallback=None)
         consuming = config.getboolean("COMMON", "consuming", fallback=False)
         if mode == "ROI":

@@ -10,9 +10,9 @@ LABELS_BLOCKED = ("Blocked/Consuming", "Blocked/NotConsuming")
 
 def count_matches(insertion_dict, read_dir, scaling, min_overlap, genome_size=None, n_barcodes=None, device=0):
     """count_matches(insertion_dict, read_dir, scaling, min_overlap) (counting.py:7-61) computed by the CUDA
-    engine from a reference-shaped read dict (replay level 1).  Returns the reference's list of dicts, minus the
-    per-read `overlap` list (use Session.hit_records for it); `scaling` < 1 needs the native stream and is
-    rejected here, exactly because it would consume the reference's RNG."""
+    engine from a reference-shaped read dict (replay level 1).  Returns the reference's list of dicts including the
+    per-read `overlap` lists; `scaling` < 1 is rejected because the reference thins pairs with draws from its own
+    numpy stream (counting.py:46,51)."""
     if not isinstance(scaling, (int, float)):
         scaling = 1  # counting.py:16-17
     if scaling < 1:
@@ -30,9 +30,17 @@ def count_matches(insertion_dict, read_dir, scaling, min_overlap, genome_size=No
     eng.set_targets(ts, te, tb)
     eng.set_blocked()
     sess.invalidate()
-    res = eng.replay_reads(start, length, label, [0, start.size], min_overlap=min_overlap).cpu()
+    eng.set_hit_buffer(max(1 << 16, 8 * start.size))
+    try:
+        res = eng.replay_reads(start, length, label, [0, start.size], min_overlap=min_overlap).cpu()
+        hits = eng.take_hits(res.n_reads)
+    finally:
+        eng.set_hit_buffer(0)
+    overlaps = [[] for _ in keys]
+    for _it, row, _n, ov in hits.tolist():
+        overlaps[row].append(ov)
     t = res.tallies[0].numpy()
-    return [{"target_region": k, "full_matches": int(t[i, 0]), "partial_matches": int(t[i, 1]),
+    return [{"target_region": k, "full_matches": int(t[i, 0]), "partial_matches": int(t[i, 1]), "overlap": overlaps[i],
              "on_target_bases": int(t[i, 2])} for i, k in enumerate(keys)]
 
 

@@ -73,6 +73,11 @@ struct esl_ctx {
     DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_mrec, d_mpmax, d_grp, d_mgrid;
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
 
+    // optional hit-record buffer (esl_set_hit_buffer)
+    int64_t *d_hits = nullptr;
+    int64_t *d_hit_count = nullptr;
+    int64_t hit_cap = 0;
+
     // optional per-kernel timing (esl_set_profiling): events around the bulk and the cut-off kernel
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -574,6 +579,17 @@ int64_t esl_workspace_bytes(const esl_ctx *ctx, int32_t n_iter, double coverage,
     return (int64_t)(ws_tile_bytes(cap, n_iter) + (size_t)(2 * n_iter + 2) * sizeof(i64)) + 256;
 }
 
+int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t *d_count)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if ((d_hits == nullptr) != (d_count == nullptr) || capacity < 0 || (d_hits && capacity == 0))
+        return ctx->fail(ESL_ERR_INVALID, "hit buffer needs both pointers and a positive capacity (or all NULL / 0)");
+    ctx->d_hits = d_hits;
+    ctx->d_hit_count = d_count;
+    ctx->hit_cap = d_hits ? capacity : 0;
+    return ESL_OK;
+}
+
 int esl_set_profiling(esl_ctx *ctx, int32_t on)
 {
     if (!ctx) return ESL_ERR_INVALID;
@@ -618,7 +634,7 @@ int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_beg
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
-    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0};
+    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0, ctx->d_hits, (u64 *)ctx->d_hit_count, ctx->hit_cap};
     esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iter_begin, philox_keys((uint32_t)seed, (uint32_t)(seed >> 32))};
     const i64 n1 = bulk_reads(ctx, coverage);
     const i64 cap = (ctx->n_mask > 0 && !consuming) ? bulk_cap(ctx, coverage) : n1;
@@ -649,7 +665,7 @@ int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_leng
     if (total_reads >= 0xFFFF0000ll) return ctx->fail(ESL_ERR_UNSUPPORTED, "more than 2^32 reads in one replay call");
     if (max_reads_per_iter <= 0 || max_reads_per_iter > total_reads) max_reads_per_iter = total_reads;
     CU(ctx->d_scratch.reserve(ws_tile_bytes(max_reads_per_iter, n_iter) + 64));
-    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, ctx->d_scratch.as<u64>(), 0};
+    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, ctx->d_scratch.as<u64>(), 0, ctx->d_hits, (u64 *)ctx->d_hit_count, ctx->hit_cap};
     esl::ReadSrc src{d_start, d_length, d_label, d_seg};
     const i64 big = max_reads_per_iter; // every iteration's reads are all "bulk" (clipped to its own count on device)
     if (ctx->wide)
@@ -680,7 +696,7 @@ int esl_replay_draws(esl_ctx *ctx, const double *d_ubc, const int64_t *d_length,
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
     if (max_draws >= 0xFFFF0000ll) return ctx->fail(ESL_ERR_UNSUPPORTED, "more than 2^32 draws per iteration");
     CU(cudaMemsetAsync(d_ws, 0, ws_tile_bytes(std::max<i64>(bulk_draws, 1), n_iter), st));
-    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0};
+    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0, ctx->d_hits, (u64 *)ctx->d_hit_count, ctx->hit_cap};
     esl::DrawSrc src{d_ubc, d_length, d_start, d_uoff, d_ublock, d_seg};
     if (ctx->wide)
         return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, bulk_draws, bulk_draws, nullptr, n_iter, true, st);

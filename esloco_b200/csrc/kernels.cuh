@@ -154,6 +154,11 @@ struct DevOut {
     int *status;       // [n_iter]
     u64 *tile_sum;     // [n_iter][tiles_per_iter] counted-length sum of each bulk tile (zeroed by the host call)
     int tiles_per_iter;
+    // optional hit records for the reference's per-target `overlap` lists (counting.py:49,53,56): one
+    // {iteration in batch, target row, draw index, overlap} per counted pair, in no particular order
+    i64 *hits;         // [hit_cap][4] or NULL
+    u64 *hit_count;    // number of records appended (may exceed hit_cap: the host reports the overflow)
+    i64 hit_cap;
 };
 
 // ---------------------------------------------------------------- draw sources
@@ -309,7 +314,7 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
 // K6 + K7 for one layer whose first candidate starts before the read's end: walk the candidates and add
 // (sign = +1) or take back (sign = -1) the read's contribution (counting.py:40-57).
 template <typename C, typename Src>
-__device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src, u64 *__restrict__ tallies_it, int it, i64 n,
+__device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it, i64 n,
                                          int sg, int a, C rs, C re, i64 sign)
 {
     const SegDesc d = load_desc(cx.seg + sg);
@@ -322,6 +327,13 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
                 u64 *t = tallies_it + (i64)r.row * 3;
                 atomicAdd(t + ((rs <= r.s && r.e <= re) ? 0 : 1), (u64)sign);
                 atomicAdd(t + 2, (u64)(sign * (i64)ov));
+                if (out.hits && sign > 0) { // draws beyond the cut-off are dropped on the host by their index
+                    const u64 slot = atomicAdd(out.hit_count, 1ull);
+                    if ((i64)slot < out.hit_cap) {
+                        i64 *h = out.hits + slot * 4;
+                        h[0] = it; h[1] = r.row; h[2] = n; h[3] = (i64)ov;
+                    }
+                }
             }
         }
         if (r.s_next >= re) break; // known without touching the next record
@@ -330,13 +342,13 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
 
 // Extra layers of barcode bc (only when its targets nest).
 template <typename C, typename Src>
-__device__ __forceinline__ void tally_extra_layers(const DevCtx<C> &cx, const Src &src, u64 *__restrict__ tallies_it, int it,
+__device__ __forceinline__ void tally_extra_layers(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it,
                                                 i64 n, int bc, int n_extra, C rs, C re, i64 sign)
 {
     const int s0 = cx.n_barcodes + __ldg(cx.extra_off + bc);
     for (int sg = s0; sg < s0 + n_extra; ++sg) {
         const Probe<C> p = probe(cx.seg, sg, cx.tgrid, rs);
-        if (p.s < re) tally_layer(cx, src, tallies_it, it, n, sg, p.a, rs, re, sign);
+        if (p.s < re) tally_layer(cx, src, out, tallies_it, it, n, sg, p.a, rs, re, sign);
     }
 }
 
@@ -344,14 +356,14 @@ __device__ __forceinline__ void tally_extra_layers(const DevCtx<C> &cx, const Sr
 // the read's end.  Out of line: the bulk kernel only calls it for the few reads whose first-layer probe says
 // "maybe" (or when some barcode has nesting targets), the cut-off kernel for every read.
 template <typename C, typename Src>
-__device__ __forceinline__ void tally_read(const DevCtx<C> &cx, const Src &src, u64 *__restrict__ tallies_it, int it,
+__device__ __forceinline__ void tally_read(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it,
                                         i64 n, C rs, C re, int bc, i64 sign)
 {
     const SegDesc d = load_desc(cx.seg + bc);
     const GridEntry<C> e = load_entry(cx.tgrid + d.grid_off + (int)((u64)rs >> (d.flags & 0xff)));
-    if (e.s < re) tally_layer(cx, src, tallies_it, it, n, bc, e.j, rs, re, sign);
+    if (e.s < re) tally_layer(cx, src, out, tallies_it, it, n, bc, e.j, rs, re, sign);
     const int n_extra = (int)((uint32_t)d.flags >> 16);
-    if (n_extra) tally_extra_layers(cx, src, tallies_it, it, n, bc, n_extra, rs, re, sign);
+    if (n_extra) tally_extra_layers(cx, src, out, tallies_it, it, n, bc, n_extra, rs, re, sign);
 }
 
 // Resolve label + counted length of one drawn read (read_operations.py:104-121).
@@ -515,10 +527,10 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             for (int i = 0; i < kBulkIpt; ++i) {
                 const C re = (C)(st[i] + L[i]);
                 const i64 n = (i64)(base + i * kBulkBlock + tid);
-                if (pt[i].s < re) tally_layer(cx, src, tallies_it, it, n, label[i], pt[i].a, st[i], re, 1);
+                if (pt[i].s < re) tally_layer(cx, src, out, tallies_it, it, n, label[i], pt[i].a, st[i], re, 1);
                 if (cx.any_extra && label[i] >= 0 && label[i] < B) {
                     const int n_extra = (int)((uint32_t)__ldg(&cx.seg[label[i]].flags) >> 16);
-                    if (n_extra) tally_extra_layers(cx, src, tallies_it, it, n, label[i], n_extra, st[i], re, 1);
+                    if (n_extra) tally_extra_layers(cx, src, out, tallies_it, it, n, label[i], n_extra, st[i], re, 1);
                 }
             }
         }
@@ -690,7 +702,7 @@ k_cutoff_tail(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src 
             inc_bases += counted[i];
             inc_reads += 1;
             if (label[i] >= 0 && label[i] < B)
-                tally_read(cx, src, tallies_it, it, n + (i64)tid * kTailIpt + i, st[i], (C)(st[i] + L[i]), label[i], sign);
+                tally_read(cx, src, out, tallies_it, it, n + (i64)tid * kTailIpt + i, st[i], (C)(st[i] + L[i]), label[i], sign);
         }
         u64 tot_b, tot_r, tot_x;
         block_excl_scan(inc_bases, s_warp, &tot_b);

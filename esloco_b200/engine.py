@@ -24,6 +24,7 @@ class BatchResult:
     n_bases: "torch.Tensor"       # [n_iter]
     n_reads: "torch.Tensor"       # [n_iter]
     status: "torch.Tensor"        # [n_iter] int32
+    overlaps = None               # optional: per iteration, per target, list of overlaps (run_simulation_batch)
 
     def cpu(self):
         return BatchResult(*(t.cpu() for t in (self.tallies, self.label_counts, self.n_bases, self.n_reads, self.status)))
@@ -181,6 +182,29 @@ class Engine:
                                                    int(bool(consuming)), n_reads, s.data_ptr(), ln.data_ptr(),
                                                    lab.data_ptr(), self._stream()))
         return s, ln, lab
+
+    def set_hit_buffer(self, capacity):
+        """Collect {iteration, row, draw index, overlap} records of the following batches (None/0 = off)."""
+        t = self.torch
+        if not capacity:
+            self._hits = self._hit_count = None
+            self._check(self.lib.esl_set_hit_buffer(self.ctx, None, 0, None))
+            return
+        self._hits = t.empty((int(capacity), 4), dtype=t.int64, device=self.tdev)
+        self._hit_count = t.zeros(1, dtype=t.int64, device=self.tdev)
+        self._check(self.lib.esl_set_hit_buffer(self.ctx, self._hits.data_ptr(), int(capacity), self._hit_count.data_ptr()))
+
+    def take_hits(self, n_reads):
+        """Records collected since the last call, draws beyond each iteration's cut-off removed, sorted by
+        (iteration, row, draw index): int64 array [k, 4].  n_reads = the batch's reads-placed counts."""
+        count = int(self._hit_count.item())
+        if count > self._hits.shape[0]:
+            raise EngineError(-5, f"hit buffer overflow: {count} pairs, capacity {self._hits.shape[0]}")
+        h = self._hits[:count].cpu().numpy()
+        self._hit_count.zero_()
+        nr = np.asarray(n_reads.cpu() if hasattr(n_reads, "cpu") else n_reads, dtype=np.int64)
+        h = h[h[:, 2] < nr[h[:, 0]]]
+        return h[np.lexsort((h[:, 2], h[:, 1], h[:, 0]))]
 
     def coverage_bins(self, start, length, label, bin_size):
         """[n_barcodes+2, n_bins] int64 read bases per bin and label slot for device-resident reads."""

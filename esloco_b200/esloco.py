@@ -95,9 +95,11 @@ def run(param_dictionary):
     n_targets = len(target_regions)
     moments = [None] * len(combos)
     tallies = [[] for _ in combos]; labels = [[] for _ in combos]; nbases = [[] for _ in combos]
+    overlap_rows = [[] for _ in combos]  # [combo][iteration][target] -> list, only with overlap_lists on one GPU
     t_gpu = time.time()
     for chunk in iteration_chunks(mine, n_targets, len(combos)) if len(mine) else []:
-        batches, keys = run_simulation_batch(chunk, p, genome_size, target_regions, masked_tree, device=local, to_host=False)
+        batches, keys = run_simulation_batch(chunk, p, genome_size, target_regions, masked_tree, device=local, to_host=False,
+                                             overlap_lists=p.get("overlap_lists", False))
         for c, res in enumerate(batches):
             if (res.status & 2).any().item():
                 raise RuntimeError("coverage not reached")
@@ -114,6 +116,8 @@ def run(param_dictionary):
                 write_coverage_track(os.path.join(p["output_path_plots"], f"{mrl}_{cov}_coverage.tsv"), *track)
             moments[c] = sess.engine.moments(res.tallies, moments[c])
             tallies[c].append(res.tallies); labels[c].append(res.label_counts); nbases[c].append(res.n_bases)
+            if res.overlaps is not None:
+                overlap_rows[c].extend(res.overlaps)
     if not len(mine):  # a rank without iterations still takes part in the collectives
         sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"])
         keys = sess.keys
@@ -134,7 +138,10 @@ def run(param_dictionary):
     out = None
     if rank == 0:
         its = list(range(p["iterations"]))
-        matches = matches_table(keys, mode, combos, its, [t.cpu().numpy() for t in tallies])
+        overlaps = None
+        if p.get("overlap_lists", False) and ws == 1:  # rows: iteration -> combination -> target
+            overlaps = [overlap_rows[c][i][j] for i in range(len(its)) for c in range(len(combos)) for j in range(n_targets)]
+        matches = matches_table(keys, mode, combos, its, [t.cpu().numpy() for t in tallies], overlaps)
         dist_df = barcode_distribution_table(p["n_barcodes"], combos, its, [x.cpu().numpy() for x in labels],
                                              [x.cpu().numpy() for x in nbases])
         summary = summary_table(keys, mode, combos, [m.cpu().numpy() for m in moments])

@@ -155,6 +155,14 @@ int esl_coverage_bins(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_len
 #define ESL_MOMENT_COLS 8
 int esl_moments(esl_ctx *ctx, const int64_t *d_tallies, int32_t n_iter, int64_t *d_moments, void *stream);
 
+/* Optional hit records behind the reference's per-target `overlap` list column (counting.py:49,53,56): while a
+ * buffer is set, every counted (target, read) pair of esl_run_batch / esl_replay_* appends
+ * {iteration in batch, target row, draw index, overlap} (4 x int64) at an atomically claimed slot; *d_count is
+ * the number of pairs seen (the caller zeroes it; if it exceeds `capacity` the surplus was dropped).  Records
+ * whose draw index is >= that iteration's d_n_reads lie beyond the coverage cut-off and must be ignored.
+ * Sorting by (iteration, row, draw index) gives the reference's list order.  NULL / 0 / NULL switches it off. */
+int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t *d_count);
+
 /* Per-kernel device timing for bench.py's roofline: when on, the next esl_run_batch / esl_replay_* records CUDA
  * events on its stream around the bulk kernel and around the cut-off kernel; esl_get_timing waits for them and
  * returns the two durations of the last such call in milliseconds. */

@@ -93,6 +93,10 @@ def test_run_simulation_iteration_shape_and_determinism(tmp_path):
         assert "Blocked/Consuming" in dists[c] and "0" in dists[c] and "1" in dists[c]
     again, _ = run_simulation_iteration(5, p, G, targets, tree, None)
     assert again == results  # seed + iteration id fix the result, whatever the call pattern
+    with_lists, _ = run_simulation_iteration(5, dict(p, overlap_lists=True), G, targets, tree, None)
+    for a, b in zip(with_lists[0], results[0]):
+        assert sum(a["overlap"]) == b["on_target_bases"] and len(a["overlap"]) == b["full_matches"] + b["partial_matches"]
+        assert list(a) == ["target_region", "full_matches", "partial_matches", "overlap", "on_target_bases", "mean_read_length", "coverage"]
     batch, _ = run_simulation_batch(range(4, 7), p, G, targets, tree)
     assert [int(x) for x in batch[0].tallies[1, :, 2]] == [r["on_target_bases"] for r in results[0]]
 
@@ -112,6 +116,9 @@ def test_count_matches_mirror(tmp_path):
     assert [d["full_matches"] for d in out] == g.combo(0, "full").tolist()
     assert [d["partial_matches"] for d in out] == g.combo(0, "partial").tolist()
     assert [d["on_target_bases"] for d in out] == g.combo(0, "otb").tolist()
+    off, flat = g.combo(0, "overlap_off"), g.combo(0, "overlap_flat")
+    assert [d["overlap"] for d in out] == [flat[a:b].tolist() for a, b in zip(off[:-1], off[1:])]
+    assert list(out[0]) == ["target_region", "full_matches", "partial_matches", "overlap", "on_target_bases"]  # counting.py:34,54-57
     hist = count_barcode_occurrences(reads)
     assert list(hist) == m["combos"][0]["label_order"] and list(hist.values()) == g.combo(0, "label_counts").tolist()
 

@@ -82,6 +82,42 @@ def test_replay_reads_bit_exact(eng, name):
         assert int(res.status[ci]) == 0
 
 
+@pytest.mark.parametrize("name", REPLAYABLE)
+def test_overlap_lists_match_reference(eng, name):
+    """The per-target `overlap` lists (counting.py:49,53,56), rebuilt from the device's hit records, equal the
+    reference's lists element for element and in the reference's order -- from a level-1 replay and from a level-2
+    replay whose bulk range overshoots the cut-off (records of taken-back draws must be dropped)."""
+    g = Golden(name)
+    configure(eng, g)
+    m = g.meta
+    tb = O.target_barcodes(m["target_keys"], m["n_barcodes"])
+    ci = 0
+    rs, re_ = g.combo(ci, "read_start"), g.combo(ci, "read_end")
+    eng.set_hit_buffer(1 << 18)
+    try:
+        res = eng.replay_reads(rs, re_ - rs, g.combo(ci, "read_label").astype(np.int32), [0, rs.size], min_overlap=m["min_overlap"])
+        h1 = eng.take_hits(res.n_reads)
+        rng = O.Rng(m["seed"])
+        mrl, cov = m["combinations"][ci]
+        out = O.process_combination(rng, mrl, cov, m["genome_size"], g["target_start"], g["target_end"], tb, m["n_barcodes"],
+                                    m["barcode_weights"], m["consuming"], g.mask, m["sigma"], m["min_read_length"],
+                                    m["scaling"], m["min_overlap"], source_lengths=g.source_lengths, n_extra=3000, record_draws=True)
+        pl = out["placement"]
+        n_total = pl["start"].size
+        res2 = eng.replay_draws(pl["u_barcode"], pl["length"], pl["start"], [0, n_total], cov, consuming=m["consuming"],
+                                min_overlap=m["min_overlap"], ublock_off=pl["ublock_off"] if g.mask is not None else None,
+                                ublock=pl["ublock"] if g.mask is not None else None, bulk_draws=n_total)
+        h2 = eng.take_hits(res2.n_reads)
+    finally:
+        eng.set_hit_buffer(0)
+    off, flat = g.combo(ci, "overlap_off"), g.combo(ci, "overlap_flat")
+    for h in (h1, h2):
+        assert h.shape[0] == flat.size
+        assert np.array_equal(h[:, 3], flat)  # sorted by (row, draw index) == target-major, read order
+        assert np.array_equal(np.bincount(h[:, 1], minlength=len(tb)), np.diff(off))
+    assert np.array_equal(res.tallies.cpu()[0, :, 2].numpy(), np.add.reduceat(np.append(flat, 0), off[:-1]) * (np.diff(off) > 0))
+
+
 @pytest.mark.parametrize("bulk_mode", ["tail_only", "bulk_half", "bulk_overshoot"])
 @pytest.mark.parametrize("name", REPLAYABLE)
 def test_replay_draws_bit_exact(eng, name, bulk_mode):
