@@ -94,6 +94,37 @@ def format_iteration(res, i, keys, iteration_id, mean_read_length, coverage, n_b
     return detected, dist
 
 
+def process_combination(mean_read_length, coverage, genome_size, target_regions, iteration, sequenced_data_path, sigma,
+                        min_read_length, n_barcodes, barcode_weights, consuming, masked_tree, output_path, scaling,
+                        min_overlap_for_detection, no_cov_plots, seed=0, combo=0, device=0, overlap_lists=False):
+    """process_combination with the reference's positional signature (combined_calculations.py:11-28) -> (detected,
+    barcode_distribution) for ONE combination of ONE iteration.  `seed` and `combo` key the Philox stream (the
+    reference takes its randomness from numpy's global state instead); output_path / no_cov_plots are accepted for
+    signature compatibility -- the coverage track is written by the CLI, not here."""
+    p = dict(n_barcodes=n_barcodes, barcode_weights=barcode_weights, seed=seed, scaling=scaling,
+             combinations=[None] * combo + [(mean_read_length, coverage)], sequenced_data_path=sequenced_data_path,
+             sigma=sigma, min_read_length=min_read_length, consuming=consuming,
+             min_overlap_for_detection=min_overlap_for_detection)
+    sess = get_session(device)
+    sess.configure(genome_size, target_regions, masked_tree, n_barcodes, barcode_weights)
+    key, factory = _length_pool_key_and_factory(seed, combo, mean_read_length, sequenced_data_path, sigma, min_read_length)
+    sess.set_pool(key, factory)
+    sc = scaling if isinstance(scaling, (int, float)) else 1
+    if overlap_lists:
+        sess.engine.set_hit_buffer(max(1 << 20, 64 * len(target_regions)))
+    try:
+        res = sess.engine.run_batch(seed, combo, iteration, 1, coverage, consuming, min_overlap_for_detection, sc)
+        overlaps = group_hits(sess.engine.take_hits(res.n_reads), 1, len(target_regions)) if overlap_lists else None
+    finally:
+        if overlap_lists:
+            sess.engine.set_hit_buffer(0)
+    res = res.cpu()
+    res.overlaps = overlaps
+    if int(res.status[0]) & 2:
+        raise RuntimeError("coverage not reached")
+    return format_iteration(res, 0, sess.keys, iteration, mean_read_length, coverage, n_barcodes)
+
+
 def run_simulation_iteration(iteration_id, param_dictionary, genome_size, target_regions, masked_tree, log_file=None,
                              device=0, overlap_lists=None):
     """run_simulation_iteration(iteration_id, param_dictionary, genome_size, target_regions, masked_tree,

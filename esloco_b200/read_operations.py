@@ -70,3 +70,23 @@ def dict_to_reads(read_dir):
             label[i] = int(tok)
         start[i] = int(s); length[i] = int(e) - int(s)
     return start, length, label
+
+
+def generate_reads_based_on_coverage(genome_size, coverage, read_length_distribution, n_barcodes, barcode_weights, consuming,
+                                     masked_tree, seed=0, iteration=0, combo=0, device=0):
+    """generate_reads_based_on_coverage with the reference's signature (read_operations.py:86-123) -> (read dict
+    "Read_{n}_{label}" -> (start, end) in draw order, covered_length), placed by the CUDA engine and copied back.
+    Meant for inspection and small runs: the simulation itself never materialises reads.  seed / iteration / combo
+    key the Philox stream."""
+    from .session import get_session
+    sess = get_session(device)
+    sess.invalidate()
+    sess.configure(genome_size, {}, masked_tree, n_barcodes, barcode_weights)
+    lengths = np.asarray(read_length_distribution)
+    sess.set_pool(("explicit", id(read_length_distribution)), lambda: lengths)
+    eng = sess.engine
+    res = eng.run_batch(seed, combo, iteration, 1, coverage, consuming).cpu()
+    if int(res.status[0]) & 2:
+        raise RuntimeError("coverage not reached")
+    start, length, label = (x.cpu().numpy() for x in eng.materialize_reads(seed, combo, iteration, consuming, int(res.n_reads[0])))
+    return reads_to_dict(start, length, label), int(res.n_bases[0])

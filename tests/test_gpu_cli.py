@@ -154,3 +154,37 @@ def test_binned_coverage_track_matches_per_base_arrays(tmp_path):
     from scipy.ndimage import gaussian_filter1d
     assert np.allclose(smoothed["Combined"], gaussian_filter1d(raw["Combined"], 3))
     assert abs(raw["Combined"].mean() - 8.0) < 1.0
+
+
+def test_generate_reads_and_process_combination_mirrors():
+    """The reference-signature wrappers: reads dict from generate_reads_based_on_coverage fed to count_matches gives
+    the tallies process_combination reports for the same seed / iteration / combination."""
+    from esloco_b200.combined_calculations import process_combination
+    from esloco_b200.counting import count_barcode_occurrences, count_matches
+    from esloco_b200.read_operations import generate_reads_based_on_coverage
+    from esloco_b200.synthetic import random_insertions
+    from esloco_b200.utils import build_mask_tree
+    G = 3_000_000
+    targets = random_insertions(G, 5, 3000, 2, seed=9)
+    tree = build_mask_tree({"m": {"start": 500_000, "end": 900_000, "weight": 1, "barcode": []}})
+    pool = np.random.RandomState(0).randint(500, 20_000, 20_000)
+    reads, covered = generate_reads_based_on_coverage(G, 4, pool, 2, {"0": 3}, False, tree, seed=5, iteration=2, combo=1)
+    assert covered >= 4 * G and list(reads)[0].startswith("Read_0_")
+    hist = count_barcode_occurrences(reads)
+    assert set(hist) == {"0", "1", "Blocked/NotConsuming"} and sum(hist.values()) == len(reads)
+    assert sum(e - s for k, (s, e) in reads.items() if not k.endswith("NotConsuming")) == covered
+    by_reads = count_matches(targets, reads, 1.0, 10, genome_size=G, n_barcodes=2)
+    # same combination through process_combination (needs the same pool: pass it as a FASTA-like file? use sigma path)
+    from esloco_b200.session import get_session
+    sess = get_session(0)
+    sess.invalidate()
+    sess.configure(G, targets, tree, 2, {"0": 3})
+    sess.set_pool(("explicit-test",), lambda: pool)
+    res = sess.engine.run_batch(5, 1, 2, 1, 4, False, 10, 1.0).cpu()
+    assert [int(x) for x in res.tallies[0, :, 2]] == [d["on_target_bases"] for d in by_reads]
+    assert [int(x) for x in res.tallies[0, :, 0]] == [d["full_matches"] for d in by_reads]
+    detected, dist = process_combination(5000, 2, G, targets, 3, None, 1, 100, 2, {"0": 3}, False, tree, "/tmp", 1.0, 10, True,
+                                         seed=5, combo=0, overlap_lists=True)
+    assert [d["target_region"] for d in detected] == [k + "_3" for k in targets]
+    assert dist["N_bases"] >= 2 * G and dist["iteration"] == 3 and dist["coverage"] == 2
+    assert all(sum(d["overlap"]) == d["on_target_bases"] for d in detected)
