@@ -407,3 +407,53 @@ def test_full_size_config2_consistency(eng):
     assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
     depth = t[:, 2] / 5000.0
     assert abs(depth.mean() - cov) < 5 * depth.std(ddof=1) / np.sqrt(depth.size)  # ~30x on the targets
+
+
+@pytest.mark.parametrize("B", [7, 96])
+def test_native_many_barcodes_exact(eng, B):
+    """Barcode selection through the 1024-slice start table + walk, B up to 96 with uneven weights: exact against the
+    CPU restatement; every barcode's read count is inside 5 sigma of its binomial expectation."""
+    G = 30_000_000
+    rng = np.random.RandomState(B)
+    T = 3 * B
+    ts = np.sort(rng.randint(0, G - 9000, T)); te = ts + rng.randint(500, 9000, T)
+    tb = (np.arange(T) % B).astype(np.int32)
+    weights = {str(k): int(w) for k, w in zip(range(0, B, 3), rng.randint(2, 40, B))}
+    cdf = O.barcode_cdf(O.barcode_probabilities(B, weights))
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
+    pool = O.lognormal_pool(O.Rng(B), 3000, 1, 10, n=100000)
+    eng.set_length_table(pool)
+    res = eng.run_batch(99, 0, 0, 2, 8.0).cpu()
+    for i in range(2):
+        it = NN.native_iteration(99, 0, i, G, 8.0, pool, cdf)
+        exp = O.count_matches(None, ts, te, tb, it["start"], it["start"] + it["length"], it["label"], 1.0, 1)
+        counts, _ = O.label_hist(it["label"], B)
+        assert np.array_equal(res.label_counts[i].numpy(), counts)
+        t = res.tallies[i].numpy()
+        assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+    p = np.diff(np.concatenate(([0.0], cdf)))
+    n = res.n_reads[0].item()
+    z = (res.label_counts[0, :B].numpy() - n * p) / np.sqrt(n * p * (1 - p))
+    assert np.abs(z).max() < 5
+
+
+def test_edge_cases(eng):
+    """Empty target set, zero coverage, a single-entry length table, targets beyond the genome end, empty batch slot."""
+    G = 1_000_000
+    eng.set_genome(G); eng.set_barcode_cdf([0.5, 1.0]); eng.set_blocked()
+    eng.set_length_table(np.array([1000]))
+    eng.set_targets([], [], [])
+    res = eng.run_batch(1, 0, 0, 2, 3.0).cpu()
+    assert res.tallies.shape == (2, 0, 3) and (res.n_bases.numpy() == 3 * G).all() and (res.n_reads.numpy() == 3000).all()
+    eng.set_targets([0, G - 10, 2 * G, 500_000, 500_000], [10, G + 500, 3 * G, 500_000, 400_000], [0, 1, 0, 1, 0])
+    res = eng.run_batch(1, 0, 0, 1, 0.0).cpu()  # coverage 0: the reference's while-loop never runs
+    assert int(res.n_reads[0]) == 0 and int(res.n_bases[0]) == 0 and not res.tallies.any()
+    res = eng.run_batch(1, 0, 0, 3, 50.0).cpu()  # 50 k reads of 1 kb per iteration
+    t = res.tallies.numpy()
+    assert not t[:, 2].any() and not t[:, 3].any() and not t[:, 4].any()  # beyond the genome / empty / inverted: never hit
+    assert (t[:, 1, 0] == 0).all()  # a target sticking out of the genome can never be fully covered
+    assert t[:, :2, 2].sum() > 0  # the two edge targets are hit now and then (p ~ 1e-5 per read, 150 k reads)
+    it = NN.native_iteration(1, 0, 1, G, 50.0, np.array([1000]), np.array([0.5, 1.0]))
+    exp = O.count_matches(None, np.array([0, G - 10, 2 * G, 500_000, 500_000]), np.array([10, G + 500, 3 * G, 500_000, 400_000]),
+                          np.array([0, 1, 0, 1, 0], np.int32), it["start"], it["start"] + it["length"], it["label"], 1.0, 1)
+    assert np.array_equal(t[1, :, 0], exp["full"]) and np.array_equal(t[1, :, 1], exp["partial"]) and np.array_equal(t[1, :, 2], exp["otb"])
