@@ -337,7 +337,7 @@ i64 bulk_reads(const esl_ctx *ctx, double coverage)
     return n < 2 * esl::kBulkTile ? 0 : n;
 }
 
-size_t bulk_smem(int B) { return (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
+size_t bulk_smem(int B) { return (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
 
 // Upper bound on the draws per iteration any bulk pass may cover.  Without a mask (or with consuming = True)

@@ -145,6 +145,7 @@ struct DevCtx {
     const GridEntry<C> *__restrict__ mgrid;
 };
 constexpr int kCdfLut = 1024;
+constexpr int kSmemDescs = 1024; // first-layer descriptors are staged in shared memory up to this many barcodes
 
 struct DevOut {
     u64 *tallies;      // [n_iter][T][3]
@@ -400,6 +401,14 @@ __device__ __forceinline__ u64 warp_sum(u64 v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Warp sum of values below 2^52 with two REDUX instead of ten shuffles: 26-bit halves cannot overflow 32 bits
+// when 32 lanes are added.
+__device__ __forceinline__ u64 warp_sum_redux(u64 v)
+{
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0x3ffffffu));
+    const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(v >> 26));
+    return (u64)lo + ((u64)hi << 26);
+}
 __device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
 {
 #pragma unroll
@@ -429,11 +438,14 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                    const int tiles_launch, const i64 total_tiles)
 {
     extern __shared__ u64 smem[];
-    int *s_hist = (int *)smem;                                  // [B + 2] reads per label since the last flush
-    uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2); // [B]
-    uint16_t *s_lut = (uint16_t *)(s_cdf + cx.n_barcodes);      // [kCdfLut]
-    const int tid = threadIdx.x, lane = tid & 31;
+    int4 *s_desc = (int4 *)smem;                                // [min(B, kSmemDescs)] first-layer descriptors
     const int B = cx.n_barcodes;
+    const int n_sdesc = B <= kSmemDescs ? B : 0;
+    int *s_hist = (int *)(s_desc + n_sdesc);                    // [B + 2] reads per label since the last flush
+    uint32_t *s_cdf = (uint32_t *)(s_hist + B + 2);             // [B]
+    uint16_t *s_lut = (uint16_t *)(s_cdf + B);                  // [kCdfLut]
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < n_sdesc; i += kBulkBlock) s_desc[i] = __ldg(reinterpret_cast<const int4 *>(cx.seg + i));
     for (int i = tid; i < B + 2; i += kBulkBlock) s_hist[i] = 0;
     if (!Src::kHasLabel && cx.cdf_u32 && B > 1) {
         for (int i = tid; i < B; i += kBulkBlock) s_cdf[i] = cx.cdf_u32[i];
@@ -444,47 +456,55 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     const i64 per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
     const i64 t0 = (i64)blockIdx.x * per_cta;
     const i64 t1 = t0 + per_cta < total_tiles ? t0 + per_cta : total_tiles;
+    if (t0 >= t1) return;
     const bool plain_labels = !Src::kHasLabel && B == 1 && !kMask; // every read is label 0
-    int cur_it = -1;
     u64 acc_bases = 0, acc_reads = 0; // lane 0 of each warp / thread 0
     uint32_t lo = 0, hi = 0;
     u64 *tallies_it = nullptr;
+    u64 *tile_sum_it = nullptr;
+    // (iteration, tile) of the first work item by one division; afterwards they advance incrementally
+    int it = (int)(t0 / tiles_launch);
+    int t = (int)(t0 - (i64)it * tiles_launch) + tile0;
+    bool new_it = true;
 
-    for (i64 tl = t0; tl < t1; ++tl) {
-        const int it = (int)(tl / tiles_launch);
-        const int t = (int)(tl - (i64)it * tiles_launch) + tile0; // absolute tile of this iteration
-        if (it != cur_it) {
-            if (cur_it >= 0) {
-                __syncthreads();
-                for (int i = tid; i < B + 2; i += kBulkBlock)
-                    if (s_hist[i]) { atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
-                if (lane == 0 && acc_bases) atomicAdd(out.n_bases + cur_it, acc_bases);
-                if (tid == 0) {
-                    atomicAdd(out.n_reads + cur_it, acc_reads);
-                    if (plain_labels) atomicAdd(out.label_counts + (i64)cur_it * (B + 2), acc_reads);
-                }
-                acc_bases = acc_reads = 0;
-                __syncthreads();
+    for (i64 left_tiles = t1 - t0; left_tiles > 0; --left_tiles, ++t) {
+        if (t == tile0 + tiles_launch) { // wrapped into the next iteration: flush what the CTA gathered for this one
+            __syncthreads();
+            for (int i = tid; i < B + 2; i += kBulkBlock)
+                if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
+            if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
+            if (tid == 0) {
+                atomicAdd(out.n_reads + it, acc_reads);
+                if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
             }
-            cur_it = it;
+            acc_bases = acc_reads = 0;
+            __syncthreads();
+            ++it;
+            t = tile0;
+            new_it = true;
+        }
+        if (new_it) {
+            new_it = false;
             i64 l = lo_arr ? lo_arr[it] : lo_const, h = hi_arr ? hi_arr[it] : hi_const;
             if (Src::kBounded) { const i64 c = src.count(it); h = h < c ? h : c; }
             lo = (uint32_t)l;
             hi = (uint32_t)(h > l ? h : l);
             tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
+            tile_sum_it = out.tile_sum + (i64)it * out.tiles_per_iter;
         }
         const uint32_t base = (uint32_t)t * kBulkTile;
         if (base < lo || base >= hi) continue; // tile outside this iteration's range (block-uniform)
-        const bool full_tile = hi - base >= (uint32_t)kBulkTile;
 
         uint32_t L[kBulkIpt];
         C st[kBulkIpt];
         int label[kBulkIpt];
 #pragma unroll
         for (int i = 0; i < kBulkIpt; ++i) { // phase 1: draws (Philox, pool gather, start, barcode)
+            // branch-free tail handling: a thread past the end of the range redraws the range's last draw and is
+            // masked out afterwards (label = invalid, length 0)
             const uint32_t n = base + i * kBulkBlock + tid;
-            L[i] = 0; st[i] = 0; label[i] = kLabelInvalid;
-            if (full_tile || n < hi) src.draw(cx, s_cdf, s_lut, it, (i64)n, L[i], st[i], label[i]);
+            src.draw(cx, s_cdf, s_lut, it, (i64)(n < hi ? n : hi - 1), L[i], st[i], label[i]);
+            if (n >= hi) { L[i] = 0; label[i] = kLabelInvalid; }
         }
         u64 my = 0;
         if (!Src::kHasLabel && kMask) { // phase 2: blocked regions -- probe both trees for all reads, then the slow path
@@ -520,23 +540,31 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < kBulkIpt; ++i) {
                 const bool ok = label[i] >= 0 && label[i] < B;
-                pt[i] = probe(cx.seg, ok ? label[i] : 0, cx.tgrid, st[i]);
-                if (!ok) pt[i].s = (C) ~(C)0;
+                const int b = ok ? label[i] : 0;
+                const int4 dv = n_sdesc ? s_desc[b] : __ldg(reinterpret_cast<const int4 *>(cx.seg + b));
+                const GridEntry<C> e = load_entry(cx.tgrid + dv.z + (int)((u64)st[i] >> (dv.w & 0xff)));
+                pt[i] = Probe<C>{e.j, ok ? e.s : (C) ~(C)0};
             }
 #pragma unroll
             for (int i = 0; i < kBulkIpt; ++i) {
                 const C re = (C)(st[i] + L[i]);
-                const i64 n = (i64)(base + i * kBulkBlock + tid);
-                if (pt[i].s < re) tally_layer(cx, src, out, tallies_it, it, n, label[i], pt[i].a, st[i], re, 1);
-                if (cx.any_extra && label[i] >= 0 && label[i] < B) {
+                if (pt[i].s < re)
+                    tally_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), label[i], pt[i].a, st[i], re, 1);
+            }
+            if (cx.any_extra) { // nesting targets somewhere: visit the extra layers of each read's barcode
+#pragma unroll
+                for (int i = 0; i < kBulkIpt; ++i) { // (unrolled: dynamic indexing would push the arrays to local memory)
+                    if (label[i] < 0 || label[i] >= B) continue;
                     const int n_extra = (int)((uint32_t)__ldg(&cx.seg[label[i]].flags) >> 16);
-                    if (n_extra) tally_extra_layers(cx, src, out, tallies_it, it, n, label[i], n_extra, st[i], re, 1);
+                    if (n_extra)
+                        tally_extra_layers(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), label[i], n_extra,
+                                           st[i], (C)(st[i] + L[i]), 1);
                 }
             }
         }
-        my = warp_sum(my); // phase 5: tile sum (read only when the cut-off has to be taken back)
+        my = warp_sum_redux(my); // phase 5: tile sum (read only when the cut-off has to be taken back)
         if (lane == 0) {
-            if (my) atomicAdd(out.tile_sum + (i64)it * out.tiles_per_iter + t, my);
+            if (my) atomicAdd(tile_sum_it + t, my);
             acc_bases += my;
         }
         if (tid == 0) {
@@ -544,15 +572,13 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             acc_reads += left < (uint32_t)kBulkTile ? left : (uint32_t)kBulkTile;
         }
     }
-    if (cur_it >= 0) {
-        __syncthreads();
-        for (int i = tid; i < B + 2; i += kBulkBlock)
-            if (s_hist[i]) atomicAdd(out.label_counts + (i64)cur_it * (B + 2) + i, (u64)(uint32_t)s_hist[i]);
-        if (lane == 0 && acc_bases) atomicAdd(out.n_bases + cur_it, acc_bases);
-        if (tid == 0) {
-            atomicAdd(out.n_reads + cur_it, acc_reads);
-            if (plain_labels) atomicAdd(out.label_counts + (i64)cur_it * (B + 2), acc_reads);
-        }
+    __syncthreads();
+    for (int i = tid; i < B + 2; i += kBulkBlock)
+        if (s_hist[i]) atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]);
+    if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
+    if (tid == 0 && acc_reads) {
+        atomicAdd(out.n_reads + it, acc_reads);
+        if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
     }
 }
 
