@@ -28,11 +28,17 @@ namespace esl {
 typedef unsigned long long u64;
 typedef int64_t i64;
 
-constexpr int kBulkBlock = 256;
-constexpr int kBulkIpt = 4;
+#ifndef ESL_BULK_BLOCK
+#define ESL_BULK_BLOCK 256
+#endif
+#ifndef ESL_BULK_IPT
+#define ESL_BULK_IPT 3
+#endif
+constexpr int kBulkBlock = ESL_BULK_BLOCK; // threads per CTA of the bulk kernel
+constexpr int kBulkIpt = ESL_BULK_IPT;     // reads per thread and tile (256 x 3 with 5 CTAs/SM won the round-1 sweep)
 constexpr int kBulkTile = kBulkBlock * kBulkIpt;
 #ifndef ESL_BULK_MIN_BLOCKS
-#define ESL_BULK_MIN_BLOCKS 4
+#define ESL_BULK_MIN_BLOCKS 5
 #endif
 constexpr int kBulkMinBlocks = ESL_BULK_MIN_BLOCKS; // register cap: 65536 / (256 * min blocks)
 constexpr int kTailBlock = 1024;
@@ -427,7 +433,7 @@ __device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
 //
 // A thread resolves kBulkIpt reads per tile in PHASES, each phase running over all its reads before the next
 // starts, so the dependent memory accesses of different reads overlap (pool gather -> start -> grid entry are
-// two L2 round trips per read; four reads in flight hide them):
+// two L2 round trips per read; the reads of a thread being in flight together hides them):
 //   1 draw  2 blocked probes / slow path  3 label histogram  4 target probes / slow path  5 tile sum
 // There is no block barrier inside the tile loop: warps only meet when the CTA moves to the next iteration and
 // flushes its shared label histogram.
