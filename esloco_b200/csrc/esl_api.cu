@@ -71,6 +71,8 @@ struct esl_ctx {
     double pool_mean = 0, pool_sd = 0;
 
     DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_mrec, d_mpmax, d_grp, d_mgrid;
+    DevBuf d_sgrid;
+    int sgrid_n = 0, sgrid_shift = 0; // shared-memory copy of the first-layer grids (0 = does not fit)
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
 
     // optional hit-record buffer (esl_set_hit_buffer)
@@ -137,7 +139,7 @@ template <typename C> C clampc(i64 v, u64 G) { return (C)((u64)v > G + 1 ? G + 1
 // kCrowdedBucket ends are flagged so the device bisects inside the bucket.  Appends to `grid`.
 template <typename C>
 esl::SegDesc make_grid(const std::vector<C> &keys, const std::vector<C> &starts, int lo, int hi, u64 G,
-                       std::vector<esl::GridEntry<C>> &grid)
+                       std::vector<esl::GridEntry<C>> &grid, int forced_shift = -1)
 {
     esl::SegDesc d;
     d.lo = lo; d.hi = hi; d.grid_off = (int)grid.size();
@@ -146,6 +148,7 @@ esl::SegDesc make_grid(const std::vector<C> &keys, const std::vector<C> &starts,
     const u64 want = std::min<u64>(std::max<u64>(std::max<u64>(64, 8ull * (u64)(hi - lo)), (G >> 16) + 1), 1ull << 21);
     int shift = 0;
     while (((G + 1) >> shift) + 2 > want) ++shift;
+    if (forced_shift >= 0) shift = forced_shift;
     const u64 nb = ((G + 1) >> shift) + 2; // reads start below G: bucket index <= G >> shift; one more for the bound
     int j = lo, crowded = 0, prev = lo;
     for (u64 b = 0; b < nb; ++b) {
@@ -203,6 +206,31 @@ int upload_index(esl_ctx *ctx)
         if (layers.empty()) first[b] = empty_run<C>(tgrid);
         ctx->n_layers += (int)layers.size();
         ctx->n_first_layers += layers.empty() ? 0 : 1;
+    }
+    // Shared-memory pre-filter for small target sets (typical esloco runs: a handful of ROIs / insertions per
+    // barcode): per first layer a coarser grid with only the start of each bucket's first candidate, all
+    // barcodes at one common bucket width, if that fits ~36 KB with at least four buckets per target.
+    ctx->sgrid_n = 0;
+    {
+        const size_t budget = 36 * 1024 / sizeof(C);
+        const size_t per_bc = B > 0 ? budget / (size_t)B : 0;
+        int max_t = 0;
+        for (int b = 0; b < B; ++b) max_t = std::max(max_t, first[b].hi - first[b].lo);
+        int sshift = 0;
+        while (((G + 1) >> sshift) + 2 > per_bc && sshift < 63) ++sshift;
+        const size_t n_sm = (size_t)((G + 1) >> sshift) + 2;
+        if (per_bc >= 64 && n_sm <= per_bc && n_sm >= 4 * (size_t)max_t && ctx->n_first_layers > 0) {
+            std::vector<C> sg;
+            sg.reserve(n_sm * (size_t)B);
+            for (int b = 0; b < B; ++b) {
+                std::vector<esl::GridEntry<C>> tmp;
+                make_grid<C>(te, ts, first[b].lo, first[b].hi, G, tmp, sshift);
+                for (size_t k = 0; k < n_sm; ++k) sg.push_back(tmp[std::min(k, tmp.size() - 1)].s);
+            }
+            CU(ctx->d_sgrid.upload(sg.data(), sg.size() * sizeof(C)));
+            ctx->sgrid_n = (int)n_sm;
+            ctx->sgrid_shift = sshift;
+        }
     }
     std::vector<esl::SegDesc> seg(first);
     seg.insert(seg.end(), extra.begin(), extra.end());
@@ -313,6 +341,9 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.tgrid = ctx->d_tgrid.as<esl::GridEntry<C>>();
     d.extra_off = ctx->d_extra_off.as<int32_t>();
     d.any_extra = ctx->n_layers > ctx->n_first_layers;
+    d.sgrid = ctx->sgrid_n ? ctx->d_sgrid.as<C>() : nullptr;
+    d.sgrid_n = ctx->sgrid_n;
+    d.sgrid_shift = ctx->sgrid_shift;
     d.n_targets = (i64)ctx->t_start.size();
     d.mrec = ctx->d_mrec.as<esl::MaskRec<C>>();
     d.mpmax = ctx->d_mpmax.as<C>();
@@ -337,7 +368,13 @@ i64 bulk_reads(const esl_ctx *ctx, double coverage)
     return n < 2 * esl::kBulkTile ? 0 : n;
 }
 
-size_t bulk_smem(int B) { return (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
+size_t bulk_smem(const esl_ctx *ctx)
+{
+    const int B = ctx->B;
+    const size_t entry = ctx->wide ? 8 : 4;
+    return (size_t)B * ctx->sgrid_n * entry + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
+           (size_t)esl::kCdfLut * 2 + 32;
+}
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
 
 // Upper bound on the draws per iteration any bulk pass may cover.  Without a mask (or with consuming = True)
@@ -377,10 +414,10 @@ int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const es
     if (total_tiles <= 0) return ESL_OK;
     auto kern = dc.has_mask ? esl::k_place_tally_bulk<C, Src, true> : esl::k_place_tally_bulk<C, Src, false>;
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx->B)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx)));
     if (occ < 1) occ = 1;
     const i64 grid = std::min<i64>(total_tiles, (i64)ctx->sm_count * occ);
-    kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx->B), st>>>(dc, src, out, r.lo_arr, r.lo_const, r.hi_arr, r.hi_const,
+    kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx), st>>>(dc, src, out, r.lo_arr, r.lo_const, r.hi_arr, r.hi_const,
                                                                       (int)r.tile0, (int)r.tiles, total_tiles);
     CU(cudaGetLastError());
     ctx->launches++;
@@ -546,24 +583,32 @@ int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n)
 {
     if (!ctx) return ESL_ERR_INVALID;
     if (!lengths || n < 1 || n > 0xFFFFFFFFll) return ctx->fail(ESL_ERR_INVALID, "length table must hold 1 .. 2^32-1 entries");
-    // exact integer moments of the pool: sum in u64, sum of squares in 128 bits (n < 2^32, L < 2^32)
-    u64 s = 0;
-    unsigned __int128 s2 = 0;
+    // moments of the pool (they only steer how many draws the bulk pass takes, never the result): four independent
+    // double accumulators so the loop vectorises; relative error ~1e-13
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
     uint32_t mx = 0, mn = 0xFFFFFFFFu;
-    for (int64_t i = 0; i < n; ++i) {
-        const u64 v = lengths[i];
-        s += v;
-        s2 += v * v;
-        mx = std::max(mx, lengths[i]);
-        mn = std::min(mn, lengths[i]);
+    int64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const double v0 = lengths[i], v1 = lengths[i + 1], v2 = lengths[i + 2], v3 = lengths[i + 3];
+        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+        q0 += v0 * v0; q1 += v1 * v1; q2 += v2 * v2; q3 += v3 * v3;
+        const uint32_t hi4 = std::max(std::max(lengths[i], lengths[i + 1]), std::max(lengths[i + 2], lengths[i + 3]));
+        const uint32_t lo4 = std::min(std::min(lengths[i], lengths[i + 1]), std::min(lengths[i + 2], lengths[i + 3]));
+        mx = std::max(mx, hi4); mn = std::min(mn, lo4);
     }
+    for (; i < n; ++i) {
+        const double v = lengths[i];
+        a0 += v; q0 += v * v;
+        mx = std::max(mx, lengths[i]); mn = std::min(mn, lengths[i]);
+    }
+    const long double s = (long double)a0 + a1 + a2 + a3, s2 = (long double)q0 + q1 + q2 + q3;
     if (mn == 0) return ctx->fail(ESL_ERR_INVALID, "length table holds a zero-length read");
     CU(cudaSetDevice(ctx->device));
     CU(ctx->d_pool.upload(lengths, (size_t)n * sizeof(uint32_t)));
     ctx->n_pool = (uint32_t)n;
     ctx->pool_max = mx;
-    const long double mean = (long double)s / (long double)n;
-    const long double var = (long double)s2 / (long double)n - mean * mean;
+    const long double mean = s / (long double)n;
+    const long double var = s2 / (long double)n - mean * mean;
     ctx->pool_mean = (double)mean;
     ctx->pool_sd = var > 0 ? (double)sqrtl(var) : 0.0;
     ctx->have_pool = true;

@@ -142,6 +142,12 @@ struct DevCtx {
     const GridEntry<C> *__restrict__ tgrid;
     const int32_t *__restrict__ extra_off; // [B]
     int any_extra;                         // some barcode has more than one layer
+    // small target sets: for every first layer a coarser grid holding only the START of each bucket's first
+    // candidate (sgrid_n entries per barcode, bucket width 2^sgrid_shift), staged in shared memory by the bulk
+    // kernel: "start >= read end" settles the common no-overlap case without any global load, everything else
+    // goes through the exact global grid.  NULL when the first layers do not fit the shared-memory budget.
+    const C *__restrict__ sgrid;
+    int sgrid_n, sgrid_shift;
     i64 n_targets;
     // blocked index: group g < B is barcode g's tree, group B is "ALL"; inside a group sorted by
     // (start, end) with a running max of ends (pmax) as the grid key.
@@ -359,6 +365,15 @@ __device__ __forceinline__ void tally_extra_layers(const DevCtx<C> &cx, const Sr
     }
 }
 
+// First layer of the read's barcode through the exact global grid.
+template <typename C, typename Src>
+__device__ __forceinline__ void tally_first_layer(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
+                                                  int it, i64 n, C rs, C re, int bc, i64 sign)
+{
+    const Probe<C> p = probe(cx.seg, bc, cx.tgrid, rs);
+    if (p.s < re) tally_layer(cx, src, out, tallies_it, it, n, bc, p.a, rs, re, sign);
+}
+
 // All layers of the read's barcode: probe each layer, walk its candidates when the first one starts before
 // the read's end.  Out of line: the bulk kernel only calls it for the few reads whose first-layer probe says
 // "maybe" (or when some barcode has nesting targets), the cut-off kernel for every read.
@@ -444,13 +459,16 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                    const int tiles_launch, const i64 total_tiles)
 {
     extern __shared__ u64 smem[];
-    int4 *s_desc = (int4 *)smem;                                // [min(B, kSmemDescs)] first-layer descriptors
     const int B = cx.n_barcodes;
+    const int n_sgrid = cx.sgrid ? B * cx.sgrid_n : 0;
+    int4 *s_desc = (int4 *)smem;                                // [min(B, kSmemDescs)] first-layer descriptors
     const int n_sdesc = B <= kSmemDescs ? B : 0;
     int *s_hist = (int *)(s_desc + n_sdesc);                    // [B + 2] reads per label since the last flush
     uint32_t *s_cdf = (uint32_t *)(s_hist + B + 2);             // [B]
     uint16_t *s_lut = (uint16_t *)(s_cdf + B);                  // [kCdfLut]
+    C *s_grid = (C *)(smem + ((size_t)n_sdesc * 16 + (size_t)(2 * B + 2) * 4 + (size_t)kCdfLut * 2 + 15) / 8); // [B][sgrid_n]
     const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < n_sgrid; i += kBulkBlock) s_grid[i] = cx.sgrid[i];
     for (int i = tid; i < n_sdesc; i += kBulkBlock) s_desc[i] = __ldg(reinterpret_cast<const int4 *>(cx.seg + i));
     for (int i = tid; i < B + 2; i += kBulkBlock) s_hist[i] = 0;
     if (!Src::kHasLabel && cx.cdf_u32 && B > 1) {
@@ -541,7 +559,26 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             for (int i = 0; i < kBulkIpt; ++i)
                 hist_add(s_hist, label[i] != kLabelInvalid && label[i] < B ? label_slot(label[i], B) : -1, 1);
         }
-        { // phase 4: targets -- first layer probed for all reads, then the candidate walks of the few "maybe"s
+        if (n_sgrid) { // phase 4, small target sets (block-uniform): shared-memory pre-filter, exact path for the rest
+#pragma unroll
+            for (int i = 0; i < kBulkIpt; ++i) {
+                const bool ok = label[i] >= 0 && label[i] < B;
+                const C first = s_grid[(ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift)];
+                const C re = (C)(st[i] + L[i]);
+                if (ok && first < re)
+                    tally_first_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), st[i], re, label[i], 1);
+            }
+            if (cx.any_extra) { // the pre-filter only covers first layers
+#pragma unroll
+                for (int i = 0; i < kBulkIpt; ++i) {
+                    if (label[i] < 0 || label[i] >= B) continue;
+                    const int n_extra = (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16);
+                    if (n_extra)
+                        tally_extra_layers(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), label[i], n_extra,
+                                           st[i], (C)(st[i] + L[i]), 1);
+                }
+            }
+        } else { // phase 4: targets -- first layer probed for all reads, then the candidate walks of the few "maybe"s
             Probe<C> pt[kBulkIpt];
 #pragma unroll
             for (int i = 0; i < kBulkIpt; ++i) {
