@@ -61,6 +61,7 @@ struct esl_ctx {
     std::vector<double> m_w;
     std::vector<int32_t> m_bc;
     bool have_targets = false, have_pool = false;
+    int n_seg = 0, n_tgrid = 0, n_trec = 0, n_mgrid = 0, n_mrec = 0;
     bool index_dirty = true;
     bool wide = false; // 64-bit coordinates
     int n_layers = 0, n_first_layers = 0;
@@ -248,6 +249,7 @@ int upload_index(esl_ctx *ctx)
     }
     CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>)));
     CU(ctx->d_te.upload(te.data(), te.size() * sizeof(C)));
+    ctx->n_seg = (int)seg.size(); ctx->n_tgrid = (int)tgrid.size(); ctx->n_trec = (int)trec.size();
     CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc)));
     CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(esl::GridEntry<C>)));
     CU(ctx->d_extra_off.upload(extra_off.data(), extra_off.size() * sizeof(int32_t)));
@@ -278,6 +280,7 @@ int upload_index(esl_ctx *ctx)
     ctx->n_mask = (i64)ms.size();
     std::vector<esl::MaskRec<C>> mrec(ms.size());
     for (size_t k = 0; k < ms.size(); ++k) { mrec[k] = esl::MaskRec<C>{}; mrec[k].s = ms[k]; mrec[k].e = me[k]; mrec[k].w = mw[k]; }
+    ctx->n_mgrid = (int)mgrid.size(); ctx->n_mrec = (int)mrec.size();
     CU(ctx->d_mrec.upload(mrec.data(), mrec.size() * sizeof(esl::MaskRec<C>)));
     CU(ctx->d_mpmax.upload(mp.data(), mp.size() * sizeof(C)));
     CU(ctx->d_grp.upload(grp.data(), grp.size() * sizeof(esl::SegDesc)));
@@ -341,6 +344,7 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.tgrid = ctx->d_tgrid.as<esl::GridEntry<C>>();
     d.extra_off = ctx->d_extra_off.as<int32_t>();
     d.any_extra = ctx->n_layers > ctx->n_first_layers;
+    d.n_seg = ctx->n_seg; d.n_tgrid = ctx->n_tgrid; d.n_trec = ctx->n_trec; d.n_mgrid = ctx->n_mgrid; d.n_mrec = ctx->n_mrec;
     d.sgrid = ctx->sgrid_n ? ctx->d_sgrid.as<C>() : nullptr;
     d.sgrid_n = ctx->sgrid_n;
     d.sgrid_shift = ctx->sgrid_shift;

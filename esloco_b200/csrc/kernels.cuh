@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "philox.cuh"
 
@@ -49,6 +50,18 @@ constexpr int kMaxBarcodes = 4096;
 constexpr int kLabelBlockedConsuming = -1;
 constexpr int kLabelBlockedNotConsuming = -2;
 constexpr int kLabelInvalid = -1000; // slot of a tile that holds no draw
+
+// Bounds checks for a debug build (-DESL_DEBUG_BOUNDS): compute-sanitizer is not available on the GPU pool, so
+// every index into the grids, records, pool, tallies and tile sums can be checked in-kernel instead; a violation
+// prints its site and traps.  Compiled out by default.
+#ifdef ESL_DEBUG_BOUNDS
+#define ESL_CHK(cond, what)                                                                    \
+    do {                                                                                       \
+        if (!(cond)) { printf("esl bounds violation: %s (%s:%d)\n", what, __FILE__, __LINE__); __trap(); } \
+    } while (0)
+#else
+#define ESL_CHK(cond, what) ((void)0)
+#endif
 
 // One sorted run of intervals (a monotone target layer, or one blocked group) plus its bucket grid.
 // Grid entry b (b = position >> shift) holds j = first index of the run whose (running-max) end exceeds
@@ -142,6 +155,7 @@ struct DevCtx {
     const GridEntry<C> *__restrict__ tgrid;
     const int32_t *__restrict__ extra_off; // [B]
     int any_extra;                         // some barcode has more than one layer
+    int n_seg, n_tgrid, n_trec, n_mgrid, n_mrec; // array sizes (debug bounds checks)
     // small target sets: for every first layer a coarser grid holding only the START of each bucket's first
     // candidate (sgrid_n entries per barcode, bucket width 2^sgrid_shift), staged in shared memory by the bulk
     // kernel: "start >= read end" settles the common no-overlap case without any global load, everything else
@@ -189,7 +203,8 @@ struct PhiloxSrc {
                                          uint32_t &L, C &start, int &bc) const
     {
         const Philox4 r = philox4x32_10((uint32_t)n, 0u, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, keys);
-        L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool)); // uniform pick from the pool
+        L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool)); // uniform pick from the pool (index < n_pool by construction)
+        ESL_CHK((u64)L < cx.G, "read not shorter than the genome");
         const u64 range = cx.G - (u64)L;               // start ~ U{0 .. G-L-1} = floor(u64 * range / 2^64)
         if (sizeof(C) == 4) { // range < 2^32: two 32x32->64 products instead of a 64x64 high multiply
             const uint32_t rg = (uint32_t)range;
@@ -282,6 +297,7 @@ __device__ __forceinline__ Probe<C> probe(const SegDesc *descs, int idx, const G
 {
     const SegDesc d = load_desc(descs + idx);
     const GridEntry<C> e = load_entry(grid + d.grid_off + (int)((u64)rs >> (d.flags & 0xff)));
+    ESL_CHK(e.j >= d.lo && e.j <= d.hi, "grid entry outside its run");
     return Probe<C>{e.j, e.s};
 }
 
@@ -312,6 +328,7 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
         if (p.s >= re) continue;
         const SegDesc d = load_desc(cx.grp + g);
         for (int k = skip_crowded(d, cx.mgrid, cx.mpmax, p.a, rs); k < d.hi; ++k) {
+            ESL_CHK(k >= 0 && k < cx.n_mrec, "blocked record index");
             const MaskRec<C> r = load_rec(cx.mrec + k);
             if (r.s >= re) break;
             if (r.e > rs) {
@@ -332,7 +349,9 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
 {
     const SegDesc d = load_desc(cx.seg + sg);
     for (int j = skip_crowded(d, cx.tgrid, cx.te, a, rs); j < d.hi; ++j) {
+        ESL_CHK(j >= 0 && j < cx.n_trec, "target record index");
         const TargetRec<C> r = load_rec(cx.trec + j);
+        ESL_CHK(r.row >= 0 && r.row < cx.n_targets, "target row");
         if (r.s >= re) break; // starts ascend: nothing further overlaps
         if (r.e > rs) {       // (an end inside the bucket but before the read does not overlap)
             const C ov = (r.e < re ? r.e : re) - (r.s > rs ? r.s : rs);
@@ -563,6 +582,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < kBulkIpt; ++i) {
                 const bool ok = label[i] >= 0 && label[i] < B;
+                ESL_CHK((int)((u64)st[i] >> cx.sgrid_shift) < cx.sgrid_n, "shared grid index");
                 const C first = s_grid[(ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift)];
                 const C re = (C)(st[i] + L[i]);
                 if (ok && first < re)
@@ -585,6 +605,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 const bool ok = label[i] >= 0 && label[i] < B;
                 const int b = ok ? label[i] : 0;
                 const int4 dv = n_sdesc ? s_desc[b] : __ldg(reinterpret_cast<const int4 *>(cx.seg + b));
+                ESL_CHK(dv.z + (int)((u64)st[i] >> (dv.w & 0xff)) + 1 < cx.n_tgrid, "target grid index");
                 const GridEntry<C> e = load_entry(cx.tgrid + dv.z + (int)((u64)st[i] >> (dv.w & 0xff)));
                 pt[i] = Probe<C>{e.j, ok ? e.s : (C) ~(C)0};
             }
@@ -607,6 +628,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
         }
         my = warp_sum_redux(my); // phase 5: tile sum (read only when the cut-off has to be taken back)
         if (lane == 0) {
+            ESL_CHK(t >= 0 && t < out.tiles_per_iter, "tile sum index");
             if (my) atomicAdd(tile_sum_it + t, my);
             acc_bases += my;
         }
