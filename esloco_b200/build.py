@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libesloco_b200.so")
-SOURCES = ["esl_api.cu"]
-DEPS = ["esl_api.cu", "kernels.cuh", "philox.cuh", os.path.join("..", "..", "include", "esloco_b200.h")]
+SOURCES = ["esl_api.cu", "seqscan.cpp"]
+DEPS = ["esl_api.cu", "seqscan.cpp", "kernels.cuh", "philox.cuh", os.path.join("..", "..", "include", "esloco_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     extra = os.environ.get("ESL_NVCC_EXTRA", "").split()  # e.g. -DESL_BULK_MIN_BLOCKS=5 for tuning experiments
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lz"]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

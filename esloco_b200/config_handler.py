@@ -40,9 +40,37 @@ def _fastq_lengths(handle, path):
         yield len(seq)
 
 
+def _scan_native(fasta_file, is_fastq, min_read_length):
+    """One streaming pass in the native library (esl_scan_read_lengths); None when the library is not built."""
+    import ctypes as C
+    try:
+        from . import _native
+        lib = _native.load()
+    except Exception:
+        return None
+    mean = C.c_double()
+    n = lib.esl_scan_read_lengths(fasta_file.encode(), int(is_fastq), int(min_read_length), None, 0, C.byref(mean))
+    if n == -6:
+        raise ValueError(f"This is not a correct FASTQ file {fasta_file}. Provide FASTA or FASTQ.")
+    if n < 0:
+        raise OSError(f"cannot read {fasta_file}")
+    out = np.empty(n, np.uint32)
+    lib.esl_scan_read_lengths(fasta_file.encode(), int(is_fastq), int(min_read_length), out.ctypes.data, n, C.byref(mean))
+    return out.astype(np.int64)
+
+
 def seq_read_data(fasta_file, distribution=False, min_read_length=0):
     """Read lengths of a FASTA/FASTQ file, plain or gzipped (config_handler.py:16-51): lengths > min_read_length
-    as an array (distribution=True) or their mean.  Streams the file; sequences are never kept."""
+    as an array (distribution=True) or their mean.  Streams the file; sequences are never kept.  Uses the native
+    scanner of libesloco_b200.so when it is built, else a pure-Python pass with the same result."""
+    if not os.path.exists(fasta_file):
+        raise FileNotFoundError(fasta_file)
+    if fasta_file.endswith(FASTQ_EXTS) or fasta_file.endswith(FASTA_EXTS):
+        lengths = _scan_native(fasta_file, fasta_file.endswith(FASTQ_EXTS), min_read_length)
+        if lengths is not None:
+            if lengths.size == 0:
+                raise ValueError(f"No reads found in {fasta_file}")
+            return lengths if distribution else np.mean(lengths)
     open_func = gzip.open if fasta_file.endswith(".gz") else open
     with open_func(fasta_file, "rt") as handle:
         if fasta_file.endswith(FASTQ_EXTS):

@@ -163,6 +163,13 @@ int esl_moments(esl_ctx *ctx, const int64_t *d_tallies, int32_t n_iter, int64_t 
  * Sorting by (iteration, row, draw index) gives the reference's list order.  NULL / 0 / NULL switches it off. */
 int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t *d_count);
 
+/* Host helper (no GPU): read lengths of a FASTA / FASTQ file, plain or gzip, in one streaming pass
+ * (config_handler.py:16-51).  Lengths > min_read_length are written to out[0..capacity) (out may be NULL to count
+ * only); returns how many were kept (may exceed capacity), or a negative esl_status (ESL_ERR_INVALID: cannot
+ * open; ESL_ERR_UNSUPPORTED: malformed FASTQ).  *mean_out receives their mean. */
+int64_t esl_scan_read_lengths(const char *path, int32_t is_fastq, int64_t min_read_length, uint32_t *out,
+                              int64_t capacity, double *mean_out);
+
 /* Per-kernel device timing for bench.py's roofline: when on, the next esl_run_batch / esl_replay_* records CUDA
  * events on its stream around the bulk kernel and around the cut-off kernel; esl_get_timing waits for them and
  * returns the two durations of the last such call in milliseconds. */

@@ -99,3 +99,32 @@ def test_weighted_probabilities_and_mask_keys():
     assert set(tree) == {"0", "1", "ALL", 0}
     ms, me, mw, mb = mask_tree_to_arrays(tree, 2)
     assert sorted(zip(ms, me, mw, mb)) == [(1, 2, 1.0, -1), (5, 9, 0.5, 0), (5, 9, 0.5, 1)]
+
+
+def test_native_scanner_matches_python_pass(tmp_path):
+    """esl_scan_read_lengths (C++, one streaming pass, gzip transparent) == the pure-Python pass, FASTA and FASTQ,
+    multi-line FASTA records, CRLF line ends, blank lines, min_read_length filter, malformed FASTQ."""
+    import gzip
+    from esloco_b200 import config_handler as ch
+    rng = np.random.RandomState(4)
+    lens = rng.randint(1, 5000, 300).tolist()
+    fq = tmp_path / "r.fastq"
+    fq.write_text("".join(f"@r{i} extra\n{'A' * n}\n+\n{'I' * n}\n" for i, n in enumerate(lens)))
+    fa = tmp_path / "r.fa"
+    fa.write_text("".join(f">c{i}\n" + "\n".join("ACGT"[:1] * 0 + "C" * min(70, n - k) for k in range(0, n, 70)) + "\r\n" for i, n in enumerate(lens)))
+    gz = tmp_path / "r.fq.gz"
+    with gzip.open(gz, "wt") as fh:
+        fh.write(fq.read_text())
+    for path in (fq, fa, gz):
+        for m in (0, 1000):
+            native = ch._scan_native(str(path), str(path).endswith(ch.FASTQ_EXTS), m)
+            assert native is not None
+            assert native.tolist() == [n for n in lens if n > m], path
+            assert ch.seq_read_data(str(path), distribution=True, min_read_length=m).tolist() == native.tolist()
+    assert ch.seq_read_data(str(fq)) == np.mean(lens)
+    bad = tmp_path / "bad.fastq"
+    bad.write_text("@r0\nACGT\n+\n\n")
+    with pytest.raises(ValueError):
+        ch.seq_read_data(str(bad))
+    with pytest.raises(ValueError):
+        ch.seq_read_data(str(fq), min_read_length=10**7)
