@@ -93,8 +93,9 @@ class Engine:
 
     def set_length_table(self, lengths):
         a = np.asarray(lengths)
-        if a.size and (a.min() < 1 or a.max() > 0xFFFFFFFF):
-            raise ValueError("read lengths must be in [1, 2^32)")
+        if a.dtype != np.uint32:  # (uint32 input is range-checked by the library itself: no extra passes over it)
+            if a.size and (a.min() < 1 or a.max() > 0xFFFFFFFF):
+                raise ValueError("read lengths must be in [1, 2^32)")
         a = _np(a, np.uint32)
         self._check(self.lib.esl_set_length_table(self.ctx, a.ctypes.data, a.size))
 
