@@ -457,3 +457,47 @@ def test_edge_cases(eng):
     exp = O.count_matches(None, np.array([0, G - 10, 2 * G, 500_000, 500_000]), np.array([10, G + 500, 3 * G, 500_000, 400_000]),
                           np.array([0, 1, 0, 1, 0], np.int32), it["start"], it["start"] + it["length"], it["label"], 1.0, 1)
     assert np.array_equal(t[1, :, 0], exp["full"]) and np.array_equal(t[1, :, 1], exp["partial"]) and np.array_equal(t[1, :, 2], exp["otb"])
+
+
+def test_native_u64_coordinates_bulk_path(eng):
+    """Genome > 2^32: every kernel runs its 64-bit instantiation, with enough reads for the bulk kernel (the golden
+    genome_gt_u32 case only reaches the cut-off kernel)."""
+    G = 6_000_000_000
+    rng = np.random.RandomState(64)
+    T = 300
+    ts = np.sort(rng.randint(0, G - 3_000_000, T, dtype=np.int64)); te = ts + rng.randint(1000, 3_000_000, T)
+    tb = np.zeros(T, np.int32)
+    eng.set_genome(G); eng.set_barcode_cdf([1.0]); eng.set_targets(ts, te, tb); eng.set_blocked()
+    pool = O.lognormal_pool(O.Rng(64), 20000, 1, 1, n=200000)
+    eng.set_length_table(pool)
+    cov = 0.5
+    assert eng.bulk_reads(cov) > 100_000
+    res = eng.run_batch(7, 2, 3, 2, cov).cpu()
+    for i in range(2):
+        it = NN.native_iteration(7, 2, 3 + i, G, cov, pool, np.array([1.0]))
+        assert it["start"].max() > 2**32
+        exp = O.count_matches_indexed(ts, te, tb, 1, it["start"], it["start"] + it["length"], it["label"], 1)
+        t = res.tallies[i].numpy()
+        assert int(res.n_reads[i]) == it["n_placed"] and int(res.n_bases[i]) == it["covered"]
+        assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+        assert t[:, 2].sum() > 0
+
+
+def test_native_more_barcodes_than_shared_descriptors(eng):
+    """B = 1500 > 1024: first-layer descriptors are read from global memory instead of shared memory."""
+    G, B = 40_000_000, 1500
+    rng = np.random.RandomState(15)
+    ts = np.sort(rng.randint(0, G - 20000, 2 * B)); te = ts + rng.randint(2000, 20000, 2 * B)
+    tb = (np.arange(2 * B) % B).astype(np.int32)
+    cdf = O.barcode_cdf(O.barcode_probabilities(B, {"7": 50, "900": 30}))
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
+    pool = O.lognormal_pool(O.Rng(15), 4000, 1, 10, n=100000)
+    eng.set_length_table(pool)
+    res = eng.run_batch(5, 0, 0, 1, 12.0).cpu()
+    it = NN.native_iteration(5, 0, 0, G, 12.0, pool, cdf)
+    exp = O.count_matches_indexed(ts, te, tb, B, it["start"], it["start"] + it["length"], it["label"], 1)
+    counts, _ = O.label_hist(it["label"], B)
+    t = res.tallies[0].numpy()
+    assert np.array_equal(res.label_counts[0].numpy(), counts)
+    assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+    assert t[:, 2].sum() > 0
