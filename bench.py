@@ -47,6 +47,13 @@ def make_workload(name):
                  desc="ROI mode, hg38-size, 50k ROIs, blocked centromere/gap mask, min_overlap 1000, 100 iterations")
         w["targets"] = S.barcode_rois(S.random_rois(S.HG38, 50000, 1000, 100000, seed=4), 1)
         w["mask"] = S.gap_mask(S.HG38, 800, seed=5)
+    elif name == "chr":
+        w.update(n_barcodes=1, iterations=100,
+                 desc="ROI mode, hg38-size, 24 whole-chromosome ROIs + 76 ROIs of 1-100 kb, 1 barcode, 30x, 100 iterations")
+        total, cdir = S.chromosome_dir(S.HG38)
+        rois = {f"C{i}": {"start": s, "end": e, "weight": 1, "barcode": []} for i, (s, e) in enumerate(cdir.values())}
+        rois.update(S.random_rois(S.HG38, 76, 1000, 100000, seed=6))
+        w["targets"] = S.barcode_rois(rois, 1)
     else:
         raise SystemExit(f"unknown workload {name}")
     w["pool"] = S.lognormal_lengths(w["mean_read_length"], w["sigma"], w["min_read_length"], seed=1)

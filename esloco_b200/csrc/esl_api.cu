@@ -243,6 +243,9 @@ int upload_index(esl_ctx *ctx)
             for (int k = d.lo; k < d.hi; ++k, ++j) {
                 esl::TargetRec<C> r{};
                 r.s = ts[k]; r.e = te[k]; r.row = trow[k];
+                // hot target: a read overlaps it with probability >= 1/512 (whole-chromosome ROIs and the like)
+                const long double p_hit = ((long double)(te[k] - ts[k]) + ctx->pool_mean) / (long double)G;
+                if (p_hit >= 1.0L / 512) r.row |= (int)0x80000000;
                 r.s_next = k + 1 < d.hi ? ts[k + 1] : (C) ~(C)0;
                 trec[k] = r;
             }

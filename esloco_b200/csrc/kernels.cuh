@@ -85,6 +85,7 @@ template <> struct __align__(16) GridEntry<uint64_t> { int j; int pad; uint64_t 
 // One indexed target: start, end, original row and the start of the next target of the layer (all ones at the
 // end), so a candidate walk needs one 16-byte load per candidate and none to find out that it is over.
 template <typename C> struct TargetRec;
+// (row: original row of the target; bit 31 set = "hot" target, see tally_layer)
 template <> struct __align__(16) TargetRec<uint32_t> { uint32_t s, e; int row; uint32_t s_next; };
 template <> struct __align__(16) TargetRec<uint64_t> { uint64_t s, e, s_next; int row; int pad; };
 __device__ __forceinline__ TargetRec<uint32_t> load_rec(const TargetRec<uint32_t> *p)
@@ -351,19 +352,37 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
     for (int j = skip_crowded(d, cx.tgrid, cx.te, a, rs); j < d.hi; ++j) {
         ESL_CHK(j >= 0 && j < cx.n_trec, "target record index");
         const TargetRec<C> r = load_rec(cx.trec + j);
-        ESL_CHK(r.row >= 0 && r.row < cx.n_targets, "target row");
+        ESL_CHK((r.row & 0x7fffffff) < cx.n_targets, "target row");
         if (r.s >= re) break; // starts ascend: nothing further overlaps
         if (r.e > rs) {       // (an end inside the bucket but before the read does not overlap)
             const C ov = (r.e < re ? r.e : re) - (r.s > rs ? r.s : rs);
-            if ((i64)ov >= cx.min_overlap && !(cx.scaling < 1.0 && !(src.scale_u(it, n, r.row) <= cx.scaling))) {
-                u64 *t = tallies_it + (i64)r.row * 3;
-                atomicAdd(t + ((rs <= r.s && r.e <= re) ? 0 : 1), (u64)sign);
-                atomicAdd(t + 2, (u64)(sign * (i64)ov));
+            if ((i64)ov >= cx.min_overlap && !(cx.scaling < 1.0 && !(src.scale_u(it, n, r.row & 0x7fffffff) <= cx.scaling))) {
+                const int kind = (rs <= r.s && r.e <= re) ? 0 : 1;
+                const int row = r.row & 0x7fffffff;
+                u64 *t = tallies_it + (i64)row * 3;
+                if (r.row < 0) {
+                    // "hot" target (flagged by the host: a read hits it with probability >= 1/512, e.g. a
+                    // whole-chromosome ROI): lanes that are here together with the same target and kind are combined
+                    // first (match.any + REDUX), one pair of atomics per group instead of one per lane on one address
+                    const unsigned peers = __match_any_sync(__activemask(), row * 2 + kind);
+                    const int cnt = __popc(peers);
+                    u64 ov_sum = (u64)ov; // ov <= read length < 2^32
+                    if (cnt > 1)
+                        ov_sum = (u64)__reduce_add_sync(peers, (unsigned)ov & 0xffffu) +
+                                 ((u64)__reduce_add_sync(peers, (unsigned)((u64)ov >> 16)) << 16);
+                    if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+                        atomicAdd(t + kind, (u64)(sign * (i64)cnt));
+                        atomicAdd(t + 2, (u64)(sign * (i64)ov_sum));
+                    }
+                } else {
+                    atomicAdd(t + kind, (u64)sign);
+                    atomicAdd(t + 2, (u64)(sign * (i64)ov));
+                }
                 if (out.hits && sign > 0) { // draws beyond the cut-off are dropped on the host by their index
                     const u64 slot = atomicAdd(out.hit_count, 1ull);
                     if ((i64)slot < out.hit_cap) {
                         i64 *h = out.hits + slot * 4;
-                        h[0] = it; h[1] = r.row; h[2] = n; h[3] = (i64)ov;
+                        h[0] = it; h[1] = row; h[2] = n; h[3] = (i64)ov;
                     }
                 }
             }
