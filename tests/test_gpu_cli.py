@@ -188,3 +188,35 @@ def test_generate_reads_and_process_combination_mirrors():
     assert [d["target_region"] for d in detected] == [k + "_3" for k in targets]
     assert dist["N_bases"] >= 2 * G and dist["iteration"] == 3 and dist["coverage"] == 2
     assert all(sum(d["overlap"]) == d["on_target_bases"] for d in detected)
+
+
+def test_cli_two_gpus_identical_tables(tmp_path):
+    """`torchrun --nproc-per-node 2 -m esloco_b200 --config x.ini` (iterations sharded over two GPUs, NCCL reduce of
+    the moments, gather of the tallies) writes byte-identical tables to the single-GPU run: the Philox counter
+    carries the iteration id, so the split is invisible.  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(HERE)
+    outs = {}
+    for n in (1, 2):
+        tmp = str(tmp_path / f"n{n}")
+        os.makedirs(tmp)
+        ini, _ = make_config(tmp, "I")
+        text = open(ini).read().replace("iterations = 3", "iterations = 7")
+        open(ini, "w").write(text)
+        env = dict(os.environ, PYTHONPATH=root)
+        if n == 1:
+            cmd = [sys.executable, "-m", "esloco_b200", "--config", ini]
+        else:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                   "127.0.0.1", "--master-port", "29533", "-m", "esloco_b200", "--config", ini]
+        r = subprocess.run(cmd, env=env, cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[n] = {f: open(os.path.join(tmp, "out_I", f"expI_{f}")).read()
+                   for f in ("matches_table.csv", "summary.csv", "barcode_distribution_table.csv", "insertion_locations.bed")}
+    for f in outs[1]:
+        assert outs[1][f] == outs[2][f], f
+    assert outs[1]["matches_table.csv"].count("\n") == 1 + 7 * 2 * 8  # header + iterations x combinations x targets
