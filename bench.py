@@ -310,7 +310,8 @@ def run_ours(args, w):
             binding = {"source": os.path.relpath(sp, ROOT), "warp_instructions_per_read": round(ps["warp_instructions_per_read"], 1),
                        "issue_slots_busy_pct": float(ps["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
                        "fmaheavy_pipe_pct": float(ps["sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"]),
-                       "dram_bytes_per_launch": float(ps["dram__bytes_read.sum"]) * 1e6 + float(ps["dram__bytes_write.sum"] or 0)}
+                       "dram_bytes_per_launch": sum(float(ps[k] or 0) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(ps["units"].get(k), 1)
+                                                    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))}
         n_thr = host_threads(w)
         if args.no_cpu_baseline:
             cpu = None
