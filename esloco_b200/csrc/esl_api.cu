@@ -795,6 +795,23 @@ int esl_coverage_bins(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_len
     return ESL_OK;
 }
 
+int esl_replay_thin(esl_ctx *ctx, const int64_t *d_hits, const double *d_u, int64_t n_hits, double scaling,
+                    int32_t n_iter, int64_t *d_tallies, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n_hits < 0 || n_iter < 1 || !d_tallies || (n_hits && (!d_hits || !d_u))) return ctx->fail(ESL_ERR_INVALID, "bad arguments");
+    if (!ctx->have_targets) return ctx->fail(ESL_ERR_STATE, "esl_set_targets has not been called");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 T = (i64)ctx->t_start.size();
+    CU(cudaMemsetAsync(d_tallies, 0, (size_t)n_iter * T * 3 * sizeof(int64_t), st));
+    if (n_hits == 0) return ESL_OK;
+    esl::k_thin_pairs<<<(unsigned)((n_hits + 255) / 256), 256, 0, st>>>(d_hits, d_u, n_hits, scaling, T, (u64 *)d_tallies);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return ESL_OK;
+}
+
 int esl_moments(esl_ctx *ctx, const int64_t *d_tallies, int32_t n_iter, int64_t *d_moments, void *stream)
 {
     if (!ctx) return ESL_ERR_INVALID;

@@ -382,7 +382,8 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
                     const u64 slot = atomicAdd(out.hit_count, 1ull);
                     if ((i64)slot < out.hit_cap) {
                         i64 *h = out.hits + slot * 4;
-                        h[0] = it; h[1] = row; h[2] = n; h[3] = (i64)ov;
+                        h[0] = it; h[1] = row; h[2] = n;
+                        h[3] = (i64)ov | (kind == 0 ? (i64)0x8000000000000000ULL : 0); // sign bit = full match
                     }
                 }
             }
@@ -876,6 +877,24 @@ k_coverage_bins(const i64 *__restrict__ start, const i64 *__restrict__ length, c
             if (hi > lo) atomicAdd(row + b, (u64)(hi - lo));
         }
     }
+}
+
+// Replay of the reference's pair thinning (counting.py:46,51): `hits` are the qualifying (target, read) pairs of a
+// replay in the reference's visiting order (sorted by iteration, target row, draw index), u[i] the uniform the
+// reference drew for pair i; a pair is kept iff u <= scaling.  `kind` comes back from the record's sign bit of the
+// overlap column (set by the collector for full matches).
+__global__ void __launch_bounds__(256)
+k_thin_pairs(const i64 *__restrict__ hits, const double *__restrict__ u, const i64 n_hits, const double scaling,
+             const i64 n_targets, u64 *__restrict__ tallies)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_hits || !(u[i] <= scaling)) return;
+    const i64 *h = hits + i * 4;
+    const i64 ov = h[3] & 0x7fffffffffffffffLL;
+    const int kind = h[3] < 0 ? 0 : 1;
+    u64 *t = tallies + (h[0] * n_targets + h[1]) * 3;
+    atomicAdd(t + kind, 1ull);
+    atomicAdd(t + 2, (u64)ov);
 }
 
 // Per-target moment accumulators over the iterations of a batch (operand of the multi-GPU sum-reduce).

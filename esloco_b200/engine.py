@@ -195,7 +195,7 @@ class Engine:
         self._hit_count = t.zeros(1, dtype=t.int64, device=self.tdev)
         self._check(self.lib.esl_set_hit_buffer(self.ctx, self._hits.data_ptr(), int(capacity), self._hit_count.data_ptr()))
 
-    def take_hits(self, n_reads):
+    def take_hits(self, n_reads, keep_kind=False):
         """Records collected since the last call, draws beyond each iteration's cut-off removed, sorted by
         (iteration, row, draw index): int64 array [k, 4].  n_reads = the batch's reads-placed counts."""
         count = int(self._hit_count.item())
@@ -205,7 +205,21 @@ class Engine:
         self._hit_count.zero_()
         nr = np.asarray(n_reads.cpu() if hasattr(n_reads, "cpu") else n_reads, dtype=np.int64)
         h = h[h[:, 2] < nr[h[:, 0]]]
-        return h[np.lexsort((h[:, 2], h[:, 1], h[:, 0]))]
+        h = h[np.lexsort((h[:, 2], h[:, 1], h[:, 0]))]
+        if not keep_kind:
+            h[:, 3] &= 0x7FFFFFFFFFFFFFFF  # the sign bit of the overlap column marks full matches
+        return h
+
+    def replay_thin(self, hits, uniforms, scaling, n_iter):
+        """Tallies [n_iter, T, 3] of the pairs the reference keeps for scaling < 1: hits = take_hits(..., keep_kind=True)
+        of a scaling-1 replay, uniforms = the reference's per-pair draws in that order."""
+        t = self.torch
+        dh = self._dev(hits, t.int64)
+        du = self._dev(uniforms, t.float64)
+        out = t.empty((n_iter, self.n_targets, 3), dtype=t.int64, device=self.tdev)
+        self._check(self.lib.esl_replay_thin(self.ctx, dh.data_ptr(), du.data_ptr(), int(dh.shape[0]), float(scaling),
+                                             int(n_iter), out.data_ptr(), self._stream()))
+        return out
 
     def coverage_bins(self, start, length, label, bin_size):
         """[n_barcodes+2, n_bins] int64 read bases per bin and label slot for device-resident reads."""

@@ -160,6 +160,7 @@ int esl_moments(esl_ctx *ctx, const int64_t *d_tallies, int32_t n_iter, int64_t 
  * {iteration in batch, target row, draw index, overlap} (4 x int64) at an atomically claimed slot; *d_count is
  * the number of pairs seen (the caller zeroes it; if it exceeds `capacity` the surplus was dropped).  Records
  * whose draw index is >= that iteration's d_n_reads lie beyond the coverage cut-off and must be ignored.
+ * The overlap column carries the match kind in its sign bit (set = full match); mask it off for the length.
  * Sorting by (iteration, row, draw index) gives the reference's list order.  NULL / 0 / NULL switches it off. */
 int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t *d_count);
 
@@ -169,6 +170,13 @@ int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t 
  * open; ESL_ERR_UNSUPPORTED: malformed FASTQ).  *mean_out receives their mean. */
 int64_t esl_scan_read_lengths(const char *path, int32_t is_fastq, int64_t min_read_length, uint32_t *out,
                               int64_t capacity, double *mean_out);
+
+/* Replay of the reference's pair thinning for scaling < 1 (counting.py:46,51: one rand() per qualifying pair, kept
+ * iff u <= scaling, pairs visited target-major in read order).  d_hits = the qualifying pairs of a replay run with
+ * scaling = 1 (esl_set_hit_buffer records, sorted by iteration, row, draw index, cut-off applied), d_u = the
+ * recorded uniforms in that order.  Writes tallies [n_iter][T][3] of the kept pairs (zeroed first). */
+int esl_replay_thin(esl_ctx *ctx, const int64_t *d_hits, const double *d_u, int64_t n_hits, double scaling,
+                    int32_t n_iter, int64_t *d_tallies, void *stream);
 
 /* Per-kernel device timing for bench.py's roofline: when on, the next esl_run_batch / esl_replay_* records CUDA
  * events on its stream around the bulk kernel and around the cut-off kernel; esl_get_timing waits for them and

@@ -246,14 +246,15 @@ int eslo_place(eslo_rng *st, int64_t G, double coverage, const int64_t *pool, in
  * read's label is the target's barcode (:37; blocked labels never match), the half-open intervals
  * intersect (:40) and the overlap is >= min_overlap (:43).  ONE rand() is drawn per qualifying pair, even
  * when scaling == 1 (:46,51); `u <= scaling` keeps it.  full iff read_start <= start and end <= read_end.
- * ov_off (T+1) / ov (cap ov_cap) receive the per-target overlap lists in read order when non-NULL.
+ * ov_off (T+1) / ov (cap ov_cap) receive the per-target overlap lists in read order when non-NULL; upair
+ * (cap upair_cap) the uniform of every qualifying pair in visiting order, kept or not (*n_pairs_out = how many).
  * st == NULL skips the draw (valid only for scaling >= 1: the outcome does not depend on u). */
 int64_t eslo_count_matches(eslo_rng *st, int64_t T, const int64_t *ts, const int64_t *te, const int32_t *tb,
                            int64_t R, const int64_t *rs, const int64_t *re, const int32_t *rl, double scaling,
                            int64_t min_overlap, int64_t *full, int64_t *partial, int64_t *otb, int64_t *ov_off,
-                           int64_t *ov, int64_t ov_cap)
+                           int64_t *ov, int64_t ov_cap, double *upair, int64_t upair_cap, int64_t *n_pairs_out)
 {
-    int64_t nov = 0;
+    int64_t nov = 0, npairs = 0;
     for (int64_t t = 0; t < T; t++) {
         int64_t f = 0, p = 0, sum = 0;
         const int64_t s = ts[t], e = te[t];
@@ -267,6 +268,8 @@ int64_t eslo_count_matches(eslo_rng *st, int64_t T, const int64_t *ts, const int
                     int64_t o = hi - lo;
                     if (o >= min_overlap) {
                         double u = st ? eslo_double(st) : 0.0;
+                        if (upair && npairs < upair_cap) upair[npairs] = u; /* the draw of this qualifying pair */
+                        npairs++;
                         if (u <= scaling) {
                             if (rs[r] <= s && e <= re[r]) f++; else p++;
                             sum += o;
@@ -282,6 +285,7 @@ int64_t eslo_count_matches(eslo_rng *st, int64_t T, const int64_t *ts, const int
         otb[t] = sum;
     }
     if (ov_off) ov_off[T] = nov;
+    if (n_pairs_out) *n_pairs_out = npairs;
     return nov;
 }
 

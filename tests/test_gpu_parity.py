@@ -118,6 +118,37 @@ def test_overlap_lists_match_reference(eng, name):
     assert np.array_equal(res.tallies.cpu()[0, :, 2].numpy(), np.add.reduceat(np.append(flat, 0), off[:-1]) * (np.diff(off) > 0))
 
 
+def test_replay_scaling_below_one_bit_exact(eng):
+    """scaling = 0.5 golden: the reference draws one uniform per qualifying (target, read) pair, target-major in read
+    order (counting.py:46,51).  The device finds the qualifying pairs (scaling-1 replay + hit records), the recorded
+    uniforms are applied to them in the reference's order on the device: tallies equal the reference's."""
+    g = Golden("scaling_half")
+    configure(eng, g)
+    m = g.meta
+    tb = O.target_barcodes(m["target_keys"], m["n_barcodes"])
+    rng = O.Rng(m["seed"])
+    mrl, cov = m["combinations"][0]
+    src = O.lognormal_pool(rng, mrl, m["sigma"], m["min_read_length"])
+    pool = O.choice(rng, src, int(cov * m["genome_size"] / mrl) * 10)
+    cdf = O.barcode_cdf(O.barcode_probabilities(m["n_barcodes"], m["barcode_weights"]))
+    pl = O.place(rng, m["genome_size"], cov, pool, m["n_barcodes"], cdf, m["consuming"], g.mask)
+    n = pl["n_placed"]
+    rs, ln, rl = pl["start"][:n], pl["length"][:n], pl["label"][:n]
+    assert np.array_equal(rs, g.combo(0, "read_start"))
+    orc = O.count_matches(rng, g["target_start"], g["target_end"], tb, rs, rs + ln, rl, m["scaling"], m["min_overlap"], want_pair_draws=True)
+    assert np.array_equal(orc["otb"], g.combo(0, "otb"))  # the oracle's own thinning is the reference's
+    eng.set_hit_buffer(1 << 18)
+    try:
+        res = eng.replay_reads(rs, ln, rl, [0, n], min_overlap=m["min_overlap"])
+        hits = eng.take_hits(res.n_reads, keep_kind=True)
+    finally:
+        eng.set_hit_buffer(0)
+    assert hits.shape[0] == orc["pair_u"].size
+    t = eng.replay_thin(hits, orc["pair_u"], m["scaling"], 1).cpu().numpy()[0]
+    assert np.array_equal(t[:, 0], g.combo(0, "full")) and np.array_equal(t[:, 1], g.combo(0, "partial")) and np.array_equal(t[:, 2], g.combo(0, "otb"))
+    assert t[:, :2].sum() < res.tallies.cpu().numpy()[0, :, :2].sum()  # something was thinned away
+
+
 @pytest.mark.parametrize("bulk_mode", ["tail_only", "bulk_half", "bulk_overshoot"])
 @pytest.mark.parametrize("name", REPLAYABLE)
 def test_replay_draws_bit_exact(eng, name, bulk_mode):
