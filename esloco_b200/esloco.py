@@ -43,22 +43,24 @@ def setup_logging(filename):
     logging.basicConfig(filename=filename, level=logging.INFO, format="%(asctime)s - %(levelname)s - %(message)s", filemode="a")
 
 
-def iteration_chunks(iterations, n_targets, n_combos, budget_bytes=2 << 30):
-    """Split a range of iterations into batches whose tallies fit a device-memory budget."""
+def iteration_chunks(iterations, n_targets, n_combos, budget_bytes=2 << 30, max_rows=4_000_000):
+    """Split a range of iterations into batches whose tallies fit a device-memory budget and whose table rows
+    (iterations x combinations x targets) stay below max_rows per streamed chunk."""
     per_iter = max(1, n_targets * 24 * n_combos)
-    step = max(1, min(len(iterations), budget_bytes // per_iter))
+    step = max(1, min(len(iterations), budget_bytes // per_iter, max_rows // max(1, n_targets * n_combos)))
     for i in range(0, len(iterations), step):
         yield iterations[i:i + step]
 
 
 def run(param_dictionary):
-    """Everything after config parsing; returns the three DataFrames on rank 0 (None elsewhere)."""
+    """Everything after config parsing; returns (barcode distribution, summary) DataFrames on rank 0 (None elsewhere).
+    The per-iteration matches table is streamed to disk and not kept in memory."""
     import torch
     import torch.distributed as dist
     from .combined_calculations import run_simulation_batch
     from .distributed import gather_iterations, reduce_moments, shard_iterations, world
     from .session import get_session
-    from .tables import barcode_distribution_table, matches_table, summary_table, write_tables
+    from .tables import MatchesWriter, barcode_distribution_table, summary_table, write_tables
 
     p = param_dictionary
     rank, ws, local = world()
@@ -92,14 +94,22 @@ def run(param_dictionary):
     combos = p["combinations"]
     mine = shard_iterations(p["iterations"], rank, ws)
     sess = get_session(local)
+    dev = torch.device("cuda", local)
     n_targets = len(target_regions)
-    moments = [None] * len(combos)
-    tallies = [[] for _ in combos]; labels = [[] for _ in combos]; nbases = [[] for _ in combos]
-    overlap_rows = [[] for _ in combos]  # [combo][iteration][target] -> list, only with overlap_lists on one GPU
+    sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"])
+    keys = sess.keys
+    moments = [torch.zeros((n_targets, 8), dtype=torch.int64, device=dev) for _ in combos]
+    labels = [[torch.zeros((0, p["n_barcodes"] + 2), dtype=torch.int64, device=dev)] for _ in combos]
+    nbases = [[torch.zeros((0,), dtype=torch.int64, device=dev)] for _ in combos]
+    # per-iteration rows are streamed to disk chunk by chunk; every rank writes the block of iterations it owns
+    base = f"{output_path}{experiment_name}"
+    part = f"{base}_matches_table.csv" if ws == 1 else f"{base}_matches_table.part{rank}.csv"
+    writer = MatchesWriter(part, keys, mode, combos, write_header=rank == 0)
+    want_lists = bool(p.get("overlap_lists", False))
     t_gpu = time.time()
     for chunk in iteration_chunks(mine, n_targets, len(combos)) if len(mine) else []:
         batches, keys = run_simulation_batch(chunk, p, genome_size, target_regions, masked_tree, device=local, to_host=False,
-                                             overlap_lists=p.get("overlap_lists", False))
+                                             overlap_lists=want_lists)
         for c, res in enumerate(batches):
             if (res.status & 2).any().item():
                 raise RuntimeError("coverage not reached")
@@ -114,39 +124,33 @@ def run(param_dictionary):
                 sess.set_pool(key, factory)
                 track = binned_coverage(sess.engine, int(p.get("seed", 0)), c, 0, p["consuming"], int(res.n_reads[0]))
                 write_coverage_track(os.path.join(p["output_path_plots"], f"{mrl}_{cov}_coverage.tsv"), *track)
-            moments[c] = sess.engine.moments(res.tallies, moments[c])
-            tallies[c].append(res.tallies); labels[c].append(res.label_counts); nbases[c].append(res.n_bases)
-            if res.overlaps is not None:
-                overlap_rows[c].extend(res.overlaps)
-    if not len(mine):  # a rank without iterations still takes part in the collectives
-        sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"])
-        keys = sess.keys
-        dev = torch.device("cuda", local)
-        for c in range(len(combos)):
-            tallies[c].append(torch.zeros((0, n_targets, 3), dtype=torch.int64, device=dev))
-            labels[c].append(torch.zeros((0, p["n_barcodes"] + 2), dtype=torch.int64, device=dev))
-            nbases[c].append(torch.zeros((0,), dtype=torch.int64, device=dev))
+            sess.engine.moments(res.tallies, moments[c])
+            labels[c].append(res.label_counts); nbases[c].append(res.n_bases)
+        overlaps = None
+        if want_lists:  # rows: iteration -> combination -> target
+            overlaps = [batches[c].overlaps[i][j] for i in range(len(chunk)) for c in range(len(combos)) for j in range(n_targets)]
+        writer.append(list(chunk), [res.tallies.cpu().numpy() for res in batches], overlaps)
     for c in range(len(combos)):
-        if moments[c] is None:
-            moments[c] = torch.zeros((n_targets, 8), dtype=torch.int64, device=torch.device("cuda", local))
         reduce_moments(moments[c])  # the one collective of the data path
-        tallies[c] = gather_iterations(torch.cat(tallies[c]), p["iterations"])
         labels[c] = gather_iterations(torch.cat(labels[c]), p["iterations"])
         nbases[c] = gather_iterations(torch.cat(nbases[c]), p["iterations"])
     torch.cuda.synchronize()
-    logging.info(f"GPU iterations: {time.time() - t_gpu:.2f} seconds on {ws} GPU(s).")
+    if ws > 1:
+        dist.barrier()  # all part files are complete
+    logging.info(f"GPU iterations and row streaming: {time.time() - t_gpu:.2f} seconds on {ws} GPU(s).")
     out = None
     if rank == 0:
         its = list(range(p["iterations"]))
-        overlaps = None
-        if p.get("overlap_lists", False) and ws == 1:  # rows: iteration -> combination -> target
-            overlaps = [overlap_rows[c][i][j] for i in range(len(its)) for c in range(len(combos)) for j in range(n_targets)]
-        matches = matches_table(keys, mode, combos, its, [t.cpu().numpy() for t in tallies], overlaps)
         dist_df = barcode_distribution_table(p["n_barcodes"], combos, its, [x.cpu().numpy() for x in labels],
                                              [x.cpu().numpy() for x in nbases])
         summary = summary_table(keys, mode, combos, [m.cpu().numpy() for m in moments])
         try:
-            write_tables(output_path, experiment_name, matches, dist_df, summary, insertion_bed if mode == "I" else None)
+            if ws > 1:
+                parts = [f"{base}_matches_table.part{r}.csv" for r in range(ws)]
+                MatchesWriter.merge_parts(f"{base}_matches_table.csv", parts)
+                for f in parts:
+                    os.remove(f)
+            write_tables(output_path, experiment_name, None, dist_df, summary, insertion_bed if mode == "I" else None)
             if mode == "I":
                 logging.info("Insertion locations saved.")
         except Exception as e:
@@ -156,7 +160,7 @@ def run(param_dictionary):
             logging.info(f"{param} = {value} ({type(value)})")
         logging.info(f"Total execution time: {time.time() - start_time:.2f} seconds.")
         logging.info("Simulation complete!")
-        out = (matches, dist_df, summary)
+        out = (dist_df, summary)
     if ws > 1:
         dist.barrier()
     return out

@@ -53,6 +53,32 @@ def matches_table(keys, mode, combos, iteration_ids, tallies_per_combo, overlaps
     return df
 
 
+class MatchesWriter:
+    """Streams `{exp}_matches_table.csv` to disk chunk by chunk (rows: iteration -> combination -> target), so a
+    run with 10^8+ rows never holds more than one chunk of iterations in memory.  Each rank of a multi-GPU run writes
+    its own contiguous block of iterations to a part file; `merge_parts` concatenates them in rank order."""
+
+    def __init__(self, path, keys, mode, combos, write_header=True):
+        self.path, self.keys, self.mode, self.combos = path, keys, mode, combos
+        self.header = write_header
+        open(path, "w").close()
+
+    def append(self, iteration_ids, tallies_per_combo, overlaps=None):
+        if len(iteration_ids) == 0:
+            return
+        df = matches_table(self.keys, self.mode, self.combos, iteration_ids, tallies_per_combo, overlaps)
+        df.to_csv(self.path, sep="\t", header=self.header, index=False, mode="a")
+        self.header = False
+
+    @staticmethod
+    def merge_parts(final_path, part_paths):
+        import shutil
+        with open(final_path, "wb") as out:
+            for part in part_paths:
+                with open(part, "rb") as fh:
+                    shutil.copyfileobj(fh, out, 16 << 20)
+
+
 def barcode_distribution_table(n_barcodes, combos, iteration_ids, label_counts_per_combo, n_bases_per_combo):
     """DataFrame of `{exp}_barcode_distribution_table.csv` (esloco.py:161-180): one row per (iteration,
     combination); label columns, coverage, mean_read_length, iteration, N_bases, total_Reads.  All barcode columns

@@ -220,3 +220,25 @@ def test_cli_two_gpus_identical_tables(tmp_path):
     for f in outs[1]:
         assert outs[1][f] == outs[2][f], f
     assert outs[1]["matches_table.csv"].count("\n") == 1 + 7 * 2 * 8  # header + iterations x combinations x targets
+
+
+def test_cli_streaming_chunks_are_invisible(tmp_path, monkeypatch):
+    """The matches table is streamed to disk per chunk of iterations; chunk boundaries must not show."""
+    import esloco_b200.esloco as cli
+    from esloco_b200.config_handler import parse_config
+    outs = []
+    for k, step in enumerate((None, 2)):
+        tmp = str(tmp_path / f"run{k}")
+        os.makedirs(tmp)
+        ini, _ = make_config(tmp, "ROI")
+        text = open(ini).read().replace("iterations = 3", "iterations = 5").replace("[ROI]", "overlap_lists = True\n\n[ROI]")
+        open(ini, "w").write(text)
+        if step:
+            monkeypatch.setattr(cli, "iteration_chunks", lambda its, T, C, **kw: (its[i:i + step] for i in range(0, len(its), step)))
+        cli.run(parse_config(ini))
+        outs.append(open(os.path.join(tmp, "out_ROI", "expROI_matches_table.csv")).read())
+    assert outs[0] == outs[1]
+    m = pd.read_csv(os.path.join(str(tmp_path / "run1"), "out_ROI", "expROI_matches_table.csv"), sep="\t")
+    assert len(m) == 5 * 2 * 6
+    import ast
+    assert all(sum(ast.literal_eval(o)) == b for o, b in zip(m["overlap"], m["on_target_bases"]))
