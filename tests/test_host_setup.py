@@ -128,3 +128,20 @@ def test_native_scanner_matches_python_pass(tmp_path):
         ch.seq_read_data(str(bad))
     with pytest.raises(ValueError):
         ch.seq_read_data(str(fq), min_read_length=10**7)
+
+
+def test_fasta_byte_scanner_chunk_boundaries(tmp_path):
+    """The chunked byte-level FASTA scan gives the same contig lengths for any chunk size (headers and sequence lines
+    split across chunk boundaries, CRLF, blank lines, gzip, '>' inside a description)."""
+    import gzip
+    from esloco_b200.fasta_operations import fasta_contig_lengths
+    text = ">chr1 desc >weird\nACGT\nAC\r\n\n>chr2\n" + "G" * 205 + "\n" + "T" * 17 + "\n>empty\n>chr3 last"
+    p = tmp_path / "a.fa"
+    p.write_text(text)
+    expect = [("chr1", 6), ("chr2", 222), ("empty", 0), ("chr3", 0)]
+    for cb in (1, 2, 3, 7, 64, 1 << 20):
+        assert list(fasta_contig_lengths(str(p), cb)) == expect, cb
+    gz = tmp_path / "a.fa.gz"
+    with gzip.open(gz, "wt") as fh:
+        fh.write(text)
+    assert list(fasta_contig_lengths(str(gz), 5)) == expect
