@@ -209,7 +209,10 @@ def run_ours(args, w):
     def step(k):
         # rank r owns iterations [r*n_iter + k*world*n_iter ...): disjoint iteration ids across ranks and steps
         it0 = (k * world + rank) * n_iter
-        eng.run_batch(w["seed"], 0, it0, n_iter, w["coverage"], w["consuming"], w["min_overlap"], w["scaling"], out=out)
+        if args.path == "staged":
+            eng.run_batch_staged(w["seed"], 0, it0, n_iter, w["coverage"], w["consuming"], w["min_overlap"], out=out)
+        else:
+            eng.run_batch(w["seed"], 0, it0, n_iter, w["coverage"], w["consuming"], w["min_overlap"], w["scaling"], out=out)
         if world > 1:
             acc.zero_()
             eng.moments(out.tallies, acc)
@@ -292,7 +295,7 @@ def run_ours(args, w):
         # iteration.  Masked + non-consuming runs add a second bulk pass whose per-iteration extent is decided on the
         # device; there all placed reads are counted against the bulk passes AND the cut-off kernel's time.
         two_pass = bool(w["mask"]) and not w["consuming"]
-        if two_pass:
+        if two_pass or args.path == "staged":
             reads_kernel, kernel_ms = reads_all / world / args.steps, (bulk_ms + cut_ms) / args.steps
         else:
             reads_kernel, kernel_ms = float(eng.bulk_reads(w["coverage"]) * n_iter), bulk_ms / args.steps
@@ -324,11 +327,11 @@ def run_ours(args, w):
                 "iterations_per_s": iters_all / (dev_ms * 1e-3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32" if w["genome_size"] <= 0xFFFFFFF0 else "u64", "data": "synthetic",
-                "config": {"workload": w["desc"], "iterations_per_step_per_gpu": n_iter, "targets": T,
+                "config": {"workload": w["desc"], "path": args.path, "iterations_per_step_per_gpu": n_iter, "targets": T,
                            "reads_per_iteration": reads_all / iters_all, "rng": "philox4x32-10",
                            "l2": "flushed between steps (256 MiB write) outside the per-step CUDA events",
                            "parallelism": f"iterations sharded over {world} GPU(s)" + (", one NCCL sum-reduce of per-target moments per step" if world > 1 else "")},
-                "roofline": {"bound": "hbm", "kernel": "k_place_tally_bulk", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "k_place_tally_bulk" if args.path == "fused" else "staged pipeline (16 kernels per iteration)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": kernel_ms,
                              "launches_per_step": 2 if two_pass else 1,
@@ -354,6 +357,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="fused", choices=["fused", "staged"],
+                    help="fused = the product kernels; staged = the north star's sort + sweep pipeline kept as a measured baseline")
     args = ap.parse_args()
     w = make_workload(args.workload)
     if args.impl == "reference":

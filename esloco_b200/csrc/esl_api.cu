@@ -9,6 +9,7 @@
 
 #include "../../include/esloco_b200.h"
 #include "kernels.cuh"
+#include "staged.cuh"
 
 using esl::i64;
 using esl::u64;
@@ -72,6 +73,7 @@ struct esl_ctx {
     double pool_mean = 0, pool_sd = 0;
 
     DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_mrec, d_mpmax, d_grp, d_mgrid;
+    DevBuf d_raw_ts, d_raw_te, d_raw_tb; // targets in caller order (staged baseline)
     DevBuf d_sgrid;
     int sgrid_n = 0, sgrid_shift = 0; // shared-memory copy of the first-layer grids (0 = does not fit)
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
@@ -253,6 +255,9 @@ int upload_index(esl_ctx *ctx)
     CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>)));
     CU(ctx->d_te.upload(te.data(), te.size() * sizeof(C)));
     ctx->n_seg = (int)seg.size(); ctx->n_tgrid = (int)tgrid.size(); ctx->n_trec = (int)trec.size();
+    CU(ctx->d_raw_ts.upload(ctx->t_start.data(), ctx->t_start.size() * sizeof(i64)));
+    CU(ctx->d_raw_te.upload(ctx->t_end.data(), ctx->t_end.size() * sizeof(i64)));
+    CU(ctx->d_raw_tb.upload(ctx->t_bc.data(), ctx->t_bc.size() * sizeof(int32_t)));
     CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc)));
     CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(esl::GridEntry<C>)));
     CU(ctx->d_extra_off.upload(extra_off.data(), extra_off.size() * sizeof(int32_t)));
@@ -696,6 +701,81 @@ int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_beg
     if (ctx->wide)
         return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, n1, cap, d_range, n_iter, true, st);
     return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, n1, cap, d_range, n_iter, true, st);
+}
+
+// ---- staged baseline ---------------------------------------------------------------------------------------------
+
+static i64 staged_cap(const esl_ctx *ctx, double coverage)
+{
+    const double thr = coverage * (double)ctx->G, mu = ctx->pool_mean, sd = ctx->pool_sd;
+    const double r0 = thr / mu;
+    i64 cap = (i64)(r0 + 16.0 * sd * std::sqrt(std::max(r0, 1.0)) / mu) + 8192;
+    cap = std::max(cap, bulk_cap(ctx, coverage));
+    return std::min<i64>(cap, 0x7FFF0000ll);
+}
+
+int64_t esl_staged_workspace_bytes(const esl_ctx *ctx, double coverage)
+{
+    if (!ctx || !ctx->have_pool) return ESL_ERR_STATE;
+    const i64 cap = staged_cap(ctx, coverage);
+    const i64 sort_blocks = (cap + esl::kSortTile - 1) / esl::kSortTile;
+    return (int64_t)(cap * 28 + ((cap + esl::kStageBlock - 1) / esl::kStageBlock) * 8 + sort_blocks * 256 * 4 + 4096);
+}
+
+int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_begin, int32_t n_iter, double coverage,
+                         int32_t consuming, int64_t min_overlap, int64_t *d_tallies, int64_t *d_label_counts,
+                         int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status, void *d_ws, size_t ws_bytes, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (n_iter < 1) return ctx->fail(ESL_ERR_INVALID, "n_iter must be >= 1");
+    int rc = ensure_index(ctx, true);
+    if (rc) return rc;
+    if ((rc = check_outputs(ctx, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status))) return rc;
+    if (ctx->wide) return ctx->fail(ESL_ERR_UNSUPPORTED, "the staged baseline supports 32-bit coordinates only");
+    if ((u64)ctx->pool_max >= ctx->G) return ctx->fail(ESL_ERR_INVALID, "longest read is not shorter than the genome");
+    const i64 need = esl_staged_workspace_bytes(ctx, coverage);
+    if (!d_ws || (i64)ws_bytes < need) return ctx->fail(ESL_ERR_WORKSPACE, "workspace %zu bytes < required %lld", ws_bytes, (long long)need);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
+    const int cap = (int)staged_cap(ctx, coverage);
+    const int gen_blocks = (cap + esl::kStageBlock - 1) / esl::kStageBlock;
+    const int sort_blocks = (cap + esl::kSortTile - 1) / esl::kSortTile;
+    uint32_t *w = (uint32_t *)d_ws;
+    uint32_t *start = w, *len = w + cap, *kA = w + 3 * (size_t)cap, *vA = w + 4 * (size_t)cap, *kB = w + 5 * (size_t)cap, *vB = w + 6 * (size_t)cap;
+    int *label = (int *)(w + 2 * (size_t)cap);
+    u64 *block_sum = (u64 *)(w + 7 * (size_t)cap + (((size_t)cap * 7) & 1));
+    uint32_t *hist = (uint32_t *)(block_sum + gen_blocks);
+    int *n_dev = (int *)(hist + (size_t)sort_blocks * 256);
+    const esl::DevCtx<uint32_t> dc = make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, 1.0);
+    const i64 T = (i64)ctx->t_start.size();
+    const size_t gen_smem = (size_t)ctx->B * 4 + (size_t)esl::kCdfLut * 2 + 16;
+    const bool prof = ctx->profiling && ctx->ev[0];
+    ctx->ev_valid = false;
+    if (prof) CU(cudaEventRecord(ctx->ev[0], st));
+    for (int i = 0; i < n_iter; ++i) {
+        esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iter_begin + (uint32_t)i, philox_keys((uint32_t)seed, (uint32_t)(seed >> 32))};
+        esl::k_stage_generate<<<gen_blocks, esl::kStageBlock, gen_smem, st>>>(dc, src, cap, start, len, label, block_sum);
+        esl::k_stage_cutoff<<<1, 1024, 0, st>>>(dc, cap, len, label, block_sum, (u64 *)d_n_reads + i, (u64 *)d_n_bases + i, d_status + i, n_dev);
+        esl::k_stage_labels<<<ctx->sm_count * 2, esl::kStageBlock, (size_t)(ctx->B + 2) * 4 + 16, st>>>(ctx->B, label, n_dev, (u64 *)d_label_counts + (i64)i * (ctx->B + 2));
+        const uint32_t *kin = start, *vin = nullptr;
+        uint32_t *kout = kA, *vout = vA;
+        for (int pass = 0; pass < 4; ++pass) {
+            esl::k_rs_hist<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, n_dev, pass * 8, sort_blocks, hist);
+            esl::k_rs_scan<<<1, 1024, 0, st>>>(hist, sort_blocks * 256);
+            esl::k_rs_scatter<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, vin, kout, vout, n_dev, pass * 8, sort_blocks, hist, pass == 0);
+            kin = kout; vin = vout;
+            if (kout == kA) { kout = kB; vout = vB; } else { kout = kA; vout = vA; }
+        }
+        if (T > 0)
+            esl::k_stage_sweep<<<(unsigned)((T * 32 + esl::kStageBlock - 1) / esl::kStageBlock), esl::kStageBlock, 0, st>>>(
+                ctx->d_raw_ts.as<i64>(), ctx->d_raw_te.as<i64>(), ctx->d_raw_tb.as<int32_t>(), T, kin, vin, n_dev, len, label,
+                ctx->pool_max, min_overlap, ctx->B, (u64 *)d_tallies + (i64)i * T * 3);
+        ctx->launches += 16;
+    }
+    CU(cudaGetLastError());
+    if (prof) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); CU(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid = true; }
+    return ESL_OK;
 }
 
 int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,

@@ -135,6 +135,19 @@ class Engine:
             out.n_bases.data_ptr(), out.n_reads.data_ptr(), out.status.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
         return out
 
+    def run_batch_staged(self, seed, combo, iter_begin, n_iter, coverage, consuming=False, min_overlap=1, out=None):
+        """The staged baseline pipeline (sort + sweep); same draws and outputs as run_batch, slower by design."""
+        out = out or self.alloc_outputs(n_iter)
+        need = self.lib.esl_staged_workspace_bytes(self.ctx, float(coverage))
+        if need < 0:
+            self._check(int(need))
+        ws = self._workspace(max(need, 1))
+        self._check(self.lib.esl_run_batch_staged(
+            self.ctx, int(seed) & 0xFFFFFFFFFFFFFFFF, int(combo), int(iter_begin), int(n_iter), float(coverage),
+            int(bool(consuming)), int(min_overlap), out.tallies.data_ptr(), out.label_counts.data_ptr(),
+            out.n_bases.data_ptr(), out.n_reads.data_ptr(), out.status.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
+        return out
+
     def replay_reads(self, start, length, label, seg_offsets, min_overlap=1, out=None):
         """Replay level 1: recorded reads, iteration i = reads [seg_offsets[i], seg_offsets[i+1])."""
         t = self.torch

@@ -110,6 +110,16 @@ int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_beg
                   int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status,
                   void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* The STAGED pipeline of the north star as a measured baseline (csrc/staged.cuh): generate -> block-scan cut-off ->
+ * LSD radix sort of read starts -> per-target binary-search sweep with warp-shuffle reduction.  Same draws, same
+ * outputs as esl_run_batch (tests compare them bit for bit); 32-bit coordinates, scaling = 1 only.  Iterations are
+ * processed one after the other.  Workspace: esl_staged_workspace_bytes. */
+int64_t esl_staged_workspace_bytes(const esl_ctx *ctx, double coverage);
+int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_begin, int32_t n_iter,
+                         double coverage, int32_t consuming, int64_t min_overlap, int64_t *d_tallies,
+                         int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status,
+                         void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Replay level 1: recorded reads (already cut off), iteration i owns reads [seg_offsets[i], seg_offsets[i+1]).
  * count_matches + count_barcode_occurrences over them (counting.py:7-71).  seg_offsets is a DEVICE array of
  * n_iter+1 int64; total_reads = seg_offsets[n_iter] and max_reads_per_iter = the largest segment (passed so the

@@ -532,3 +532,43 @@ def test_native_more_barcodes_than_shared_descriptors(eng):
     assert np.array_equal(res.label_counts[0].numpy(), counts)
     assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
     assert t[:, 2].sum() > 0
+
+
+@pytest.mark.parametrize("name", ["cfg1_roi_10mb", "ins_b4_weights", "blocked_w1_notconsuming", "blocked_fractional_multihit",
+                                  "dense_adversarial", "cfg2_reduced_50mb"])
+def test_staged_baseline_equals_fused(eng, name):
+    """The staged pipeline (generate -> block-scan cut-off -> radix sort -> per-target sweep) and the fused kernels are
+    two independent implementations of the same draws: every output must agree bit for bit."""
+    g = Golden(name)
+    configure(eng, g)
+    m = g.meta
+    mrl, cov = m["combinations"][0]
+    pool = O.lognormal_pool(O.Rng(17), mrl, m["sigma"], m["min_read_length"], n=150000)
+    eng.set_length_table(pool)
+    fused = eng.run_batch(4711, 2, 9, 3, cov, m["consuming"], m["min_overlap"], 1.0).cpu()
+    staged = eng.run_batch_staged(4711, 2, 9, 3, cov, m["consuming"], m["min_overlap"]).cpu()
+    assert np.array_equal(staged.n_reads.numpy(), fused.n_reads.numpy())
+    assert np.array_equal(staged.n_bases.numpy(), fused.n_bases.numpy())
+    assert np.array_equal(staged.label_counts.numpy(), fused.label_counts.numpy())
+    assert np.array_equal(staged.tallies.numpy(), fused.tallies.numpy())
+    assert not (staged.status.numpy() & 2).any() and fused.tallies.numpy().sum() > 0
+
+
+def test_staged_baseline_larger_run(eng):
+    """~0.5 M reads per iteration, 24 barcodes, 30 % of the genome blocked: radix sort over many CTAs, both bulk passes."""
+    G, B = 60_000_000, 24
+    rng = np.random.RandomState(77)
+    T = 40 * B
+    ts = np.sort(rng.randint(0, G - 30000, T)); te = ts + rng.randint(500, 30000, T)
+    tb = (np.arange(T) % B).astype(np.int32)
+    mask = (np.array([2_000_000, 30_000_000]), np.array([12_000_000, 38_000_000]), np.array([1.0, 1.0]), np.array([-1, 3], np.int32))
+    cdf = O.barcode_cdf(O.barcode_probabilities(B, {"0": 10, "1": 5}))
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked(*mask)
+    pool = O.lognormal_pool(O.Rng(78), 2500, 1, 1, n=300000)
+    eng.set_length_table(pool)
+    fused = eng.run_batch(3, 0, 0, 2, 20.0, False, 100, 1.0).cpu()
+    staged = eng.run_batch_staged(3, 0, 0, 2, 20.0, False, 100).cpu()
+    assert int(fused.n_reads[0]) > 400_000
+    for a, b in ((staged.n_reads, fused.n_reads), (staged.n_bases, fused.n_bases), (staged.label_counts, fused.label_counts),
+                 (staged.tallies, fused.tallies)):
+        assert np.array_equal(a.numpy(), b.numpy())
