@@ -331,7 +331,7 @@ def run_ours(args, w):
                            "reads_per_iteration": reads_all / iters_all, "rng": "philox4x32-10",
                            "l2": "flushed between steps (256 MiB write) outside the per-step CUDA events",
                            "parallelism": f"iterations sharded over {world} GPU(s)" + (", one NCCL sum-reduce of per-target moments per step" if world > 1 else "")},
-                "roofline": {"bound": "hbm", "kernel": "k_place_tally_bulk" if args.path == "fused" else "staged pipeline (16 kernels per iteration)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "k_place_tally_bulk" if args.path == "fused" else "staged pipeline (20 kernels per iteration)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": kernel_ms,
                              "launches_per_step": 2 if two_pass else 1,

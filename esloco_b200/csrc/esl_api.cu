@@ -719,7 +719,7 @@ int64_t esl_staged_workspace_bytes(const esl_ctx *ctx, double coverage)
     if (!ctx || !ctx->have_pool) return ESL_ERR_STATE;
     const i64 cap = staged_cap(ctx, coverage);
     const i64 sort_blocks = (cap + esl::kSortTile - 1) / esl::kSortTile;
-    return (int64_t)(cap * 28 + ((cap + esl::kStageBlock - 1) / esl::kStageBlock) * 8 + sort_blocks * 256 * 4 + 4096);
+    return (int64_t)(cap * 28 + ((cap + esl::kStageBlock - 1) / esl::kStageBlock) * 8 + sort_blocks * 256 * 4 + 8192);
 }
 
 int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_begin, int32_t n_iter, double coverage,
@@ -746,7 +746,8 @@ int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t i
     int *label = (int *)(w + 2 * (size_t)cap);
     u64 *block_sum = (u64 *)(w + 7 * (size_t)cap + (((size_t)cap * 7) & 1));
     uint32_t *hist = (uint32_t *)(block_sum + gen_blocks);
-    int *n_dev = (int *)(hist + (size_t)sort_blocks * 256);
+    uint32_t *digit_tot = hist + (size_t)sort_blocks * 256;
+    int *n_dev = (int *)(digit_tot + 256);
     const esl::DevCtx<uint32_t> dc = make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, 1.0);
     const i64 T = (i64)ctx->t_start.size();
     const size_t gen_smem = (size_t)ctx->B * 4 + (size_t)esl::kCdfLut * 2 + 16;
@@ -762,8 +763,9 @@ int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t i
         uint32_t *kout = kA, *vout = vA;
         for (int pass = 0; pass < 4; ++pass) {
             esl::k_rs_hist<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, n_dev, pass * 8, sort_blocks, hist);
-            esl::k_rs_scan<<<1, 1024, 0, st>>>(hist, sort_blocks * 256);
-            esl::k_rs_scatter<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, vin, kout, vout, n_dev, pass * 8, sort_blocks, hist, pass == 0);
+            esl::k_rs_scan_rows<<<256, 1024, 0, st>>>(hist, sort_blocks, digit_tot);
+            esl::k_rs_scan_digits<<<1, 1024, 0, st>>>(digit_tot);
+            esl::k_rs_scatter<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, vin, kout, vout, n_dev, pass * 8, sort_blocks, hist, digit_tot, pass == 0);
             kin = kout; vin = vout;
             if (kout == kA) { kout = kB; vout = vB; } else { kout = kA; vout = vA; }
         }
@@ -771,7 +773,7 @@ int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t i
             esl::k_stage_sweep<<<(unsigned)((T * 32 + esl::kStageBlock - 1) / esl::kStageBlock), esl::kStageBlock, 0, st>>>(
                 ctx->d_raw_ts.as<i64>(), ctx->d_raw_te.as<i64>(), ctx->d_raw_tb.as<int32_t>(), T, kin, vin, n_dev, len, label,
                 ctx->pool_max, min_overlap, ctx->B, (u64 *)d_tallies + (i64)i * T * 3);
-        ctx->launches += 16;
+        ctx->launches += 20;
     }
     CU(cudaGetLastError());
     if (prof) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); CU(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid = true; }

@@ -141,33 +141,45 @@ k_rs_hist(const uint32_t *__restrict__ keys, const int *__restrict__ n_dev, cons
     hist[threadIdx.x * n_blocks + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// exclusive scan of the (digit-major) histogram in place: one CTA, serial over chunks of 1024
+// exclusive scan of the (digit-major) histogram: CTA d scans the row of digit d in place (offsets of the CTAs'
+// tiles inside the digit) and leaves the digit's total; a second tiny kernel turns the 256 totals into digit bases
 __global__ void __launch_bounds__(1024)
-k_rs_scan(uint32_t *__restrict__ hist, const int n_entries)
+k_rs_scan_rows(uint32_t *__restrict__ hist, const int n_blocks, uint32_t *__restrict__ digit_tot)
 {
     __shared__ u64 s_warp[40];
+    uint32_t *row = hist + (size_t)blockIdx.x * n_blocks;
     u64 run = 0;
-    for (int b0 = 0; b0 < n_entries; b0 += 1024) {
+    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
         const int i = b0 + threadIdx.x;
-        const u64 v = i < n_entries ? hist[i] : 0;
+        const u64 v = i < n_blocks ? row[i] : 0;
         u64 tot;
         const u64 ex = block_excl_scan(v, s_warp, &tot);
-        if (i < n_entries) hist[i] = (uint32_t)(run + ex);
+        if (i < n_blocks) row[i] = (uint32_t)(run + ex);
         run += tot;
     }
+    if (threadIdx.x == 0) digit_tot[blockIdx.x] = (uint32_t)run;
+}
+__global__ void __launch_bounds__(1024)
+k_rs_scan_digits(uint32_t *__restrict__ digit_tot)
+{
+    __shared__ u64 s_warp[40];
+    const u64 v = threadIdx.x < 256 ? digit_tot[threadIdx.x] : 0;
+    u64 tot;
+    const u64 ex = block_excl_scan(v, s_warp, &tot);
+    if (threadIdx.x < 256) digit_tot[threadIdx.x] = (uint32_t)ex;
 }
 
 // stable scatter: rank of a key = global base of (digit, CTA) + keys of the same digit earlier in the CTA's tile
 __global__ void __launch_bounds__(kStageBlock)
 k_rs_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ keys_out,
              uint32_t *__restrict__ vals_out, const int *__restrict__ n_dev, const int shift, const int n_blocks,
-             const uint32_t *__restrict__ hist, const int first_pass)
+             const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_base, const int first_pass)
 {
     __shared__ uint32_t s_base[256];              // running output position of each digit for this CTA
     __shared__ uint32_t s_cnt[kStageBlock / 32][256]; // per-warp digit counts of the current slice
     const int n = *n_dev;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    s_base[tid] = hist[tid * n_blocks + blockIdx.x];
+    s_base[tid] = digit_base[tid] + hist[tid * n_blocks + blockIdx.x];
     const int base = blockIdx.x * kSortTile;
     for (int i = 0; i < kSortItems; ++i) { // slices of 256 consecutive keys keep the pass stable
         for (int k = tid; k < (kStageBlock / 32) * 256; k += kStageBlock) (&s_cnt[0][0])[k] = 0;
