@@ -74,6 +74,7 @@ struct esl_ctx {
 
     DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_mrec, d_mpmax, d_grp, d_mgrid;
     DevBuf d_raw_ts, d_raw_te, d_raw_tb; // targets in caller order (staged baseline)
+    DevBuf d_pool_stats;
     DevBuf d_sgrid;
     int sgrid_n = 0, sgrid_shift = 0; // shared-memory copy of the first-layer grids (0 = does not fit)
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
@@ -595,32 +596,25 @@ int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n)
 {
     if (!ctx) return ESL_ERR_INVALID;
     if (!lengths || n < 1 || n > 0xFFFFFFFFll) return ctx->fail(ESL_ERR_INVALID, "length table must hold 1 .. 2^32-1 entries");
-    // moments of the pool (they only steer how many draws the bulk pass takes, never the result): four independent
-    // double accumulators so the loop vectorises; relative error ~1e-13
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-    uint32_t mx = 0, mn = 0xFFFFFFFFu;
-    int64_t i = 0;
-    for (; i + 4 <= n; i += 4) {
-        const double v0 = lengths[i], v1 = lengths[i + 1], v2 = lengths[i + 2], v3 = lengths[i + 3];
-        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-        q0 += v0 * v0; q1 += v1 * v1; q2 += v2 * v2; q3 += v3 * v3;
-        const uint32_t hi4 = std::max(std::max(lengths[i], lengths[i + 1]), std::max(lengths[i + 2], lengths[i + 3]));
-        const uint32_t lo4 = std::min(std::min(lengths[i], lengths[i + 1]), std::min(lengths[i + 2], lengths[i + 3]));
-        mx = std::max(mx, hi4); mn = std::min(mn, lo4);
-    }
-    for (; i < n; ++i) {
-        const double v = lengths[i];
-        a0 += v; q0 += v * v;
-        mx = std::max(mx, lengths[i]); mn = std::min(mn, lengths[i]);
-    }
-    const long double s = (long double)a0 + a1 + a2 + a3, s2 = (long double)q0 + q1 + q2 + q3;
-    if (mn == 0) return ctx->fail(ESL_ERR_INVALID, "length table holds a zero-length read");
+    // upload, then reduce on the device: sum (exact), sum of squares (double), max and min
     CU(cudaSetDevice(ctx->device));
     CU(ctx->d_pool.upload(lengths, (size_t)n * sizeof(uint32_t)));
+    CU(ctx->d_pool_stats.reserve(32));
+    struct { u64 sum; double sq; uint32_t mx, mn; } h = {0, 0.0, 0u, 0xFFFFFFFFu};
+    CU(cudaMemcpy(ctx->d_pool_stats.p, &h, sizeof h, cudaMemcpyHostToDevice));
+    {
+        char *b8 = (char *)ctx->d_pool_stats.p;
+        const unsigned grid = (unsigned)std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 4);
+        esl::k_pool_moments<<<grid, 256>>>(ctx->d_pool.as<uint32_t>(), n, (u64 *)b8, (double *)(b8 + 8), (uint32_t *)(b8 + 16), (uint32_t *)(b8 + 20));
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    CU(cudaMemcpy(&h, ctx->d_pool_stats.p, sizeof h, cudaMemcpyDeviceToHost));
+    if (h.mn == 0) return ctx->fail(ESL_ERR_INVALID, "length table holds a zero-length read");
     ctx->n_pool = (uint32_t)n;
-    ctx->pool_max = mx;
-    const long double mean = s / (long double)n;
-    const long double var = s2 / (long double)n - mean * mean;
+    ctx->pool_max = h.mx;
+    const long double mean = (long double)h.sum / (long double)n;
+    const long double var = (long double)h.sq / (long double)n - mean * mean;
     ctx->pool_mean = (double)mean;
     ctx->pool_sd = var > 0 ? (double)sqrtl(var) : 0.0;
     ctx->have_pool = true;

@@ -897,6 +897,35 @@ k_thin_pairs(const i64 *__restrict__ hits, const double *__restrict__ u, const i
     atomicAdd(t + 2, (u64)ov);
 }
 
+// Moments of the length pool on the device (set-up): out = {sum, sum of squares (double bits), max, min}.  The
+// pool is uploaded anyway; reducing it there costs microseconds instead of a scalar pass over 10^6 host integers.
+__global__ void __launch_bounds__(256)
+k_pool_moments(const uint32_t *__restrict__ pool, const i64 n, u64 *__restrict__ out_sum, double *__restrict__ out_sq,
+               uint32_t *__restrict__ out_max, uint32_t *__restrict__ out_min)
+{
+    u64 s = 0;
+    double q = 0.0;
+    uint32_t mx = 0, mn = 0xFFFFFFFFu;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const uint32_t v = pool[i];
+        s += v; q += (double)v * (double)v;
+        mx = v > mx ? v : mx; mn = v < mn ? v : mn;
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+        const uint32_t a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+        mx = a > mx ? a : mx; mn = b < mn ? b : mn;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out_sum, s);
+        atomicAdd(out_sq, q);
+        atomicMax(out_max, mx);
+        atomicMin(out_min, mn);
+    }
+}
+
 // Per-target moment accumulators over the iterations of a batch (operand of the multi-GPU sum-reduce).
 __global__ void __launch_bounds__(256)
 k_moments(const i64 *__restrict__ tallies, const int n_iter, const i64 n_targets, i64 *__restrict__ mom)
