@@ -307,7 +307,7 @@ def run_ours(args, w):
             traffic = json.load(open(tp)).get(w["name"])  # bytes per launch, from the committed ncu capture
         # what actually binds the fused kernel, from the committed ncu capture of this workload (not measured live)
         binding = None
-        sp = os.path.join(ROOT, "profiles", f"r1f_bulk_{w['name']}_summary.json")
+        sp = os.path.join(ROOT, "profiles", f"r1h_bulk_{w['name']}_summary.json")
         if os.path.exists(sp):
             ps = json.load(open(sp))
             binding = {"source": os.path.relpath(sp, ROOT), "warp_instructions_per_read": round(ps["warp_instructions_per_read"], 1),
