@@ -274,7 +274,7 @@ def run_ours(args, w):
         sess.invalidate()
         its = range((10_000 + k * world + rank) * n_iter, (10_000 + k * world + rank) * n_iter + n_iter)
         res, _ = run_simulation_batch(its, params, w["genome_size"], w["targets"], masked_tree, device=local, to_host=True,
-                                      length_pools={0: pool})
+                                      length_pools={0: pool}, reuse_host_buffers=True)
         e2e_reads += int(res[0].n_reads.sum())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0

@@ -34,13 +34,15 @@ def group_hits(hits, n_iter, n_targets):
 
 
 def run_simulation_batch(iteration_ids, param_dictionary, genome_size, target_regions, masked_tree, device=0,
-                         to_host=True, length_pools=None, overlap_lists=False, hit_capacity=None):
+                         to_host=True, length_pools=None, overlap_lists=False, hit_capacity=None, reuse_host_buffers=False):
     """All combinations for a contiguous run of iterations.  Returns one BatchResult per combination (on the
     host when to_host) plus the target keys; iteration i of the batch is iteration_ids[0] + i.
     length_pools optionally maps a combination index to a ready-made host array of read lengths (already
     filtered by min_read_length), bypassing the FASTQ scan / log-normal draw.  With overlap_lists=True each
     BatchResult gets an `overlaps` attribute: per iteration, per target, the list of overlaps in read order (the
-    reference's `overlap` column); hit_capacity bounds the number of (target, read) pairs per combination."""
+    reference's `overlap` column); hit_capacity bounds the number of (target, read) pairs per combination.
+    Host copies go through page-locked staging tensors owned by the session; with reuse_host_buffers=True the
+    returned tensors ARE those staging tensors (valid until the next call) instead of private copies."""
     iteration_ids = list(iteration_ids)
     first, n_iter = iteration_ids[0], len(iteration_ids)
     if iteration_ids != list(range(first, first + n_iter)):
@@ -67,7 +69,10 @@ def run_simulation_batch(iteration_ids, param_dictionary, genome_size, target_re
         finally:
             if overlap_lists:
                 sess.engine.set_hit_buffer(0)
-        res = res.cpu() if to_host else res
+        if to_host:
+            staged = res.cpu(pinned=sess.pinned)
+            res = staged if (reuse_host_buffers and len(p["combinations"]) == 1) else type(staged)(*(t.clone() for t in (
+                staged.tallies, staged.label_counts, staged.n_bases, staged.n_reads, staged.status)))
         res.overlaps = overlaps
         out.append(res)
     return out, sess.keys

@@ -13,6 +13,7 @@ _sessions = {}
 class Session:
     def __init__(self, device=0):
         self.engine = Engine(device)
+        self.pinned = {}  # page-locked staging tensors for device -> host result copies (BatchResult.cpu)
         self.invalidate()
 
     def invalidate(self):
