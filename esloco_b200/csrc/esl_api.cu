@@ -65,7 +65,7 @@ struct esl_ctx {
     int n_seg = 0, n_tgrid = 0, n_trec = 0, n_mgrid = 0, n_mrec = 0;
     bool index_dirty = true;
     bool wide = false; // 64-bit coordinates
-    int n_layers = 0, n_first_layers = 0;
+    int n_layers = 0, n_first_layers = 0, cdf_walk = 0;
     i64 n_indexed = 0, n_mask = 0;
 
     // pool statistics
@@ -301,12 +301,17 @@ int upload_index(esl_ctx *ctx)
         cu[k] = v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
     }
     std::vector<uint16_t> lut(esl::kCdfLut);
-    int k = 0;
+    int k = 0, walk = 0;
     for (int q = 0; q < esl::kCdfLut; ++q) {
         const uint32_t w = (uint32_t)q << 22; // lowest draw of the slice
         while (k < B - 1 && cu[k] <= w) ++k;
         lut[q] = (uint16_t)k;
+        const uint32_t w_hi = w | 0x3FFFFFu; // highest draw of the slice
+        int k2 = k;
+        while (k2 < B - 1 && cu[k2] <= w_hi) ++k2;
+        walk = std::max(walk, k2 - k);
     }
+    ctx->cdf_walk = walk;
     CU(ctx->d_cdf.upload(ctx->cdf.data(), B * sizeof(double)));
     CU(ctx->d_cdf_u32.upload(cu.data(), B * sizeof(uint32_t)));
     CU(ctx->d_cdf_lut.upload(lut.data(), lut.size() * sizeof(uint16_t)));
@@ -347,6 +352,9 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.cdf = ctx->d_cdf.as<double>();
     d.cdf_u32 = ctx->d_cdf_u32.as<uint32_t>();
     d.cdf_lut = ctx->d_cdf_lut.as<uint16_t>();
+    d.cdf_walk = ctx->cdf_walk;
+    d.min_ov32 = min_overlap <= 0 ? 0u : (min_overlap > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)min_overlap);
+    d.thin = scaling < 1.0;
     d.trec = ctx->d_trec.as<esl::TargetRec<C>>();
     d.te = ctx->d_te.as<C>();
     d.seg = ctx->d_seg.as<esl::SegDesc>();

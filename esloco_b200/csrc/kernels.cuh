@@ -147,6 +147,9 @@ struct DevCtx {
     const double *__restrict__ cdf;       // numpy-style cdf, replay path
     const uint32_t *__restrict__ cdf_u32; // ceil(cdf * 2^32) saturated, native path
     const uint16_t *__restrict__ cdf_lut; // [kCdfLut] barcode of the lowest u32 in each of kCdfLut equal slices
+    int cdf_walk;                         // most thresholds inside one slice (steps the walk after the table needs)
+    uint32_t min_ov32;                    // min_overlap clamped to [0, 2^32-1] (an overlap never exceeds a read length)
+    int thin;                             // scaling < 1: draw a thinning uniform per qualifying pair
     // target index: per barcode a run of "monotone layers" (starts AND ends ascending inside a layer), so the
     // targets a read overlaps are one contiguous range per layer.  seg[b], b < B, is barcode b's first layer;
     // its extra layers (nesting targets only) are seg[B + extra_off[b] ...].
@@ -216,7 +219,11 @@ struct PhiloxSrc {
         int k = 0;
         if (cx.n_barcodes > 1) { // searchsorted(cdf, u, side='right') on integer thresholds: table start + short walk
             k = s_lut[r.w >> 22];
-            while (k < cx.n_barcodes - 1 && s_cdf[k] <= r.w) ++k;
+            // a slice of the start table holds at most cx.cdf_walk thresholds: one branch-free step covers almost
+            // every CDF; the loop only exists for more than ~1000 barcodes or pathological weights
+            k += (k < cx.n_barcodes - 1 && s_cdf[k] <= r.w) ? 1 : 0;
+            if (cx.cdf_walk > 1)
+                while (k < cx.n_barcodes - 1 && s_cdf[k] <= r.w) ++k;
         }
         bc = k;
     }
@@ -356,7 +363,7 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
         if (r.s >= re) break; // starts ascend: nothing further overlaps
         if (r.e > rs) {       // (an end inside the bucket but before the read does not overlap)
             const C ov = (r.e < re ? r.e : re) - (r.s > rs ? r.s : rs);
-            if ((i64)ov >= cx.min_overlap && !(cx.scaling < 1.0 && !(src.scale_u(it, n, r.row & 0x7fffffff) <= cx.scaling))) {
+            if ((u64)ov >= (u64)cx.min_ov32 && !(cx.thin && !(src.scale_u(it, n, r.row & 0x7fffffff) <= cx.scaling))) {
                 const int kind = (rs <= r.s && r.e <= re) ? 0 : 1;
                 const int row = r.row & 0x7fffffff;
                 u64 *t = tallies_it + (i64)row * 3;
@@ -448,7 +455,8 @@ __device__ __forceinline__ int label_slot(int label, int B) { return label >= 0 
 
 // Shared-memory label histogram update, called by ALL lanes of a warp (slot < 0 = nothing to add).  Lanes with
 // the same slot are combined with match.any so one 32-bit ATOMS per distinct label is issued (64-bit shared
-// atomics are CAS loops and serialise badly when every lane hits the same counter).
+// atomics are CAS loops; and plain per-lane 32-bit atomics, tried in round 1, serialise 32-fold when a masked
+// single-barcode run sends every lane to the same counter: config 4 lost a third of its throughput).
 __device__ __forceinline__ void hist_add(int *s_hist, int slot, int delta)
 {
     const unsigned peers = __match_any_sync(0xffffffffu, slot);
