@@ -316,7 +316,7 @@ def run_ours(args, w):
                        "dram_bytes_per_launch": sum(float(ps[k] or 0) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(ps["units"].get(k), 1)
                                                     for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))}
         n_thr = host_threads(w)
-        if args.no_cpu_baseline:
+        if args.no_cpu_baseline or world > 1:  # the CPU baseline is reported at N = 1 only
             cpu = None
         else:
             r, it, dt = cpu_port_sample(w, n_thr)
