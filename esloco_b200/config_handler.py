@@ -89,65 +89,78 @@ def random_seed():
     return np.random.randint(0, 2**32 - 1)
 
 
+# [COMMON] options: (key, reader, default) in the order the reference's parameter dictionary lists them
+# (config_handler.py:70-129); `None` reader = plain string.
+_COMMON = (
+    ("sequenced_data_path", None, None), ("sigma", "int", 1), ("output_path", None, "./output/"),
+    ("experiment_name", None, "default_experiment"), ("output_path_plots", None, "<output_path>"),
+    ("min_overlap_for_detection", "int", 1), ("chr_restriction", None, None), ("barcode_weights", "literal", None),
+    ("n_barcodes", "int", 1), ("iterations", "int", 1), ("scaling", "float", 1.0), ("min_read_length", "int", 1),
+    ("no_cov_plots", "bool", False), ("parallel_jobs", "int", 1), ("seed", "int", "<random>"),
+    ("coverages", "json_list", "[1]"), ("mean_read_lengths", "json_list", "[10000]"),
+    ("overlap_lists", "bool", False),  # extension: fill the per-read `overlap` column
+    ("blocked_regions_bedpath", None, None), ("consuming", "bool", False),
+)
+_MODE = {
+    "ROI": (("roi_bedpath", None, None),),
+    "I": (("insertion_length", "int", 1000), ("insertion_number_distribution", None, None), ("bedpath", None, None),
+          ("insertion_numbers", "float", 5.0)),
+}
+
+
+def _read(config, section, key, kind, default):
+    if kind == "int":
+        return config.getint(section, key, fallback=default)
+    if kind == "float":
+        return config.getfloat(section, key, fallback=default)
+    if kind == "bool":
+        return config.getboolean(section, key, fallback=default)
+    if kind == "literal":  # Python literal, the string "None" meaning absent (barcode_weights)
+        text = config.get(section, key, fallback="None")
+        return ast.literal_eval(text) if text != "None" else None
+    if kind == "json_list":  # JSON scalar or list -> list
+        value = json.loads(config.get(section, key, fallback=default))
+        return value if isinstance(value, list) else [value]
+    return config.get(section, key, fallback=default)
+
+
 def parse_config(config_file):
-    """[COMMON]/[ROI]/[I] INI -> parameter dict with the reference's keys and defaults (config_handler.py:59-152)."""
+    """[COMMON]/[ROI]/[I] INI -> parameter dict with the reference's keys, types and defaults
+    (config_handler.py:59-152, README.md:76-114): creates the output directories, replaces mean_read_lengths by the
+    integer mean of the sequencing data when sequenced_data_path is set, adds `combinations`.  Any problem prints
+    "Configuration parsing failed" and exits with status 1, as the reference does."""
     try:
         config = configparser.ConfigParser()
         config.read(config_file)
-        mode = config.get("COMMON", "mode", fallback=None)
-        reference_genome_path = config.get("COMMON", "reference_genome_path", fallback=None)
-        if mode is None:
-            print("Missing required parameter: mode")
-            raise ValueError("Missing required parameter: mode")
-        if reference_genome_path is None:
-            print("Missing required parameter: reference_genome_path")
-            raise ValueError("Missing required parameter: reference_genome_path")
-        sequenced_data_path = config.get("COMMON", "sequenced_data_path", fallback=None)
-        sigma = config.getint("COMMON", "sigma", fallback=1)
-        output_path = config.get("COMMON", "output_path", fallback="./output/")
-        experiment_name = config.get("COMMON", "experiment_name", fallback="default_experiment")
-        output_path_plots = config.get("COMMON", "output_path_plots", fallback=output_path)
-        min_overlap_for_detection = config.getint("COMMON", "min_overlap_for_detection", fallback=1)
-        chr_restriction = config.get("COMMON", "chr_restriction", fallback=None)
-        barcode_weights = config.get("COMMON", "barcode_weights", fallback="None")
-        barcode_weights = ast.literal_eval(barcode_weights) if barcode_weights != "None" else None
-        n_barcodes = config.getint("COMMON", "n_barcodes", fallback=1)
-        iterations = config.getint("COMMON", "iterations", fallback=1)
-        scaling = config.getfloat("COMMON", "scaling", fallback=1.0)
-        min_read_length = config.getint("COMMON", "min_read_length", fallback=1)
-        no_cov_plots = config.getboolean("COMMON", "no_cov_plots", fallback=False)
-        parallel_jobs = config.getint("COMMON", "parallel_jobs", fallback=1)
-        seed = config.getint("COMMON", "seed", fallback=random_seed())
-        for path in (output_path, output_path_plots):
-            if not os.path.exists(path):
-                os.makedirs(path)
-        coverages = json.loads(config.get("COMMON", "coverages", fallback="[1]"))
-        if not isinstance(coverages, list):
-            coverages = [coverages]
-        mean_read_lengths = json.loads(config.get("COMMON", "mean_read_lengths", fallback="[10000]"))
-        if not isinstance(mean_read_lengths, list):
-            mean_read_lengths = [mean_read_lengths]
-        if sequenced_data_path:
-            print("Sequencing data provided. Calculating the mean read length may take a while...")
-            logging.info("Sequencing data provided. Calculating the mean read length may take a while...")
-            mrl = int(seq_read_data(sequenced_data_path, min_read_length=min_read_length))
-            logging.info(f"Mean read length set to: {mrl}")
-            mean_read_lengths = [mrl]
-        overlap_lists = config.getboolean("COMMON", "overlap_lists", fallback=False)  # extension: fill the `overlap` column
-        blocked_regions_bedpath = config.get("COMMON", "blocked_regions_bedpath", fallback=None)
-        consuming = config.getboolean("COMMON", "consuming", fallback=False)
-        if mode == "ROI":
-            roi_bedpath = config.get("ROI", "roi_bedpath", fallback=None)
-        elif mode == "I":
-            insertion_length = config.getint("I", "insertion_length", fallback=1000)
-            insertion_number_distribution = config.get("I", "insertion_number_distribution", fallback=None)
-            bedpath = config.get("I", "bedpath", fallback=None)
-            insertion_numbers = config.getfloat("I", "insertion_numbers", fallback=5.0)
-        else:
+        params = {"config_file": config_file}
+        for required in ("mode", "reference_genome_path"):
+            params[required] = config.get("COMMON", required, fallback=None)
+            if params[required] is None:
+                print(f"Missing required parameter: {required}")
+                raise ValueError(f"Missing required parameter: {required}")
+        if params["mode"] not in _MODE:
             print("Invalid mode selected. Exiting.")
             raise ValueError("Invalid mode selected. Allowed values: 'ROI' or 'I'.")
-        combinations = list(itertools.product(mean_read_lengths, coverages))
-        return {k: v for k, v in locals().items() if k != "config" and k != "path" and not k.startswith("_")}
+        for key, kind, default in _COMMON:
+            if default == "<output_path>":
+                default = params["output_path"]
+            elif default == "<random>":
+                default = random_seed()
+            params[key] = _read(config, "COMMON", key, kind, default)
+        for path in (params["output_path"], params["output_path_plots"]):
+            if not os.path.exists(path):
+                os.makedirs(path)
+        if params["sequenced_data_path"]:
+            print("Sequencing data provided. Calculating the mean read length may take a while...")
+            logging.info("Sequencing data provided. Calculating the mean read length may take a while...")
+            mrl = int(seq_read_data(params["sequenced_data_path"], min_read_length=params["min_read_length"]))
+            logging.info(f"Mean read length set to: {mrl}")
+            params["mean_read_lengths"] = [mrl]
+            params["mrl"] = mrl  # the reference's dictionary is its locals(), so this helper shows up there too
+        for key, kind, default in _MODE[params["mode"]]:
+            params[key] = _read(config, params["mode"], key, kind, default)
+        params["combinations"] = list(itertools.product(params["mean_read_lengths"], params["coverages"]))
+        return params
     except Exception as e:
         print("Configuration parsing failed: ", e)
         sys.exit(1)

@@ -145,3 +145,27 @@ def test_fasta_byte_scanner_chunk_boundaries(tmp_path):
     with gzip.open(gz, "wt") as fh:
         fh.write(text)
     assert list(fasta_contig_lengths(str(gz), 5)) == expect
+
+
+def test_parse_config_matches_reference(tmp_path):
+    """parse_config returns the reference's parameter dictionary (keys, types, defaults, derived values) for the INI
+    files recorded from the unmodified reference in tests/golden/config_golden.json (+ the `overlap_lists` extension)."""
+    import json
+    from esloco_b200.config_handler import parse_config
+    tmp = str(tmp_path)
+    with open(os.path.join(tmp, "reads.fastq"), "w") as fh:
+        for i, n in enumerate((10, 30, 55, 100, 21)):
+            fh.write(f"@r{i}\n{'A' * n}\n+\n{'I' * n}\n")
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_golden.json")))
+    assert len(cases) >= 4
+    for k, case in enumerate(cases):
+        ini = os.path.join(tmp, f"c{k}.ini")
+        open(ini, "w").write(case["ini"].replace("{tmp}", tmp))
+        got = parse_config(ini)
+        assert got.pop("overlap_lists") is False
+        got = json.loads(json.dumps(got, default=str).replace(tmp, "{tmp}"))
+        assert got == case["params"], k
+    bad = os.path.join(tmp, "bad.ini")
+    open(bad, "w").write("[COMMON]\nmode = X\nreference_genome_path = a\n")
+    with pytest.raises(SystemExit):
+        parse_config(bad)
