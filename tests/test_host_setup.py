@@ -169,3 +169,51 @@ def test_parse_config_matches_reference(tmp_path):
     open(bad, "w").write("[COMMON]\nmode = X\nreference_genome_path = a\n")
     with pytest.raises(SystemExit):
         parse_config(bad)
+
+
+def _jsonable(x):
+    if isinstance(x, dict):
+        return {str(k): _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, np.integer):
+        return int(x)
+    if isinstance(x, np.floating):
+        return float(x)
+    return x
+
+
+def test_bed_variants_match_reference(tmp_path):
+    """Header-less BEDs, BED-guided insertion placement (length-weighted, explicit weights, one insertion per row) and
+    Poisson insertion counts: same targets / masked regions as the unmodified reference for the same numpy seed, and
+    the numpy stream is left at the same position (tests/golden/setup_golden.json)."""
+    import json
+    from esloco_b200.genome_generation import create_barcoded_insertion_genome, create_barcoded_roi_genome
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "setup_golden.json")))
+    assert len(cases) >= 5
+    for g in cases:
+        c = g["case"]
+        tmp = str(tmp_path / c["name"])
+        os.makedirs(tmp)
+        fasta = os.path.join(tmp, "g.fa")
+        write_fasta(fasta, g["contigs"])
+
+        def bed(spec, name):
+            if spec is None:
+                return None
+            p = os.path.join(tmp, name)
+            write_bed(p, spec[0], spec[1])
+            return p
+        blocked = bed(c.get("blocked"), "blocked.bed")
+        np.random.seed(c["seed"])
+        if c["mode"] == "I":
+            G, targets, masked, cdir = create_barcoded_insertion_genome(
+                1, fasta, bed(c.get("guide"), "guide.bed"), blocked, None, c["insertion_length"], c["insertion_numbers"], c["dist"],
+                c["n_barcodes"])
+        else:
+            targets, _bed, masked, G, cdir = create_barcoded_roi_genome(fasta, None, bed(c["roi"], "roi.bed"), c["n_barcodes"], blocked)
+        assert G == g["genome_size"], c["name"]
+        assert _jsonable(cdir) == g["chromosome_dir"], c["name"]
+        assert _jsonable(targets) == g["targets"], c["name"]
+        assert _jsonable(masked) == g["masked"], c["name"]
+        assert float(np.random.rand()) == g["stream_tail"], c["name"]
