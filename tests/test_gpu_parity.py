@@ -572,3 +572,31 @@ def test_staged_baseline_larger_run(eng):
     for a, b in ((staged.n_reads, fused.n_reads), (staged.n_bases, fused.n_bases), (staged.label_counts, fused.label_counts),
                  (staged.tallies, fused.tallies)):
         assert np.array_equal(a.numpy(), b.numpy())
+
+
+def test_full_size_config2_replay_of_reference_stream(eng):
+    """BASELINE.json configs[1] at FULL size, replay check: the oracle (pinned to the reference by the golden files)
+    produces the reference's numpy-stream draws for one hg38-size iteration from a seed -- 1 M log-normal pool, 62 M
+    resample, ~6.2 M placed reads, oversampled by 50 k draws; the device does the cut-off and the tally from the raw
+    draws, and must match the oracle's (faithful O(T*R)) tally, N_bases and read count bit for bit."""
+    from esloco_b200 import synthetic as S
+    from esloco_b200.utils import targets_to_arrays
+    G, _ = S.chromosome_dir(S.HG38)
+    np.random.seed(20261019)
+    from esloco_b200.create_insertion_genome import add_insertions_to_genome_sequence_with_bed
+    _, cdir = S.chromosome_dir(S.HG38)
+    targets = add_insertions_to_genome_sequence_with_bed(G, 5000, 100, {f"Barcode_0_{k}": v for k, v in cdir.items()})
+    keys, ts, te, tb = targets_to_arrays(targets, 1)
+    rng = O.Rng(424242)
+    out = O.process_combination(rng, 15000, 30, G, ts, te, tb, 1, None, False, None, 1, 1, 1.0, 1, n_extra=50_000, record_draws=True)
+    pl = out["placement"]
+    n_placed, n_total = pl["n_placed"], pl["start"].size
+    assert 6_000_000 < n_placed < 6_400_000 and n_total == n_placed + 50_000
+    eng.set_genome(G); eng.set_barcode_cdf([1.0]); eng.set_targets(ts, te, tb); eng.set_blocked()
+    for bulk in (0, n_placed - 30_000, n_total):  # cut-off kernel only / normal split / overshoot + take-back
+        res = eng.replay_draws(pl["u_barcode"], pl["length"], pl["start"], [0, n_total], 30, bulk_draws=bulk).cpu()
+        t = res.tallies[0].numpy()
+        assert int(res.n_reads[0]) == n_placed and int(res.n_bases[0]) == pl["covered_length"]
+        assert np.array_equal(t[:, 0], out["full"]) and np.array_equal(t[:, 1], out["partial"]) and np.array_equal(t[:, 2], out["otb"])
+        assert int(res.label_counts[0, 0]) == n_placed and not int(res.status[0]) & 2
+    assert out["otb"].sum() > 0
