@@ -255,6 +255,7 @@ int upload_index(esl_ctx *ctx)
     }
     CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>)));
     CU(ctx->d_te.upload(te.data(), te.size() * sizeof(C)));
+    if (seg.size() >= ((size_t)1 << esl::kQueueSegBits)) return ctx->fail(ESL_ERR_UNSUPPORTED, "too many target layers (barcodes + nesting levels must stay below 2^22)");
     ctx->n_seg = (int)seg.size(); ctx->n_tgrid = (int)tgrid.size(); ctx->n_trec = (int)trec.size();
     CU(ctx->d_raw_ts.upload(ctx->t_start.data(), ctx->t_start.size() * sizeof(i64)));
     CU(ctx->d_raw_te.upload(ctx->t_end.data(), ctx->t_end.size() * sizeof(i64)));
@@ -393,7 +394,9 @@ size_t bulk_smem(const esl_ctx *ctx)
 {
     const int B = ctx->B;
     const size_t entry = ctx->wide ? 8 : 4;
-    return (size_t)B * ctx->sgrid_n * entry + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
+    const size_t item = ctx->wide ? sizeof(esl::WalkItem<uint64_t>) : sizeof(esl::WalkItem<uint32_t>);
+    const size_t queues = ctx->sgrid_n ? 0 : (size_t)(esl::kBulkBlock / 32) * esl::kQueueCap * item; // per-warp candidate queues
+    return queues + (size_t)B * ctx->sgrid_n * entry + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
            (size_t)esl::kCdfLut * 2 + 32;
 }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
@@ -433,8 +436,10 @@ int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const es
 {
     const i64 total_tiles = r.tiles * n_iter;
     if (total_tiles <= 0) return ESL_OK;
-    auto kern = dc.has_mask ? esl::k_place_tally_bulk<C, Src, true> : esl::k_place_tally_bulk<C, Src, false>;
+    auto kern = dc.sgrid ? (dc.has_mask ? esl::k_place_tally_bulk<C, Src, true, true> : esl::k_place_tally_bulk<C, Src, false, true>)
+                         : (dc.has_mask ? esl::k_place_tally_bulk<C, Src, true, false> : esl::k_place_tally_bulk<C, Src, false, false>);
     int occ = 0;
+    if (bulk_smem(ctx) > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem(ctx)));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx)));
     if (occ < 1) occ = 1;
     const i64 grid = std::min<i64>(total_tiles, (i64)ctx->sm_count * occ);

@@ -42,6 +42,15 @@ constexpr int kBulkTile = kBulkBlock * kBulkIpt;
 #define ESL_BULK_MIN_BLOCKS 5
 #endif
 constexpr int kBulkMinBlocks = ESL_BULK_MIN_BLOCKS; // register cap: 65536 / (256 * min blocks)
+#ifndef ESL_BULK_MIN_BLOCKS_GENERAL
+#define ESL_BULK_MIN_BLOCKS_GENERAL 4
+#endif
+// The general variant of the kernel (candidate queues, any number of targets and layers) needs 62 registers to stay
+// free of spills: 4 CTAs/SM.  Measured on config 3: queue @4 96 G reads/s, queue @5 with 120 B of spills 83 G,
+// direct walks @5 85 G, direct walks @4 81 G.  64-bit coordinates (genomes above 4 Gb) cost one CTA/SM more.
+constexpr int kBulkMinBlocksGeneral = ESL_BULK_MIN_BLOCKS_GENERAL;
+template <typename C, bool kShared>
+constexpr int bulk_min_blocks() { return (kShared ? kBulkMinBlocks : kBulkMinBlocksGeneral) - (sizeof(C) == 8 ? 1 : 0); }
 constexpr int kTailBlock = 1024;
 constexpr int kTailIpt = 2;
 constexpr int kTailChunk = kTailBlock * kTailIpt;
@@ -303,9 +312,9 @@ struct Probe {
 template <typename C>
 __device__ __forceinline__ Probe<C> probe(const SegDesc *descs, int idx, const GridEntry<C> *grid, C rs)
 {
-    const SegDesc d = load_desc(descs + idx);
-    const GridEntry<C> e = load_entry(grid + d.grid_off + (int)((u64)rs >> (d.flags & 0xff)));
-    ESL_CHK(e.j >= d.lo && e.j <= d.hi, "grid entry outside its run");
+    const int2 d = __ldg(reinterpret_cast<const int2 *>(descs + idx) + 1); // {grid_off, flags}: half a descriptor, half the registers
+    const GridEntry<C> e = load_entry(grid + d.x + (int)((u64)rs >> (d.y & 0xff)));
+    ESL_CHK(e.j >= descs[idx].lo && e.j <= descs[idx].hi, "grid entry outside its run");
     return Probe<C>{e.j, e.s};
 }
 
@@ -493,6 +502,45 @@ __device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
     return v;
 }
 
+// ---------------------------------------------------------------- per-warp candidate queue
+//
+// Only a few lanes of a warp have a target candidate for a given read (config 3: 6 %, config 4: about half), so
+// walking the candidates where they are found runs the whole walk at a few lanes' occupancy, once per read slot
+// and layer.  Instead every (read, layer, first candidate) whose probe says "maybe" is pushed to a queue in shared
+// memory owned by the warp, and the warp drains the queue 32 items at a time with all lanes busy.
+template <typename C> struct WalkItem;
+template <> struct __align__(16) WalkItem<uint32_t> { uint32_t st, L; int a; uint32_t sg_n; };
+template <> struct __align__(8) WalkItem<uint64_t> { uint64_t st; uint32_t L; int a; uint32_t sg_n, pad; };
+constexpr int kQueueCap = 128;    // items per warp; drained early when a tile row (32 lanes x kBulkIpt reads) may not fit
+constexpr int kQueueSegBits = 22; // sg_n = run index | (draw offset inside the tile << 22); host checks n_seg < 2^22
+static_assert(kBulkTile <= (1 << (32 - kQueueSegBits)), "draw offset must fit above the run index");
+
+// Called by all 32 lanes; n (the queue length) is warp-uniform.
+template <typename C>
+__device__ __forceinline__ void queue_push(WalkItem<C> *q, int &n, bool want, C st, uint32_t L, int a, uint32_t sg_n)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (want) {
+        WalkItem<C> w;
+        w.st = st; w.L = L; w.a = a; w.sg_n = sg_n;
+        q[n + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = w;
+    }
+    n += __popc(m);
+}
+template <typename C, typename Src>
+__device__ __forceinline__ void queue_drain(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
+                                            int it, uint32_t base, const WalkItem<C> *q, int &n)
+{
+    __syncwarp();
+    for (int k = threadIdx.x & 31; k < n; k += 32) {
+        const WalkItem<C> w = q[k];
+        tally_layer(cx, src, out, tallies_it, it, (i64)(base + (w.sg_n >> kQueueSegBits)), (int)(w.sg_n & ((1u << kQueueSegBits) - 1u)),
+                    w.a, w.st, (C)(w.st + w.L), 1);
+    }
+    __syncwarp();
+    n = 0;
+}
+
 // ---------------------------------------------------------------- bulk kernel
 
 // Persistent flat grid; CTA c owns a contiguous run of (iteration, tile) pairs.  One launch covers the absolute
@@ -505,21 +553,24 @@ __device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
 //   1 draw  2 blocked probes / slow path  3 label histogram  4 target probes / slow path  5 tile sum
 // There is no block barrier inside the tile loop: warps only meet when the CTA moves to the next iteration and
 // flushes its shared label histogram.
-template <typename C, typename Src, bool kMask>
-__global__ void __launch_bounds__(kBulkBlock, kBulkMinBlocks)
+template <typename C, typename Src, bool kMask, bool kShared>
+__global__ void __launch_bounds__(kBulkBlock, bulk_min_blocks<C, kShared>())
 k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src src, const DevOut out, const i64 *__restrict__ lo_arr,
                    const i64 lo_const, const i64 *__restrict__ hi_arr, const i64 hi_const, const int tile0,
                    const int tiles_launch, const i64 total_tiles)
 {
     extern __shared__ u64 smem[];
     const int B = cx.n_barcodes;
-    const int n_sgrid = cx.sgrid ? B * cx.sgrid_n : 0;
-    int4 *s_desc = (int4 *)smem;                                // [min(B, kSmemDescs)] first-layer descriptors
+    const int n_sgrid = kShared ? B * cx.sgrid_n : 0; // kShared: small target sets with a shared-memory pre-filter grid
+    // candidate queues first (16-byte aligned); the shared pre-filter path tallies in place and has none
+    WalkItem<C> *queue = (WalkItem<C> *)smem + (threadIdx.x >> 5) * kQueueCap;
+    const size_t q_words = kShared ? 0 : (size_t)(kBulkBlock / 32) * kQueueCap * sizeof(WalkItem<C>) / 8;
+    int4 *s_desc = (int4 *)(smem + q_words);                    // [min(B, kSmemDescs)] first-layer descriptors
     const int n_sdesc = B <= kSmemDescs ? B : 0;
     int *s_hist = (int *)(s_desc + n_sdesc);                    // [B + 2] reads per label since the last flush
     uint32_t *s_cdf = (uint32_t *)(s_hist + B + 2);             // [B]
     uint16_t *s_lut = (uint16_t *)(s_cdf + B);                  // [kCdfLut]
-    C *s_grid = (C *)(smem + ((size_t)n_sdesc * 16 + (size_t)(2 * B + 2) * 4 + (size_t)kCdfLut * 2 + 15) / 8); // [B][sgrid_n]
+    C *s_grid = (C *)(smem + q_words + ((size_t)n_sdesc * 16 + (size_t)(2 * B + 2) * 4 + (size_t)kCdfLut * 2 + 15) / 8); // [B][sgrid_n]
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < n_sgrid; i += kBulkBlock) s_grid[i] = cx.sgrid[i];
     for (int i = tid; i < n_sdesc; i += kBulkBlock) s_desc[i] = __ldg(reinterpret_cast<const int4 *>(cx.seg + i));
@@ -612,7 +663,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             for (int i = 0; i < kBulkIpt; ++i)
                 hist_add(s_hist, label[i] != kLabelInvalid && label[i] < B ? label_slot(label[i], B) : -1, 1, B + 2);
         }
-        if (n_sgrid) { // phase 4, small target sets (block-uniform): shared-memory pre-filter, exact path for the rest
+        if (kShared) { // phase 4, small target sets: shared-memory pre-filter, exact path for the rest
 #pragma unroll
             for (int i = 0; i < kBulkIpt; ++i) {
                 const bool ok = label[i] >= 0 && label[i] < B;
@@ -632,7 +683,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                                            st[i], (C)(st[i] + L[i]), 1);
                 }
             }
-        } else { // phase 4: targets -- first layer probed for all reads, then the candidate walks of the few "maybe"s
+        } else { // phase 4: targets -- probe the layers for all reads, queue the "maybe"s, drain the queue converged
             Probe<C> pt[kBulkIpt];
 #pragma unroll
             for (int i = 0; i < kBulkIpt; ++i) {
@@ -643,22 +694,42 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 const GridEntry<C> e = load_entry(cx.tgrid + dv.z + (int)((u64)st[i] >> (dv.w & 0xff)));
                 pt[i] = Probe<C>{e.j, ok ? e.s : (C) ~(C)0};
             }
+            int qn = 0;
 #pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i) {
-                const C re = (C)(st[i] + L[i]);
-                if (pt[i].s < re)
-                    tally_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), label[i], pt[i].a, st[i], re, 1);
-            }
-            if (cx.any_extra) { // nesting targets somewhere: visit the extra layers of each read's barcode
+            for (int i = 0; i < kBulkIpt; ++i)
+                queue_push(queue, qn, pt[i].s < (C)(st[i] + L[i]), st[i], L[i], pt[i].a,
+                           (uint32_t)label[i] | (uint32_t)(i * kBulkBlock + tid) << kQueueSegBits);
+            if (cx.any_extra) { // nesting targets somewhere: layer k of every read's barcode, k ascending
+                int ne_max = 0;
 #pragma unroll
-                for (int i = 0; i < kBulkIpt; ++i) { // (unrolled: dynamic indexing would push the arrays to local memory)
-                    if (label[i] < 0 || label[i] >= B) continue;
-                    const int n_extra = (int)((uint32_t)__ldg(&cx.seg[label[i]].flags) >> 16);
-                    if (n_extra)
-                        tally_extra_layers(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), label[i], n_extra,
-                                           st[i], (C)(st[i] + L[i]), 1);
+                for (int i = 0; i < kBulkIpt; ++i) {
+                    const bool ok = label[i] >= 0 && label[i] < B;
+                    const int ne = ok ? (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16) : 0;
+                    ne_max = ne > ne_max ? ne : ne_max;
+                }
+                ne_max = __reduce_max_sync(0xffffffffu, ne_max);
+                for (int k = 0; k < ne_max; ++k) {
+                    Probe<C> pe[kBulkIpt];
+                    int sg[kBulkIpt];
+#pragma unroll
+                    for (int i = 0; i < kBulkIpt; ++i) { // (layer counts re-read from shared memory: keeping them live spills)
+                        const bool ok = label[i] >= 0 && label[i] < B;
+                        const int ne = ok ? (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16) : 0;
+                        pe[i] = Probe<C>{0, (C) ~(C)0};
+                        sg[i] = 0;
+                        if (k < ne) {
+                            sg[i] = B + __ldg(cx.extra_off + label[i]) + k;
+                            pe[i] = probe(cx.seg, sg[i], cx.tgrid, st[i]);
+                        }
+                    }
+                    if (qn > kQueueCap - 32 * kBulkIpt) queue_drain(cx, src, out, tallies_it, it, base, queue, qn);
+#pragma unroll
+                    for (int i = 0; i < kBulkIpt; ++i)
+                        queue_push(queue, qn, pe[i].s < (C)(st[i] + L[i]), st[i], L[i], pe[i].a,
+                                   (uint32_t)sg[i] | (uint32_t)(i * kBulkBlock + tid) << kQueueSegBits);
                 }
             }
+            queue_drain(cx, src, out, tallies_it, it, base, queue, qn);
         }
         my = warp_sum_redux(my); // phase 5: tile sum (read only when the cut-off has to be taken back)
         if (lane == 0) {
