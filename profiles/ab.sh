@@ -1,3 +1,4 @@
+# A/B of library variants built by profiles/mkvar.sh on one GPU box: VARS="a b" WLS="cfg2 cfg3" bash profiles/ab.sh
 set -e
 VARS=${VARS:-"base queue2 queue3"}; WLS=${WLS:-"cfg2 cfg3 cfg4 chr"}
 for v in $VARS; do for w in $WLS; do
