@@ -113,32 +113,65 @@ namespace {
 
 struct Rec { i64 s, e; int32_t row; };
 
-// Split one barcode's targets (sorted by start, end) into the fewest layers whose ends are non-decreasing:
-// first-fit on the layers' last ends (patience sorting).  Non-nesting target sets give one layer.
-void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers)
+// Split one barcode's targets (sorted by start, end) into layers the device can scan front to back.  A read
+// [rs, re) walks a layer from the first record whose running max of ends exceeds rs until a start reaches re, so
+// every record in between that ended before rs is a wasted ("dead") load.  A layer whose ends never decrease has
+// none; strict patience sorting gives that, but random ROIs of mixed lengths nest all the time (50 k ROIs of
+// 1-100 kb: 9 strict layers, each costing every read a probe).  So nesting is tolerated while it stays cheap:
+// first-fit into the first layer where (a) at most kDeadScan records separate the target from the oldest record
+// still open at its start (bounds the dead loads of any read) and (b) the layer's summed dead spans
+// (max end so far - end) stay below a quarter of the genome (bounds them on average: < 0.25 per read).
+// Whole-chromosome ROIs over many small ones still split into two layers; 50 k mixed ROIs become one.
+// Layers past the 64th are strictly monotone (binary search), so pathological nesting stays O(n log n).
+constexpr int kDeadScan = 16;
+constexpr size_t kRelaxedLayers = 64;
+void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers, u64 G)
 {
     std::sort(v.begin(), v.end(), [](const Rec &a, const Rec &b) {
         if (a.s != b.s) return a.s < b.s;
         if (a.e != b.e) return a.e < b.e;
         return a.row < b.row;
     });
-    std::vector<i64> last; // last end per layer; strictly decreasing across layers under first-fit
+    struct Open { size_t head = 0; i64 max_end = 0; long double dead = 0; }; // head: oldest record that may still be open
+    std::vector<Open> relaxed;
+    std::vector<i64> last; // last end of each strict layer (index kRelaxedLayers + k); decreasing under first-fit
+    const long double budget = 0.25L * (long double)G;
     for (const Rec &r : v) {
+        bool placed = false;
+        for (size_t l = 0; l < relaxed.size() && !placed; ++l) {
+            Open &o = relaxed[l];
+            std::vector<Rec> &lay = layers[l];
+            while (o.head < lay.size() && lay[o.head].e <= r.s) ++o.head; // closed for good: starts ascend
+            const long double dead = o.max_end > r.e ? (long double)(o.max_end - r.e) : 0;
+            if (lay.size() - o.head <= (size_t)kDeadScan && o.dead + dead <= budget) {
+                lay.push_back(r);
+                o.dead += dead;
+                o.max_end = std::max(o.max_end, r.e);
+                placed = true;
+            }
+        }
+        if (placed) continue;
+        if (relaxed.size() < kRelaxedLayers) {
+            relaxed.emplace_back();
+            relaxed.back().max_end = r.e;
+            layers.emplace_back(1, r);
+            continue;
+        }
         size_t lo = 0, hi = last.size();
-        while (lo < hi) { // first layer with last <= r.e
+        while (lo < hi) { // first strict layer with last <= r.e
             size_t mid = (lo + hi) / 2;
             if (last[mid] <= r.e) hi = mid; else lo = mid + 1;
         }
         if (lo == last.size()) { last.push_back(r.e); layers.emplace_back(); }
         else last[lo] = r.e;
-        layers[lo].push_back(r);
+        layers[kRelaxedLayers + lo].push_back(r);
     }
 }
 
 template <typename C> C clampc(i64 v, u64 G) { return (C)((u64)v > G + 1 ? G + 1 : (u64)v); }
 
-// Bucket grid over one sorted run: keys[lo..hi) ascending (target ends of a layer, or the running max of
-// blocked-interval ends), starts[lo..hi) the interval starts.  At least 8 buckets per interval, so a bucket
+// Bucket grid over one sorted run: keys[lo..hi) ascending (the running max of the ends of a target layer or of a
+// group of blocked intervals), starts[lo..hi) the interval starts.  At least 8 buckets per interval, so a bucket
 // rarely holds more than one interval end; runs where some bucket holds more than
 // kCrowdedBucket ends are flagged so the device bisects inside the bucket.  Appends to `grid`.
 template <typename C>
@@ -186,7 +219,7 @@ int upload_index(esl_ctx *ctx)
     const int B = ctx->B;
     const u64 G = ctx->G;
     // targets: seg[b] = first layer of barcode b, extra layers appended behind the B first-layer descriptors
-    std::vector<C> ts, te;
+    std::vector<C> ts, te, tp; // tp: running max of te inside each layer = the grid / bisection keys
     std::vector<int32_t> trow, extra_off(B, 0);
     std::vector<esl::GridEntry<C>> tgrid;
     std::vector<esl::SegDesc> first(B), extra;
@@ -197,13 +230,18 @@ int upload_index(esl_ctx *ctx)
         for (size_t i = 0; i < ctx->t_start.size(); ++i)
             if (ctx->t_bc[i] == b && ctx->t_end[i] > ctx->t_start[i]) v.push_back(Rec{ctx->t_start[i], ctx->t_end[i], (int32_t)i});
         std::vector<std::vector<Rec>> layers;
-        build_layers(v, layers);
+        build_layers(v, layers, G);
         if (layers.size() > 0xFFFF) return ctx->fail(ESL_ERR_UNSUPPORTED, "barcode %d needs %zu nesting layers (max 65535)", b, layers.size());
         extra_off[b] = (int32_t)extra.size();
         for (size_t l = 0; l < layers.size(); ++l) {
             const int lo = (int)ts.size();
-            for (const Rec &r : layers[l]) { ts.push_back(clampc<C>(r.s, G)); te.push_back(clampc<C>(r.e, G)); trow.push_back(r.row); }
-            esl::SegDesc d = make_grid<C>(te, ts, lo, (int)ts.size(), G, tgrid);
+            C run = 0;
+            for (const Rec &r : layers[l]) {
+                ts.push_back(clampc<C>(r.s, G)); te.push_back(clampc<C>(r.e, G)); trow.push_back(r.row);
+                run = std::max(run, te.back());
+                tp.push_back(run);
+            }
+            esl::SegDesc d = make_grid<C>(tp, ts, lo, (int)ts.size(), G, tgrid);
             if (l == 0) { d.flags |= (int)((layers.size() - 1) << 16); first[b] = d; }
             else extra.push_back(d);
         }
@@ -228,7 +266,7 @@ int upload_index(esl_ctx *ctx)
             sg.reserve(n_sm * (size_t)B);
             for (int b = 0; b < B; ++b) {
                 std::vector<esl::GridEntry<C>> tmp;
-                make_grid<C>(te, ts, first[b].lo, first[b].hi, G, tmp, sshift);
+                make_grid<C>(tp, ts, first[b].lo, first[b].hi, G, tmp, sshift);
                 for (size_t k = 0; k < n_sm; ++k) sg.push_back(tmp[std::min(k, tmp.size() - 1)].s);
             }
             CU(ctx->d_sgrid.upload(sg.data(), sg.size() * sizeof(C)));
@@ -254,7 +292,7 @@ int upload_index(esl_ctx *ctx)
             }
     }
     CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>)));
-    CU(ctx->d_te.upload(te.data(), te.size() * sizeof(C)));
+    CU(ctx->d_te.upload(tp.data(), tp.size() * sizeof(C))); // bisection keys of crowded buckets
     if (seg.size() >= ((size_t)1 << esl::kQueueSegBits)) return ctx->fail(ESL_ERR_UNSUPPORTED, "too many target layers (barcodes + nesting levels must stay below 2^22)");
     ctx->n_seg = (int)seg.size(); ctx->n_tgrid = (int)tgrid.size(); ctx->n_trec = (int)trec.size();
     CU(ctx->d_raw_ts.upload(ctx->t_start.data(), ctx->t_start.size() * sizeof(i64)));

@@ -5,7 +5,7 @@
 //   K2 length table gather                          read_operations.py:102 / combined_calculations.py:57
 //   K3 barcode CDF search + uniform placement       read_operations.py:96-103
 //   K4 blocked-interval search                      read_operations.py:59-67
-//   K6 target overlap search (read-centric, over monotone target layers)   counting.py:36-53
+//   K6 target overlap search (read-centric, over start-sorted target layers) counting.py:36-53
 //   K7 integer tallies via red.global               counting.py:54-57, :63-71
 // and K5, the coverage cut-off (read_operations.py:100), is split in two kernels:
 //   k_place_tally_bulk  : the first n_bulk draws of every iteration, which lie before the cut-off with
@@ -72,7 +72,7 @@ constexpr int kLabelInvalid = -1000; // slot of a tile that holds no draw
 #define ESL_CHK(cond, what) ((void)0)
 #endif
 
-// One sorted run of intervals (a monotone target layer, or one blocked group) plus its bucket grid.
+// One sorted run of intervals (a target layer, or one blocked group) plus its bucket grid.
 // Grid entry b (b = position >> shift) holds j = first index of the run whose (running-max) end exceeds
 // b << shift, together with the START of that interval.  For a read [rs, re) with bucket b = rs >> shift:
 //   * every interval before j ends at or before the bucket start <= rs, so it cannot overlap;
@@ -159,11 +159,12 @@ struct DevCtx {
     int cdf_walk;                         // most thresholds inside one slice (steps the walk after the table needs)
     uint32_t min_ov32;                    // min_overlap clamped to [0, 2^32-1] (an overlap never exceeds a read length)
     int thin;                             // scaling < 1: draw a thinning uniform per qualifying pair
-    // target index: per barcode a run of "monotone layers" (starts AND ends ascending inside a layer), so the
-    // targets a read overlaps are one contiguous range per layer.  seg[b], b < B, is barcode b's first layer;
-    // its extra layers (nesting targets only) are seg[B + extra_off[b] ...].
+    // target index: per barcode a few layers sorted by start whose ends are (nearly) ascending: the targets a read
+    // overlaps lie in one short contiguous range per layer, with at most a few nested "dead" records in between
+    // (host: build_layers).  seg[b], b < B, is barcode b's first layer; its extra layers (deep nesting only) are
+    // seg[B + extra_off[b] ...].
     const TargetRec<C> *__restrict__ trec; // targets in layer order
-    const C *__restrict__ te;              // their ends again, contiguous (bisect key of crowded buckets)
+    const C *__restrict__ te;              // running max of their ends inside each layer (bisect key of crowded buckets)
     const SegDesc *__restrict__ seg;
     const GridEntry<C> *__restrict__ tgrid;
     const int32_t *__restrict__ extra_off; // [B]

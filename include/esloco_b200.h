@@ -196,7 +196,7 @@ int esl_get_timing(esl_ctx *ctx, float *bulk_ms, float *cutoff_ms);
 
 /* Introspection (for bench.py / DESIGN.md): number of kernel launches issued by this context so far. */
 int64_t esl_launch_count(const esl_ctx *ctx);
-/* Target index shape: total monotone layers over all barcodes (1 per barcode when targets do not nest).  The index is
+/* Target index shape: total layers over all barcodes (1 per barcode unless targets nest deeply).  The index is
  * built by the first run after esl_set_targets / esl_set_genome, so query it after a run. */
 int32_t esl_target_layers(const esl_ctx *ctx);
 /* Reads per iteration the bulk kernel processes before the exact cut-off kernel takes over. */

@@ -603,17 +603,18 @@ def test_full_size_config2_replay_of_reference_stream(eng):
 
 
 def test_native_deep_nesting_fills_candidate_queues(eng):
-    """General variant of the bulk kernel (too many first-layer targets for the shared pre-filter): twelve nested
-    genome-spanning targets on barcode 0 make every read of that barcode a candidate in twelve layers, so the per-warp
-    candidate queues overflow and are drained mid-tile; barcode 1 has a single layer.  Exact against the CPU
-    restatement, with and without thinning (the thinning uniform is keyed by the draw index the queue item carries)."""
+    """General variant of the bulk kernel (too many first-layer targets for the shared pre-filter): 200 nested
+    genome-spanning targets on barcode 0 (the index tolerates 16 open records per layer, so they need 12 layers) make
+    every read of that barcode a candidate in every layer, so the per-warp candidate queues overflow and are drained
+    mid-tile; barcode 1 has a single layer.  Exact against the CPU restatement, with and without thinning (the
+    thinning uniform is keyed by the draw index the queue item carries)."""
     G = 5_000_000
     rng = np.random.RandomState(12)
     n_small = 3000
     ss = np.sort(rng.randint(0, G - 3000, n_small)); se = ss + rng.randint(200, 1500, n_small)
-    ns = np.arange(12) * 1000 + 5; ne = G - np.arange(12) * 1000 - 7
+    ns = np.arange(200) * 1000 + 5; ne = G - np.arange(200) * 1000 - 7
     ts = np.concatenate([ns, ss, ss + 3]); te = np.concatenate([ne, se, se + 3])
-    tb = np.concatenate([np.zeros(12 + n_small), np.ones(n_small)]).astype(np.int32)
+    tb = np.concatenate([np.zeros(200 + n_small), np.ones(n_small)]).astype(np.int32)
     cdf = np.array([0.5, 1.0])
     eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
     pool = O.lognormal_pool(O.Rng(12), 2500, 1, 10, n=50000)
@@ -621,18 +622,18 @@ def test_native_deep_nesting_fills_candidate_queues(eng):
     cov = 4.0
     assert eng.bulk_reads(cov) > 3000
     res = eng.run_batch(21, 1, 5, 2, cov).cpu()
-    assert eng.target_layers() >= 13  # (the index is built by the first run after set_targets)
+    assert eng.target_layers() >= 12  # (the index is built by the first run after set_targets)
     for i in range(2):
         it = NN.native_iteration(21, 1, 5 + i, G, cov, pool, cdf)
         exp = O.count_matches_indexed(ts, te, tb, 2, it["start"], it["start"] + it["length"], it["label"], 1)
         t = res.tallies[i].numpy()
         assert int(res.n_reads[i]) == it["n_placed"] and int(res.n_bases[i]) == it["covered"]
         assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
-        assert (t[:12, 1] > 0.4 * it["n_placed"]).all()
+        assert (t[:200, 1] > 0.35 * it["n_placed"]).all()
     thin = eng.run_batch(21, 1, 5, 1, cov, False, 1, 0.6).cpu().tallies[0].numpy()
     it = NN.native_iteration(21, 1, 5, G, cov, pool, cdf)
     rs, re_ = it["start"], it["start"] + it["length"]
-    for row in (0, 11, 12, 12 + n_small):  # outermost / innermost nested, one small target per barcode
+    for row in (0, 199, 200, 200 + n_small):  # outermost / innermost nested, one small target per barcode
         s, e, b_ = ts[row], te[row], tb[row]
         exp = np.zeros(3, np.int64)
         for n in np.nonzero((it["label"] == b_) & (rs < e) & (re_ > s))[0]:
