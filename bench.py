@@ -305,13 +305,15 @@ def run_ours(args, w):
             reads_kernel, kernel_ms = float(eng.bulk_reads(w["coverage"]) * n_iter), bulk_ms / args.steps
         alg_bytes = ALG_BYTES_PER_READ * reads_kernel + ALG_BYTES_PER_TARGET * T * n_iter
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, summary = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(w["name"])  # bytes per launch, from the committed ncu capture
+        if os.path.exists(tp) and args.path == "fused":
+            tj = json.load(open(tp))
+            traffic = tj.get(w["name"])  # bytes per launch, from the committed ncu capture
+            summary = tj.get("summaries", {}).get(w["name"])
         # what actually binds the fused kernel, from the committed ncu capture of this workload (not measured live)
         binding = None
-        sp = os.path.join(ROOT, "profiles", f"r1h_bulk_{w['name']}_summary.json")
+        sp = os.path.join(ROOT, "profiles", summary or "none")
         if os.path.exists(sp):
             ps = json.load(open(sp))
             binding = {"source": os.path.relpath(sp, ROOT), "warp_instructions_per_read": round(ps["warp_instructions_per_read"], 1),
