@@ -641,3 +641,40 @@ def test_native_deep_nesting_fills_candidate_queues(eng):
                 exp[0 if (rs[n] <= s and e <= re_[n]) else 1] += 1
                 exp[2] += min(e, re_[n]) - max(s, rs[n])
         assert np.array_equal(thin[row], exp)
+
+
+def test_full_size_config4_consistency(eng):
+    """BASELINE.json configs[3] at FULL size: hg38-size genome, 30x, 50 k ROIs of 1-100 kb (nested all over: the index
+    keeps them in one layer with dead records), 824 blocked intervals of weight 1 not consuming coverage (two bulk
+    passes), min_overlap 1000, ~13.6 M draws per iteration.  The native kernels, a level-1 replay of the materialised
+    reads and the oracle's indexed CPU tally of the same reads agree bit for bit; the blocked labels equal an
+    independent numpy interval test; the cut-off is tight on the counted bases."""
+    from esloco_b200 import synthetic as S
+    from esloco_b200.utils import build_mask_tree, mask_tree_to_arrays, targets_to_arrays
+    G, _ = S.chromosome_dir(S.HG38)
+    keys, ts, te, tb = targets_to_arrays(S.barcode_rois(S.random_rois(S.HG38, 50000, 1000, 100000, seed=4), 1), 1)
+    ms, me, mw, mb = (np.asarray(x) for x in mask_tree_to_arrays(build_mask_tree(S.gap_mask(S.HG38, 800, seed=5)), 1))
+    pool = S.lognormal_lengths(8000, 1, 1, seed=1)
+    eng.set_genome(G); eng.set_barcode_cdf([1.0]); eng.set_targets(ts, te, tb); eng.set_blocked(ms, me, mw, mb)
+    eng.set_length_table(pool)
+    cov, seed, min_ov = 30, 4, 1000
+    res = eng.run_batch(seed, 0, 3, 2, cov, False, min_ov).cpu()
+    assert eng.target_layers() == 1
+    thr = cov * G
+    nb, nr = res.n_bases.numpy(), res.n_reads.numpy()
+    assert (nb >= thr).all() and (nb - thr < pool.max()).all() and not (res.status.numpy() & 2).any()
+    s, ln, lab = eng.materialize_reads(seed, 0, 4, False, int(nr[1]))
+    sh, lh, labh = s.cpu().numpy(), ln.cpu().numpy(), lab.cpu().numpy()
+    # blocked <=> the read overlaps some blocked interval (all weights are 1): merged intervals + two bisections
+    o = np.argsort(ms); a, b = ms[o], np.maximum.accumulate(me[o])
+    first = np.searchsorted(b, sh, side="right")          # first interval whose running max of ends passes the start
+    blocked = (first < a.size) & (a[np.minimum(first, a.size - 1)] < sh + lh)
+    assert np.array_equal(labh == -2, blocked) and ((labh == 0) | (labh == -2)).all()
+    assert int(lh[~blocked].sum()) == int(nb[1]) and 0.10 < blocked.mean() < 0.20
+    assert np.array_equal(res.label_counts[1].numpy(), [int((~blocked).sum()), 0, int(blocked.sum())])
+    rep = eng.replay_reads(s, ln, lab, [0, int(nr[1])], min_ov).cpu()
+    assert np.array_equal(rep.tallies[0].numpy(), res.tallies[1].numpy())
+    exp = O.count_matches_indexed(ts, te, tb, 1, sh, sh + lh, labh, min_ov)
+    t = res.tallies[1].numpy()
+    assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+    assert t[:, 2].sum() > 0 and t[:, 0].sum() > 0
