@@ -524,6 +524,7 @@ __device__ __forceinline__ void queue_push(WalkItem<C> *q, int &n, bool want, C 
     if (want) {
         WalkItem<C> w;
         w.st = st; w.L = L; w.a = a; w.sg_n = sg_n;
+        ESL_CHK(n + __popc(m) <= kQueueCap, "candidate queue overflow");
         q[n + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = w;
     }
     n += __popc(m);
