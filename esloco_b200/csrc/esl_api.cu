@@ -65,14 +65,14 @@ struct esl_ctx {
     int n_seg = 0, n_tgrid = 0, n_trec = 0, n_mgrid = 0, n_mrec = 0;
     bool index_dirty = true;
     bool wide = false; // 64-bit coordinates
-    int n_layers = 0, n_first_layers = 0, cdf_walk = 0;
+    int n_layers = 0, n_first_layers = 0, cdf_walk = 0, n_hot = 0;
     i64 n_indexed = 0, n_mask = 0;
 
     // pool statistics
     uint32_t n_pool = 0, pool_max = 0;
     double pool_mean = 0, pool_sd = 0;
 
-    DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_mrec, d_mpmax, d_grp, d_mgrid;
+    DevBuf d_pool, d_cdf, d_cdf_u32, d_cdf_lut, d_trec, d_te, d_seg, d_tgrid, d_extra_off, d_mrec, d_mpmax, d_grp, d_mgrid, d_hot_row;
     DevBuf d_raw_ts, d_raw_te, d_raw_tb; // targets in caller order (staged baseline)
     DevBuf d_pool_stats;
     DevBuf d_sgrid;
@@ -278,6 +278,7 @@ int upload_index(esl_ctx *ctx)
     seg.insert(seg.end(), extra.begin(), extra.end());
     ctx->n_indexed = (i64)ts.size();
     std::vector<esl::TargetRec<C>> trec(ts.size());
+    std::vector<int32_t> hot_row; // rows of the targets that get a private shared-memory tally (first kHotSlots hot ones)
     {
         size_t j = 0;
         for (const esl::SegDesc &d : seg)
@@ -286,12 +287,18 @@ int upload_index(esl_ctx *ctx)
                 r.s = ts[k]; r.e = te[k]; r.row = trow[k];
                 // hot target: a read overlaps it with probability >= 1/512 (whole-chromosome ROIs and the like)
                 const long double p_hit = ((long double)(te[k] - ts[k]) + ctx->pool_mean) / (long double)G;
-                if (p_hit >= 1.0L / 512) r.row |= (int)0x80000000;
+                if (p_hit >= 1.0L / 512 && (int)hot_row.size() < esl::kHotSlots) {
+                    r.row = (int)(0x80000000u | (uint32_t)hot_row.size()); // the record carries the slot, hot_row[] the row
+                    hot_row.push_back(trow[k]);
+                }
                 r.s_next = k + 1 < d.hi ? ts[k + 1] : (C) ~(C)0;
                 trec[k] = r;
             }
     }
     CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>)));
+    ctx->n_hot = (int)hot_row.size();
+    hot_row.resize(esl::kHotSlots, 0);
+    CU(ctx->d_hot_row.upload(hot_row.data(), hot_row.size() * sizeof(int32_t)));
     CU(ctx->d_te.upload(tp.data(), tp.size() * sizeof(C))); // bisection keys of crowded buckets
     if (seg.size() >= ((size_t)1 << esl::kQueueSegBits)) return ctx->fail(ESL_ERR_UNSUPPORTED, "too many target layers (barcodes + nesting levels must stay below 2^22)");
     ctx->n_seg = (int)seg.size(); ctx->n_tgrid = (int)tgrid.size(); ctx->n_trec = (int)trec.size();
@@ -400,6 +407,8 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.tgrid = ctx->d_tgrid.as<esl::GridEntry<C>>();
     d.extra_off = ctx->d_extra_off.as<int32_t>();
     d.any_extra = ctx->n_layers > ctx->n_first_layers;
+    d.hot_row = ctx->d_hot_row.as<int32_t>();
+    d.n_hot = ctx->n_hot;
     d.n_seg = ctx->n_seg; d.n_tgrid = ctx->n_tgrid; d.n_trec = ctx->n_trec; d.n_mgrid = ctx->n_mgrid; d.n_mrec = ctx->n_mrec;
     d.sgrid = ctx->sgrid_n ? ctx->d_sgrid.as<C>() : nullptr;
     d.sgrid_n = ctx->sgrid_n;
@@ -434,7 +443,7 @@ size_t bulk_smem(const esl_ctx *ctx)
     const size_t entry = ctx->wide ? 8 : 4;
     const size_t item = ctx->wide ? sizeof(esl::WalkItem<uint64_t>) : sizeof(esl::WalkItem<uint32_t>);
     const size_t queues = ctx->sgrid_n ? 0 : (size_t)(esl::kBulkBlock / 32) * esl::kQueueCap * item; // per-warp candidate queues
-    return queues + (size_t)B * ctx->sgrid_n * entry + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
+    return queues + (ctx->n_hot ? (size_t)esl::kHotWords * 4 : 0) + (size_t)B * ctx->sgrid_n * entry + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
            (size_t)esl::kCdfLut * 2 + 32;
 }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
@@ -474,8 +483,14 @@ int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const es
 {
     const i64 total_tiles = r.tiles * n_iter;
     if (total_tiles <= 0) return ESL_OK;
-    auto kern = dc.sgrid ? (dc.has_mask ? esl::k_place_tally_bulk<C, Src, true, true> : esl::k_place_tally_bulk<C, Src, false, true>)
-                         : (dc.has_mask ? esl::k_place_tally_bulk<C, Src, true, false> : esl::k_place_tally_bulk<C, Src, false, false>);
+    // one instantiation per (blocked regions?, small target set with a shared pre-filter?, hot targets?)
+    using Kern = void (*)(esl::DevCtx<C>, Src, esl::DevOut, const i64 *, i64, const i64 *, i64, int, int, i64);
+    static const Kern table[8] = {
+        esl::k_place_tally_bulk<C, Src, false, false, false>, esl::k_place_tally_bulk<C, Src, false, false, true>,
+        esl::k_place_tally_bulk<C, Src, false, true, false>,  esl::k_place_tally_bulk<C, Src, false, true, true>,
+        esl::k_place_tally_bulk<C, Src, true, false, false>,  esl::k_place_tally_bulk<C, Src, true, false, true>,
+        esl::k_place_tally_bulk<C, Src, true, true, false>,   esl::k_place_tally_bulk<C, Src, true, true, true>};
+    const Kern kern = table[(dc.has_mask ? 4 : 0) | (dc.sgrid ? 2 : 0) | (dc.n_hot ? 1 : 0)];
     int occ = 0;
     if (bulk_smem(ctx) > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem(ctx)));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx)));

@@ -169,6 +169,8 @@ struct DevCtx {
     const GridEntry<C> *__restrict__ tgrid;
     const int32_t *__restrict__ extra_off; // [B]
     int any_extra;                         // some barcode has more than one layer
+    const int32_t *__restrict__ hot_row;   // [n_hot] row of each hot target's slot
+    int n_hot;
     int n_seg, n_tgrid, n_trec, n_mgrid, n_mrec; // array sizes (debug bounds checks)
     // small target sets: for every first layer a coarser grid holding only the START of each bucket's first
     // candidate (sgrid_n entries per barcode, bucket width 2^sgrid_shift), staged in shared memory by the bulk
@@ -361,44 +363,48 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
 
 // K6 + K7 for one layer whose first candidate starts before the read's end: walk the candidates and add
 // (sign = +1) or take back (sign = -1) the read's contribution (counting.py:40-57).
+constexpr int kHotSlots = 64;               // "hot" targets with a private shared-memory tally per CTA
+constexpr int kHotWords = kHotSlots * 4 + kHotSlots; // {full, partial, overlap & 0xffff, overlap >> 16} per slot, then the slots' rows
+static_assert(kHotWords % 4 == 0, "the hot-target block must keep 16-byte alignment behind it");
+constexpr int kHotFlushTiles = 64;          // 64 tiles x 768 reads x 0xffff < 2^32: the 32-bit shared sums cannot overflow
+static_assert((unsigned long long)kHotFlushTiles * kBulkTile * 0xffffull < (1ull << 32), "hot-target sums must fit 32 bits between flushes");
+
 template <typename C, typename Src>
 __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it, i64 n,
-                                         int sg, int a, C rs, C re, i64 sign)
+                                         int sg, int a, C rs, C re, i64 sign, uint32_t *s_hot = nullptr)
 {
     const SegDesc d = load_desc(cx.seg + sg);
     for (int j = skip_crowded(d, cx.tgrid, cx.te, a, rs); j < d.hi; ++j) {
         ESL_CHK(j >= 0 && j < cx.n_trec, "target record index");
         const TargetRec<C> r = load_rec(cx.trec + j);
-        ESL_CHK((r.row & 0x7fffffff) < cx.n_targets, "target row");
         if (r.s >= re) break; // starts ascend: nothing further overlaps
         if (r.e > rs) {       // (an end inside the bucket but before the read does not overlap)
             const C ov = (r.e < re ? r.e : re) - (r.s > rs ? r.s : rs);
-            if ((u64)ov >= (u64)cx.min_ov32 && !(cx.thin && !(src.scale_u(it, n, r.row & 0x7fffffff) <= cx.scaling))) {
+            // "hot" target (flagged by the host: a read hits it with probability >= 1/512, e.g. a whole-chromosome
+            // ROI): the record carries a slot number instead of the row
+            int row = r.row & 0x7fffffff;
+            const int slot = row;
+            if (r.row < 0) row = s_hot ? (int)s_hot[kHotSlots * 4 + slot] : __ldg(cx.hot_row + slot);
+            ESL_CHK(row < cx.n_targets, "target row");
+            if ((u64)ov >= (u64)cx.min_ov32 && !(cx.thin && !(src.scale_u(it, n, row) <= cx.scaling))) {
                 const int kind = (rs <= r.s && r.e <= re) ? 0 : 1;
-                const int row = r.row & 0x7fffffff;
-                u64 *t = tallies_it + (i64)row * 3;
-                if (r.row < 0) {
-                    // "hot" target (flagged by the host: a read hits it with probability >= 1/512, e.g. a
-                    // whole-chromosome ROI): lanes that are here together with the same target and kind are combined
-                    // first (match.any + REDUX), one pair of atomics per group instead of one per lane on one address
-                    const unsigned peers = __match_any_sync(__activemask(), row * 2 + kind);
-                    const int cnt = __popc(peers);
-                    u64 ov_sum = (u64)ov; // ov <= read length < 2^32
-                    if (cnt > 1)
-                        ov_sum = (u64)__reduce_add_sync(peers, (unsigned)ov & 0xffffu) +
-                                 ((u64)__reduce_add_sync(peers, (unsigned)((u64)ov >> 16)) << 16);
-                    if ((threadIdx.x & 31) == __ffs(peers) - 1) {
-                        atomicAdd(t + kind, (u64)(sign * (i64)cnt));
-                        atomicAdd(t + 2, (u64)(sign * (i64)ov_sum));
-                    }
+                if (r.row < 0 && s_hot) {
+                    // bulk kernel: hits go to the CTA's private 32-bit sums in shared memory (flushed to the global
+                    // tallies every kHotFlushTiles tiles) -- thousands of atomics per iteration on one global address
+                    // serialise in L2, and combining lanes first (match.any + REDUX per group) cost more than it saved
+                    uint32_t *h = s_hot + slot * 4;
+                    atomicAdd(h + kind, 1u);
+                    atomicAdd(h + 2, (uint32_t)ov & 0xffffu); // ov <= read length < 2^32
+                    atomicAdd(h + 3, (uint32_t)((u64)ov >> 16));
                 } else {
+                    u64 *t = tallies_it + (i64)row * 3;
                     atomicAdd(t + kind, (u64)sign);
                     atomicAdd(t + 2, (u64)(sign * (i64)ov));
                 }
                 if (out.hits && sign > 0) { // draws beyond the cut-off are dropped on the host by their index
-                    const u64 slot = atomicAdd(out.hit_count, 1ull);
-                    if ((i64)slot < out.hit_cap) {
-                        i64 *h = out.hits + slot * 4;
+                    const u64 slot_h = atomicAdd(out.hit_count, 1ull);
+                    if ((i64)slot_h < out.hit_cap) {
+                        i64 *h = out.hits + slot_h * 4;
                         h[0] = it; h[1] = row; h[2] = n;
                         h[3] = (i64)ov | (kind == 0 ? (i64)0x8000000000000000ULL : 0); // sign bit = full match
                     }
@@ -409,25 +415,42 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
     }
 }
 
+// Add the CTA's private sums of the hot targets to the global tallies of iteration `it` and clear them.  Called by
+// all threads of the CTA, between two block barriers.
+__device__ __forceinline__ void flush_hot(uint32_t *s_hot, int n_hot, u64 *__restrict__ tallies_it)
+{
+    for (int i = threadIdx.x; i < n_hot; i += blockDim.x) {
+        uint32_t *h = s_hot + i * 4;
+        const uint32_t f = h[0], p = h[1], lo = h[2], hi = h[3];
+        if (f | p | lo | hi) {
+            h[0] = h[1] = h[2] = h[3] = 0;
+            u64 *t = tallies_it + (i64)s_hot[kHotSlots * 4 + i] * 3;
+            if (f) atomicAdd(t, (u64)f);
+            if (p) atomicAdd(t + 1, (u64)p);
+            atomicAdd(t + 2, (u64)lo + ((u64)hi << 16));
+        }
+    }
+}
+
 // Extra layers of barcode bc (only when its targets nest).
 template <typename C, typename Src>
 __device__ __forceinline__ void tally_extra_layers(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it,
-                                                i64 n, int bc, int n_extra, C rs, C re, i64 sign)
+                                                i64 n, int bc, int n_extra, C rs, C re, i64 sign, uint32_t *s_hot = nullptr)
 {
     const int s0 = cx.n_barcodes + __ldg(cx.extra_off + bc);
     for (int sg = s0; sg < s0 + n_extra; ++sg) {
         const Probe<C> p = probe(cx.seg, sg, cx.tgrid, rs);
-        if (p.s < re) tally_layer(cx, src, out, tallies_it, it, n, sg, p.a, rs, re, sign);
+        if (p.s < re) tally_layer(cx, src, out, tallies_it, it, n, sg, p.a, rs, re, sign, s_hot);
     }
 }
 
 // First layer of the read's barcode through the exact global grid.
 template <typename C, typename Src>
 __device__ __forceinline__ void tally_first_layer(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
-                                                  int it, i64 n, C rs, C re, int bc, i64 sign)
+                                                  int it, i64 n, C rs, C re, int bc, i64 sign, uint32_t *s_hot = nullptr)
 {
     const Probe<C> p = probe(cx.seg, bc, cx.tgrid, rs);
-    if (p.s < re) tally_layer(cx, src, out, tallies_it, it, n, bc, p.a, rs, re, sign);
+    if (p.s < re) tally_layer(cx, src, out, tallies_it, it, n, bc, p.a, rs, re, sign, s_hot);
 }
 
 // All layers of the read's barcode: probe each layer, walk its candidates when the first one starts before
@@ -531,13 +554,13 @@ __device__ __forceinline__ void queue_push(WalkItem<C> *q, int &n, bool want, C 
 }
 template <typename C, typename Src>
 __device__ __forceinline__ void queue_drain(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
-                                            int it, uint32_t base, const WalkItem<C> *q, int &n)
+                                            int it, uint32_t base, const WalkItem<C> *q, int &n, uint32_t *s_hot)
 {
     __syncwarp();
     for (int k = threadIdx.x & 31; k < n; k += 32) {
         const WalkItem<C> w = q[k];
         tally_layer(cx, src, out, tallies_it, it, (i64)(base + (w.sg_n >> kQueueSegBits)), (int)(w.sg_n & ((1u << kQueueSegBits) - 1u)),
-                    w.a, w.st, (C)(w.st + w.L), 1);
+                    w.a, w.st, (C)(w.st + w.L), 1, s_hot);
     }
     __syncwarp();
     n = 0;
@@ -555,7 +578,7 @@ __device__ __forceinline__ void queue_drain(const DevCtx<C> &cx, const Src &src,
 //   1 draw  2 blocked probes / slow path  3 label histogram  4 target probes / slow path  5 tile sum
 // There is no block barrier inside the tile loop: warps only meet when the CTA moves to the next iteration and
 // flushes its shared label histogram.
-template <typename C, typename Src, bool kMask, bool kShared>
+template <typename C, typename Src, bool kMask, bool kShared, bool kHot>
 __global__ void __launch_bounds__(kBulkBlock, bulk_min_blocks<C, kShared>())
 k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src src, const DevOut out, const i64 *__restrict__ lo_arr,
                    const i64 lo_const, const i64 *__restrict__ hi_arr, const i64 hi_const, const int tile0,
@@ -566,7 +589,11 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     const int n_sgrid = kShared ? B * cx.sgrid_n : 0; // kShared: small target sets with a shared-memory pre-filter grid
     // candidate queues first (16-byte aligned); the shared pre-filter path tallies in place and has none
     WalkItem<C> *queue = (WalkItem<C> *)smem + (threadIdx.x >> 5) * kQueueCap;
-    const size_t q_words = kShared ? 0 : (size_t)(kBulkBlock / 32) * kQueueCap * sizeof(WalkItem<C>) / 8;
+    const size_t queue_words = kShared ? 0 : (size_t)(kBulkBlock / 32) * kQueueCap * sizeof(WalkItem<C>) / 8;
+    // private tallies of the hot targets + their rows (kHot: the host flagged some; otherwise the null pointer is a
+    // compile-time constant and every hot-target branch below folds away)
+    uint32_t *const s_hot = kHot ? (uint32_t *)(smem + queue_words) : nullptr;
+    const size_t q_words = queue_words + (kHot ? kHotWords / 2 : 0); // (a multiple of 16 bytes: s_desc is an int4 array)
     int4 *s_desc = (int4 *)(smem + q_words);                    // [min(B, kSmemDescs)] first-layer descriptors
     const int n_sdesc = B <= kSmemDescs ? B : 0;
     int *s_hist = (int *)(s_desc + n_sdesc);                    // [B + 2] reads per label since the last flush
@@ -577,6 +604,9 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     for (int i = tid; i < n_sgrid; i += kBulkBlock) s_grid[i] = cx.sgrid[i];
     for (int i = tid; i < n_sdesc; i += kBulkBlock) s_desc[i] = __ldg(reinterpret_cast<const int4 *>(cx.seg + i));
     for (int i = tid; i < B + 2; i += kBulkBlock) s_hist[i] = 0;
+    if (s_hot)
+        for (int i = tid; i < kHotWords; i += kBulkBlock)
+            s_hot[i] = i >= kHotSlots * 4 && i - kHotSlots * 4 < cx.n_hot ? (uint32_t)cx.hot_row[i - kHotSlots * 4] : 0u;
     if (!Src::kHasLabel && cx.cdf_u32 && B > 1) {
         for (int i = tid; i < B; i += kBulkBlock) s_cdf[i] = cx.cdf_u32[i];
         for (int i = tid; i < kCdfLut; i += kBulkBlock) s_lut[i] = cx.cdf_lut[i];
@@ -598,8 +628,14 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     bool new_it = true;
 
     for (i64 left_tiles = t1 - t0; left_tiles > 0; --left_tiles, ++t) {
+        if (s_hot && (left_tiles & (kHotFlushTiles - 1)) == 0 && t != tile0 + tiles_launch) { // (block-uniform)
+            __syncthreads();
+            flush_hot(s_hot, cx.n_hot, tallies_it);
+            __syncthreads();
+        }
         if (t == tile0 + tiles_launch) { // wrapped into the next iteration: flush what the CTA gathered for this one
             __syncthreads();
+            if (s_hot) flush_hot(s_hot, cx.n_hot, tallies_it);
             for (int i = tid; i < B + 2; i += kBulkBlock)
                 if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
             if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
@@ -673,7 +709,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 const C first = s_grid[(ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift)];
                 const C re = (C)(st[i] + L[i]);
                 if (ok && first < re)
-                    tally_first_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), st[i], re, label[i], 1);
+                    tally_first_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), st[i], re, label[i], 1, s_hot);
             }
             if (cx.any_extra) { // the pre-filter only covers first layers
 #pragma unroll
@@ -682,7 +718,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                     const int n_extra = (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16);
                     if (n_extra)
                         tally_extra_layers(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), label[i], n_extra,
-                                           st[i], (C)(st[i] + L[i]), 1);
+                                           st[i], (C)(st[i] + L[i]), 1, s_hot);
                 }
             }
         } else { // phase 4: targets -- probe the layers for all reads, queue the "maybe"s, drain the queue converged
@@ -724,14 +760,14 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                             pe[i] = probe(cx.seg, sg[i], cx.tgrid, st[i]);
                         }
                     }
-                    if (qn > kQueueCap - 32 * kBulkIpt) queue_drain(cx, src, out, tallies_it, it, base, queue, qn);
+                    if (qn > kQueueCap - 32 * kBulkIpt) queue_drain(cx, src, out, tallies_it, it, base, queue, qn, s_hot);
 #pragma unroll
                     for (int i = 0; i < kBulkIpt; ++i)
                         queue_push(queue, qn, pe[i].s < (C)(st[i] + L[i]), st[i], L[i], pe[i].a,
                                    (uint32_t)sg[i] | (uint32_t)(i * kBulkBlock + tid) << kQueueSegBits);
                 }
             }
-            queue_drain(cx, src, out, tallies_it, it, base, queue, qn);
+            queue_drain(cx, src, out, tallies_it, it, base, queue, qn, s_hot);
         }
         my = warp_sum_redux(my); // phase 5: tile sum (read only when the cut-off has to be taken back)
         if (lane == 0) {
@@ -745,6 +781,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
         }
     }
     __syncthreads();
+    if (s_hot) flush_hot(s_hot, cx.n_hot, tallies_it);
     for (int i = tid; i < B + 2; i += kBulkBlock)
         if (s_hist[i]) atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]);
     if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);

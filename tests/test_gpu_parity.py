@@ -678,3 +678,34 @@ def test_full_size_config4_consistency(eng):
     t = res.tallies[1].numpy()
     assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
     assert t[:, 2].sum() > 0 and t[:, 0].sum() > 0
+
+
+def test_native_hot_targets_private_tallies(eng):
+    """Targets a read hits with probability >= 1/512 ("hot": whole-genome / whole-chromosome ROIs) are tallied in
+    per-CTA shared-memory sums that the bulk kernel flushes every 64 tiles and at iteration boundaries; 75 such
+    targets exceed the 64 slots, so some take the plain global-atomic path.  12 M reads per iteration make every CTA
+    pass several flush points.  Exact against the CPU restatement; a level-1 replay of the same reads agrees."""
+    G = 20_000_000
+    rng = np.random.RandomState(5)
+    big_s = np.array([0, 0, 5_000_000, 17_000_000]); big_e = np.array([G, G // 2, 9_000_000, G + 50])
+    mid_s = np.sort(rng.randint(0, G - 300_000, 71)); mid_e = mid_s + rng.randint(60_000, 300_000, 71)  # p_hit >= 1/330
+    sm_s = np.sort(rng.randint(0, G - 5000, 400)); sm_e = sm_s + rng.randint(100, 5000, 400)
+    ts = np.concatenate([big_s, mid_s, sm_s]); te = np.concatenate([big_e, mid_e, sm_e])
+    tb = (np.arange(ts.size) % 2).astype(np.int32)
+    cdf = np.array([0.7, 1.0])
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
+    pool = O.lognormal_pool(O.Rng(5), 1000, 1, 50, n=100000)
+    eng.set_length_table(pool)
+    cov = 600.0
+    res = eng.run_batch(77, 0, 0, 2, cov).cpu()
+    nr = res.n_reads.numpy()
+    assert nr.min() > 10_000_000
+    it = NN.native_iteration(77, 0, 1, G, cov, pool, cdf)
+    assert int(nr[1]) == it["n_placed"] and int(res.n_bases[1]) == it["covered"]
+    exp = O.count_matches_indexed(ts, te, tb, 2, it["start"], it["start"] + it["length"], it["label"], 1)
+    t = res.tallies[1].numpy()
+    assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+    assert t[0, 1] > 8_000_000 and t[0, 2] > 2**32  # the whole-genome target: every read of barcode 0, > 32 bits of bases
+    s, ln, lab = eng.materialize_reads(77, 0, 1, False, int(nr[1]))
+    rep = eng.replay_reads(s, ln, lab, [0, int(nr[1])]).cpu()
+    assert np.array_equal(rep.tallies[0].numpy(), t)
