@@ -38,6 +38,11 @@ def make_workload(name):
     if name == "cfg2":
         w.update(n_barcodes=1, iterations=100, desc="I mode, hg38-size (3.1 Gb, 24 contigs), 1 barcode, 30x, 100 insertions of 5 kb, 100 iterations")
         w["targets"] = S.random_insertions(G, 100, 5000, 1, seed=2)
+    elif name.startswith("sweep:"):  # a cell of BASELINE.json configs[4]: "sweep:<barcodes>:<coverage>" on the config-2 shape
+        _, nb, cov = name.split(":")
+        w.update(n_barcodes=int(nb), coverage=float(cov), iterations=100,
+                 desc=f"config-2 shape (hg38-size, 100 insertions of 5 kb per barcode), {nb} barcode(s), {cov}x, 100 iterations")
+        w["targets"] = S.random_insertions(G, 100, 5000, int(nb), seed=2)
     elif name == "cfg3":
         w.update(n_barcodes=24, iterations=125, barcode_weights={"0": 10, "1": 5},
                  desc="I mode, hg38-size, 24 barcodes (weights 0:10, 1:5), 30x, 10k insertions per barcode, 125 iterations per GPU")

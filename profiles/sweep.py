@@ -8,6 +8,7 @@ coverage), the C port of the reference algorithm on all host threads (one iterat
 import itertools
 import json
 import os
+import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,7 +18,6 @@ sys.path.insert(0, ROOT)
 def main():
     import torch
     import torch.distributed as dist
-    import bench
     from esloco_b200 import synthetic as S
     from esloco_b200.distributed import shard_iterations
     from esloco_b200.session import get_session
@@ -65,10 +65,12 @@ def main():
                    "reads_per_iteration": reads / n_iter}
             if "--cpu" in sys.argv and rank == 0:
                 if coverage not in cpu:  # the CPU port's rate does not depend on the iteration count: one sample per coverage
-                    w = dict(bench.make_workload("cfg2"), targets=targets, n_barcodes=n_barcodes, coverage=coverage)
-                    n_thr = bench.host_threads(w)
-                    r_cpu, it_cpu, dt = bench.cpu_port_sample(w, n_thr)
-                    cpu[coverage] = {"cpu_reads_per_s": r_cpu / dt, "cpu_iterations_per_s": it_cpu / dt, "cpu_threads": n_thr}
+                    # bench.py's reference arm on this cell (the CPU port is test / baseline infrastructure: bench.py runs it)
+                    ref = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                                          "--workload", f"sweep:{n_barcodes}:{coverage}"], capture_output=True, text=True, check=True)
+                    line = json.loads(ref.stdout.strip().splitlines()[-1])
+                    cpu[coverage] = {"cpu_reads_per_s": line["value"], "cpu_iterations_per_s": line["iterations_per_s"],
+                                     "cpu_threads": line["cpu_baseline"]["cores"]}
                 row.update(cpu[coverage])
             if rank == 0:
                 print(json.dumps(row), flush=True)
