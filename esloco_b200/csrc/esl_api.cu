@@ -118,11 +118,13 @@ struct Rec { i64 s, e; int32_t row; };
 // every record in between that ended before rs is a wasted ("dead") load.  A layer whose ends never decrease has
 // none; strict patience sorting gives that, but random ROIs of mixed lengths nest all the time (50 k ROIs of
 // 1-100 kb: 9 strict layers, each costing every read a probe).  So nesting is tolerated while it stays cheap:
-// first-fit into the first layer where (a) at most kDeadScan records separate the target from the oldest record
-// still open at its start (bounds the dead loads of any read) and (b) the layer's summed dead spans
-// (max end so far - end) stay below a quarter of the genome (bounds them on average: < 0.25 per read).
-// Whole-chromosome ROIs over many small ones still split into two layers; 50 k mixed ROIs become one.
-// Layers past the 64th are strictly monotone (binary search), so pathological nesting stays O(n log n).
+// a target that ends before the layer's running max is nested in an earlier record; it is accepted (first-fit over
+// the layers) if (a) it lies at most kDeadScan records behind the OLDEST record that outlives it -- a walk starts at
+// such a record, so no read ever passes more than kDeadScan dead records -- and (b) the layer's summed dead spans
+// (running max - end) stay below a quarter of the genome (< 0.25 dead loads per read on average).  Targets whose
+// ends keep ascending are always accepted, however densely they overlap.  Whole-chromosome ROIs over many small
+// ones still split into two layers; 50 k mixed ROIs become one.  Layers past the 64th are strictly monotone
+// (binary search), so pathological nesting stays O(n log n).
 constexpr int kDeadScan = 16;
 constexpr size_t kRelaxedLayers = 64;
 void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers, u64 G)
@@ -132,28 +134,39 @@ void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers, u6
         if (a.e != b.e) return a.e < b.e;
         return a.row < b.row;
     });
-    struct Open { size_t head = 0; i64 max_end = 0; long double dead = 0; }; // head: oldest record that may still be open
-    std::vector<Open> relaxed;
+    struct Relaxed {
+        std::vector<i64> pm_end;    // the records that raised the running max of ends: their ends (ascending) ...
+        std::vector<size_t> pm_idx; // ... and their positions in the layer
+        long double dead = 0;
+    };
+    std::vector<Relaxed> relaxed;
     std::vector<i64> last; // last end of each strict layer (index kRelaxedLayers + k); decreasing under first-fit
     const long double budget = 0.25L * (long double)G;
     for (const Rec &r : v) {
         bool placed = false;
         for (size_t l = 0; l < relaxed.size() && !placed; ++l) {
-            Open &o = relaxed[l];
+            Relaxed &o = relaxed[l];
             std::vector<Rec> &lay = layers[l];
-            while (o.head < lay.size() && lay[o.head].e <= r.s) ++o.head; // closed for good: starts ascend
-            const long double dead = o.max_end > r.e ? (long double)(o.max_end - r.e) : 0;
-            if (lay.size() - o.head <= (size_t)kDeadScan && o.dead + dead <= budget) {
+            if (r.e >= o.pm_end.back()) { // not nested: no read will ever see it dead
+                if (r.e > o.pm_end.back()) { o.pm_end.push_back(r.e); o.pm_idx.push_back(lay.size()); }
+                lay.push_back(r);
+                placed = true;
+                break;
+            }
+            // oldest record that ends at or after this one = first running-max record with end >= r.e
+            const size_t k = (size_t)(std::lower_bound(o.pm_end.begin(), o.pm_end.end(), r.e) - o.pm_end.begin());
+            const long double dead = (long double)(o.pm_end.back() - r.e);
+            if (lay.size() - o.pm_idx[k] <= (size_t)kDeadScan && o.dead + dead <= budget) {
                 lay.push_back(r);
                 o.dead += dead;
-                o.max_end = std::max(o.max_end, r.e);
                 placed = true;
             }
         }
         if (placed) continue;
         if (relaxed.size() < kRelaxedLayers) {
             relaxed.emplace_back();
-            relaxed.back().max_end = r.e;
+            relaxed.back().pm_end.push_back(r.e);
+            relaxed.back().pm_idx.push_back(0);
             layers.emplace_back(1, r);
             continue;
         }
@@ -730,6 +743,21 @@ int esl_get_timing(esl_ctx *ctx, float *bulk_ms, float *cutoff_ms)
 
 int64_t esl_launch_count(const esl_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int32_t esl_target_layers(const esl_ctx *ctx) { return ctx ? ctx->n_layers : 0; }
+
+int32_t esl_plan_target_layers(uint64_t genome_size, const int64_t *start, const int64_t *end, int64_t n, int32_t *layer_out)
+{
+    if (n < 0 || (n > 0 && (!start || !end || !layer_out)) || genome_size == 0) return ESL_ERR_INVALID;
+    std::vector<Rec> v;
+    for (int64_t i = 0; i < n; ++i) {
+        layer_out[i] = -1;
+        if (end[i] > start[i]) v.push_back(Rec{start[i], end[i], (int32_t)i});
+    }
+    std::vector<std::vector<Rec>> layers;
+    build_layers(v, layers, genome_size);
+    for (size_t l = 0; l < layers.size(); ++l)
+        for (const Rec &r : layers[l]) layer_out[r.row] = (int32_t)l;
+    return (int32_t)layers.size();
+}
 
 int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_begin, int32_t n_iter, double coverage,
                   int32_t consuming, int64_t min_overlap, double scaling, int64_t *d_tallies, int64_t *d_label_counts,

@@ -181,6 +181,13 @@ int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t 
 int64_t esl_scan_read_lengths(const char *path, int32_t is_fastq, int64_t min_read_length, uint32_t *out,
                               int64_t capacity, double *mean_out);
 
+/* Host helper (no GPU): how the library would split one barcode's n targets into index layers over a genome of
+ * size genome_size (a layer is scanned front to back, nesting is tolerated while it costs
+ * reads at most a few wasted record loads).  layer_out[i] receives the layer of target i (-1 for an empty target,
+ * end <= start, which is never indexed); returns the number of layers, or a negative esl_status.  For tests and for
+ * sizing: the device index built by the first run after esl_set_targets uses exactly this split per barcode. */
+int32_t esl_plan_target_layers(uint64_t genome_size, const int64_t *start, const int64_t *end, int64_t n, int32_t *layer_out);
+
 /* Replay of the reference's pair thinning for scaling < 1 (counting.py:46,51: one rand() per qualifying pair, kept
  * iff u <= scaling, pairs visited target-major in read order).  d_hits = the qualifying pairs of a replay run with
  * scaling = 1 (esl_set_hit_buffer records, sorted by iteration, row, draw index, cut-off applied), d_u = the
