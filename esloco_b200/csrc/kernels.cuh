@@ -361,14 +361,15 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
     return false;
 }
 
-// K6 + K7 for one layer whose first candidate starts before the read's end: walk the candidates and add
-// (sign = +1) or take back (sign = -1) the read's contribution (counting.py:40-57).
 constexpr int kHotSlots = 64;               // "hot" targets with a private shared-memory tally per CTA
 constexpr int kHotWords = kHotSlots * 4 + kHotSlots; // {full, partial, overlap & 0xffff, overlap >> 16} per slot, then the slots' rows
 static_assert(kHotWords % 4 == 0, "the hot-target block must keep 16-byte alignment behind it");
 constexpr int kHotFlushTiles = 64;          // 64 tiles x 768 reads x 0xffff < 2^32: the 32-bit shared sums cannot overflow
 static_assert((unsigned long long)kHotFlushTiles * kBulkTile * 0xffffull < (1ull << 32), "hot-target sums must fit 32 bits between flushes");
 
+// K6 + K7 for one layer whose first candidate starts before the read's end: walk the candidates and add
+// (sign = +1) or take back (sign = -1) the read's contribution (counting.py:40-57).  s_hot = the CTA's private tallies
+// of the hot targets (bulk kernel) or null (cut-off kernel: plain atomics, it sees 0.4 % of the reads).
 template <typename C, typename Src>
 __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it, i64 n,
                                          int sg, int a, C rs, C re, i64 sign, uint32_t *s_hot = nullptr)
