@@ -747,6 +747,7 @@ int32_t esl_target_layers(const esl_ctx *ctx) { return ctx ? ctx->n_layers : 0; 
 int32_t esl_plan_target_layers(uint64_t genome_size, const int64_t *start, const int64_t *end, int64_t n, int32_t *layer_out)
 {
     if (n < 0 || (n > 0 && (!start || !end || !layer_out)) || genome_size == 0) return ESL_ERR_INVALID;
+    if (n > 0x7fffffffLL) return ESL_ERR_UNSUPPORTED; // rows are 31-bit, as in esl_set_targets
     std::vector<Rec> v;
     for (int64_t i = 0; i < n; ++i) {
         layer_out[i] = -1;
