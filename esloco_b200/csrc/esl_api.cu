@@ -77,6 +77,7 @@ struct esl_ctx {
     DevBuf d_pool_stats;
     DevBuf d_sgrid;
     int sgrid_n = 0, sgrid_shift = 0; // shared-memory copy of the first-layer grids (0 = does not fit)
+    u64 sgrid_lmax = 0;               // longest read its upper bounds were built for
     DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
 
     // optional hit-record buffer (esl_set_hit_buffer)
@@ -263,11 +264,16 @@ int upload_index(esl_ctx *ctx)
         ctx->n_first_layers += layers.empty() ? 0 : 1;
     }
     // Shared-memory pre-filter for small target sets (typical esloco runs: a handful of ROIs / insertions per
-    // barcode): per first layer a coarser grid with only the start of each bucket's first candidate, all
-    // barcodes at one common bucket width, if that fits ~36 KB with at least four buckets per target.
+    // barcode): per first layer a coarser grid, all barcodes at one common bucket width, holding per bucket the
+    // pair {start of the bucket's first candidate, largest end among the targets a read STARTING in the bucket can
+    // reach}.  A read [rs, re) can only overlap something if first < re and rs < that end; the second test needs
+    // the longest read, so it only serves draws from the length pool (rounded up to a power of two: a longer pool
+    // rebuilds the index, ensure_index).  Used if it fits ~36 KB with at least four buckets per target.
     ctx->sgrid_n = 0;
+    ctx->sgrid_lmax = 1;
+    while (ctx->sgrid_lmax < (u64)ctx->pool_max) ctx->sgrid_lmax <<= 1;
     {
-        const size_t budget = 36 * 1024 / sizeof(C);
+        const size_t budget = 36 * 1024 / sizeof(C) / 2;
         const size_t per_bc = B > 0 ? budget / (size_t)B : 0;
         int max_t = 0;
         for (int b = 0; b < B; ++b) max_t = std::max(max_t, first[b].hi - first[b].lo);
@@ -276,11 +282,20 @@ int upload_index(esl_ctx *ctx)
         const size_t n_sm = (size_t)((G + 1) >> sshift) + 2;
         if (per_bc >= 64 && n_sm <= per_bc && n_sm >= 4 * (size_t)max_t && ctx->n_first_layers > 0) {
             std::vector<C> sg;
-            sg.reserve(n_sm * (size_t)B);
+            sg.reserve(2 * n_sm * (size_t)B);
             for (int b = 0; b < B; ++b) {
                 std::vector<esl::GridEntry<C>> tmp;
                 make_grid<C>(tp, ts, first[b].lo, first[b].hi, G, tmp, sshift);
-                for (size_t k = 0; k < n_sm; ++k) sg.push_back(tmp[std::min(k, tmp.size() - 1)].s);
+                for (size_t k = 0; k < n_sm; ++k) {
+                    const esl::GridEntry<C> &e = tmp[std::min(k, tmp.size() - 1)];
+                    // targets a read starting in bucket k can reach: from the first candidate on, starting before the
+                    // end of the bucket plus the longest read
+                    const long double reach = (long double)(((u64)k + 1) << sshift) + (long double)ctx->sgrid_lmax;
+                    C hi_end = 0;
+                    for (int j = e.j; j < first[b].hi && (long double)ts[j] < reach; ++j) hi_end = std::max(hi_end, te[j]);
+                    sg.push_back(e.s);
+                    sg.push_back(hi_end);
+                }
             }
             CU(ctx->d_sgrid.upload(sg.data(), sg.size() * sizeof(C)));
             ctx->sgrid_n = (int)n_sm;
@@ -385,6 +400,8 @@ int ensure_index(esl_ctx *ctx, bool need_pool)
     if (need_pool && !ctx->have_pool) return ctx->fail(ESL_ERR_STATE, "esl_set_length_table has not been called");
     for (int32_t b : ctx->m_bc)
         if (b >= ctx->B) return ctx->fail(ESL_ERR_INVALID, "blocked interval names barcode %d but n_barcodes is %d", b, ctx->B);
+    // the shared pre-filter's upper bounds assume no read is longer than sgrid_lmax
+    if (need_pool && ctx->sgrid_n && (u64)ctx->pool_max > ctx->sgrid_lmax) ctx->index_dirty = true;
     if (ctx->index_dirty) {
         CU(cudaSetDevice(ctx->device));
         ctx->wide = ctx->G > 0xFFFFFFF0ull;
@@ -456,7 +473,7 @@ size_t bulk_smem(const esl_ctx *ctx)
     const size_t entry = ctx->wide ? 8 : 4;
     const size_t item = ctx->wide ? sizeof(esl::WalkItem<uint64_t>) : sizeof(esl::WalkItem<uint32_t>);
     const size_t queues = ctx->sgrid_n ? 0 : (size_t)(esl::kBulkBlock / 32) * esl::kQueueCap * item; // per-warp candidate queues
-    return queues + (ctx->n_hot ? (size_t)esl::kHotWords * 4 : 0) + (size_t)B * ctx->sgrid_n * entry + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
+    return queues + (ctx->n_hot ? (size_t)esl::kHotWords * 4 : 0) + (size_t)B * ctx->sgrid_n * entry * 2 + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
            (size_t)esl::kCdfLut * 2 + 32;
 }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }

@@ -172,10 +172,11 @@ struct DevCtx {
     const int32_t *__restrict__ hot_row;   // [n_hot] row of each hot target's slot
     int n_hot;
     int n_seg, n_tgrid, n_trec, n_mgrid, n_mrec; // array sizes (debug bounds checks)
-    // small target sets: for every first layer a coarser grid holding only the START of each bucket's first
-    // candidate (sgrid_n entries per barcode, bucket width 2^sgrid_shift), staged in shared memory by the bulk
-    // kernel: "start >= read end" settles the common no-overlap case without any global load, everything else
-    // goes through the exact global grid.  NULL when the first layers do not fit the shared-memory budget.
+    // small target sets: for every first layer a coarser grid holding per bucket the pair {START of the bucket's
+    // first candidate, largest END a read starting in the bucket can meet} (sgrid_n pairs per barcode, bucket width
+    // 2^sgrid_shift), staged in shared memory by the bulk kernel: "start >= read end" or "end <= read start" settles
+    // the common no-overlap case without any global load, everything else goes through the exact global grid.
+    // NULL when the first layers do not fit the shared-memory budget.
     const C *__restrict__ sgrid;
     int sgrid_n, sgrid_shift;
     i64 n_targets;
@@ -212,6 +213,7 @@ struct PhiloxSrc {
     PhiloxKeys keys; // round keys of (k0, k1), filled by the host
     static constexpr bool kHasLabel = false;
     static constexpr bool kBounded = false;
+    static constexpr bool kPoolLengths = true; // no read is longer than the pool's longest entry
     __device__ __forceinline__ i64 count(int) const { return 0x7fffffffffffffffLL; }
 
     template <typename C>
@@ -263,6 +265,7 @@ struct DrawSrc {
     const i64 *__restrict__ seg;
     static constexpr bool kHasLabel = false;
     static constexpr bool kBounded = true;
+    static constexpr bool kPoolLengths = false; // recorded lengths: the pool's maximum says nothing about them
     __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
 
     template <typename C>
@@ -289,6 +292,7 @@ struct ReadSrc {
     const i64 *__restrict__ seg;
     static constexpr bool kHasLabel = true;
     static constexpr bool kBounded = true;
+    static constexpr bool kPoolLengths = false; // recorded lengths: the pool's maximum says nothing about them
     __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
 
     template <typename C>
@@ -587,7 +591,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
 {
     extern __shared__ u64 smem[];
     const int B = cx.n_barcodes;
-    const int n_sgrid = kShared ? B * cx.sgrid_n : 0; // kShared: small target sets with a shared-memory pre-filter grid
+    const int n_sgrid = kShared ? 2 * B * cx.sgrid_n : 0; // kShared: small target sets with a shared-memory pre-filter grid (pairs)
     // candidate queues first (16-byte aligned); the shared pre-filter path tallies in place and has none
     WalkItem<C> *queue = (WalkItem<C> *)smem + (threadIdx.x >> 5) * kQueueCap;
     const size_t queue_words = kShared ? 0 : (size_t)(kBulkBlock / 32) * kQueueCap * sizeof(WalkItem<C>) / 8;
@@ -707,9 +711,10 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             for (int i = 0; i < kBulkIpt; ++i) {
                 const bool ok = label[i] >= 0 && label[i] < B;
                 ESL_CHK((int)((u64)st[i] >> cx.sgrid_shift) < cx.sgrid_n, "shared grid index");
-                const C first = s_grid[(ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift)];
+                const C *g = s_grid + 2 * ((ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift));
+                const C first = g[0], reach = g[1]; // first candidate's start; largest end a read from this bucket can meet
                 const C re = (C)(st[i] + L[i]);
-                if (ok && first < re)
+                if (ok && first < re && (!Src::kPoolLengths || st[i] < reach))
                     tally_first_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), st[i], re, label[i], 1, s_hot);
             }
             if (cx.any_extra) { // the pre-filter only covers first layers

@@ -709,3 +709,26 @@ def test_native_hot_targets_private_tallies(eng):
     s, ln, lab = eng.materialize_reads(77, 0, 1, False, int(nr[1]))
     rep = eng.replay_reads(s, ln, lab, [0, int(nr[1])]).cpu()
     assert np.array_equal(rep.tallies[0].numpy(), t)
+
+
+def test_native_longer_pool_rebuilds_prefilter(eng):
+    """Small target sets are pre-filtered in shared memory with per-bucket bounds that assume a longest read; a new
+    length table with longer reads must rebuild them (no stale bound may hide an overlap).  Exact against the CPU
+    restatement before and after the switch, targets untouched in between."""
+    G = 40_000_000
+    rng = np.random.RandomState(31)
+    ts = np.sort(rng.randint(0, G - 20000, 60)); te = ts + rng.randint(500, 20000, 60)
+    tb = (np.arange(60) % 3).astype(np.int32)
+    cdf = np.array([0.2, 0.5, 1.0])
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
+    for mean, cov in ((800, 3.0), (150000, 25.0)):  # the second pool's reads are ~200x longer than the first's
+        pool = O.lognormal_pool(O.Rng(mean), mean, 1, 10, n=50000)
+        eng.set_length_table(pool)
+        assert eng.bulk_reads(cov) > 3000
+        res = eng.run_batch(8, 0, 2, 1, cov).cpu()
+        it = NN.native_iteration(8, 0, 2, G, cov, pool, cdf)
+        exp = O.count_matches_indexed(ts, te, tb, 3, it["start"], it["start"] + it["length"], it["label"], 1)
+        t = res.tallies[0].numpy()
+        assert int(res.n_reads[0]) == it["n_placed"]
+        assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+        assert t[:, 2].sum() > 0
