@@ -473,7 +473,7 @@ size_t bulk_smem(const esl_ctx *ctx)
     const size_t entry = ctx->wide ? 8 : 4;
     const size_t item = ctx->wide ? sizeof(esl::WalkItem<uint64_t>) : sizeof(esl::WalkItem<uint32_t>);
     const size_t queues = ctx->sgrid_n ? 0 : (size_t)(esl::kBulkBlock / 32) * esl::kQueueCap * item; // per-warp candidate queues
-    return queues + (ctx->n_hot ? (size_t)esl::kHotWords * 4 : 0) + (size_t)B * ctx->sgrid_n * entry * 2 + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
+    return queues + (ctx->n_hot ? (size_t)esl::kHotWords * 4 : 0) + ((size_t)B * ctx->sgrid_n * entry * 2 + 15) / 16 * 16 + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
            (size_t)esl::kCdfLut * 2 + 32;
 }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }

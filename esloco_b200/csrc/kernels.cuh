@@ -592,19 +592,24 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     extern __shared__ u64 smem[];
     const int B = cx.n_barcodes;
     const int n_sgrid = kShared ? 2 * B * cx.sgrid_n : 0; // kShared: small target sets with a shared-memory pre-filter grid (pairs)
-    // candidate queues first (16-byte aligned); the shared pre-filter path tallies in place and has none
+    // Shared-memory layout: the arrays of compile-time size come first, so the hot ones sit at constant addresses
+    // (at 48 registers the compiler otherwise recomputes their bases from the kernel parameters on every use):
+    //   [candidate queues (general variant)] [hot-target tallies (kHot)] [barcode start table] [pre-filter grid
+    //   (shared variant)] then, 16-byte aligned, [first-layer descriptors] [label histogram] [CDF thresholds]
     WalkItem<C> *queue = (WalkItem<C> *)smem + (threadIdx.x >> 5) * kQueueCap;
-    const size_t queue_words = kShared ? 0 : (size_t)(kBulkBlock / 32) * kQueueCap * sizeof(WalkItem<C>) / 8;
+    constexpr size_t queue_words = kShared ? 0 : (size_t)(kBulkBlock / 32) * kQueueCap * sizeof(WalkItem<C>) / 8;
     // private tallies of the hot targets + their rows (kHot: the host flagged some; otherwise the null pointer is a
     // compile-time constant and every hot-target branch below folds away)
     uint32_t *const s_hot = kHot ? (uint32_t *)(smem + queue_words) : nullptr;
-    const size_t q_words = queue_words + (kHot ? kHotWords / 2 : 0); // (a multiple of 16 bytes: s_desc is an int4 array)
-    int4 *s_desc = (int4 *)(smem + q_words);                    // [min(B, kSmemDescs)] first-layer descriptors
+    constexpr size_t lut_words = queue_words + (kHot ? kHotWords / 2 : 0);
+    uint16_t *s_lut = (uint16_t *)(smem + lut_words);           // [kCdfLut]
+    constexpr size_t grid_words = lut_words + kCdfLut * 2 / 8;
+    C *s_grid = (C *)(smem + grid_words);                       // [B][sgrid_n] pairs
+    const size_t desc_words = grid_words + ((size_t)n_sgrid * sizeof(C) + 15) / 16 * 2;
+    int4 *s_desc = (int4 *)(smem + desc_words);                 // [min(B, kSmemDescs)] first-layer descriptors
     const int n_sdesc = B <= kSmemDescs ? B : 0;
     int *s_hist = (int *)(s_desc + n_sdesc);                    // [B + 2] reads per label since the last flush
     uint32_t *s_cdf = (uint32_t *)(s_hist + B + 2);             // [B]
-    uint16_t *s_lut = (uint16_t *)(s_cdf + B);                  // [kCdfLut]
-    C *s_grid = (C *)(smem + q_words + ((size_t)n_sdesc * 16 + (size_t)(2 * B + 2) * 4 + (size_t)kCdfLut * 2 + 15) / 8); // [B][sgrid_n]
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < n_sgrid; i += kBulkBlock) s_grid[i] = cx.sgrid[i];
     for (int i = tid; i < n_sdesc; i += kBulkBlock) s_desc[i] = __ldg(reinterpret_cast<const int4 *>(cx.seg + i));
