@@ -217,3 +217,25 @@ def test_bed_variants_match_reference(tmp_path):
         assert _jsonable(targets) == g["targets"], c["name"]
         assert _jsonable(masked) == g["masked"], c["name"]
         assert float(np.random.rand()) == g["stream_tail"], c["name"]
+
+
+def test_targets_to_arrays_shapes_and_barcode_rule():
+    """The column-wise fast path (I mode: every value a [start, end] list) and the per-entry path (ROI dicts, mixed or
+    ragged values) give the same arrays; the barcode of a key is its second `_` token iff that is the canonical decimal
+    spelling of a barcode number below n_barcodes (counting.py:37 compares strings)."""
+    from esloco_b200.utils import targets_to_arrays
+    ins = {"Barcode_0_insertion_0": [10, 20], "Barcode_1_insertion_0": [30, 45], "Barcode_01_insertion_1": [5, 6],
+           "Barcode_7_insertion_2": [1, 2], "nounderscore": [3, 4], "x_-1_y": [8, 9]}
+    keys, s, e, b = targets_to_arrays(ins, 2)
+    assert keys == list(ins) and s.tolist() == [10, 30, 5, 1, 3, 8] and e.tolist() == [20, 45, 6, 2, 4, 9]
+    assert b.tolist() == [0, 1, -1, -1, -1, -1] and s.dtype == np.int64 and b.dtype == np.int32
+    roi = {"R0_0": {"start": 10, "end": 20, "weight": 1}, "R0_1": {"start": 10, "end": 20, "weight": 1}, "R1_0": [7, 9, "extra"]}
+    keys, s, e, b = targets_to_arrays(roi, 2)
+    assert s.tolist() == [10, 10, 7] and e.tolist() == [20, 20, 9] and b.tolist() == [0, 1, 0]
+    big = {f"Barcode_{i % 3}_insertion_{i}": [i * 10, i * 10 + 5] for i in range(5000)}
+    keys, s, e, b = targets_to_arrays(big, 3)
+    assert (s == np.arange(5000) * 10).all() and (e - s == 5).all() and (b == np.arange(5000) % 3).all()
+    np_vals = {"a_0": [np.int64(4), np.int64(9)], "b_1": [np.int64(1), 2]}
+    keys, s, e, b = targets_to_arrays(np_vals, 2)
+    assert s.tolist() == [4, 1] and e.tolist() == [9, 2]
+    assert targets_to_arrays({}, 4)[1].size == 0
