@@ -674,13 +674,20 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
         uint32_t L[kBulkIpt];
         C st[kBulkIpt];
         int label[kBulkIpt];
+        // phase 1: draws (Philox, pool gather, start, barcode)
+        if (hi - base >= (uint32_t)kBulkTile) { // full tile (block-uniform; all but the last tile of a range)
 #pragma unroll
-        for (int i = 0; i < kBulkIpt; ++i) { // phase 1: draws (Philox, pool gather, start, barcode)
-            // branch-free tail handling: a thread past the end of the range redraws the range's last draw and is
-            // masked out afterwards (label = invalid, length 0)
-            const uint32_t n = base + i * kBulkBlock + tid;
-            src.draw(cx, s_cdf, s_lut, it, (i64)(n < hi ? n : hi - 1), L[i], st[i], label[i]);
-            if (n >= hi) { L[i] = 0; label[i] = kLabelInvalid; }
+            for (int i = 0; i < kBulkIpt; ++i)
+                src.draw(cx, s_cdf, s_lut, it, (i64)(base + i * kBulkBlock + tid), L[i], st[i], label[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kBulkIpt; ++i) {
+                // branch-free tail handling: a thread past the end of the range redraws the range's last draw and is
+                // masked out afterwards (label = invalid, length 0)
+                const uint32_t n = base + i * kBulkBlock + tid;
+                src.draw(cx, s_cdf, s_lut, it, (i64)(n < hi ? n : hi - 1), L[i], st[i], label[i]);
+                if (n >= hi) { L[i] = 0; label[i] = kLabelInvalid; }
+            }
         }
         u64 my = 0;
         if (!Src::kHasLabel && kMask) { // phase 2: blocked regions -- probe both trees for all reads, then the slow path
