@@ -719,15 +719,28 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 hist_add(s_hist, label[i] != kLabelInvalid && label[i] < B ? label_slot(label[i], B) : -1, 1, B + 2);
         }
         if (kShared) { // phase 4, small target sets: shared-memory pre-filter, exact path for the rest
+            unsigned maybe = 0; // bit i: read i may overlap a first-layer target
+            if (plain_labels && hi - base >= (uint32_t)kBulkTile) { // one barcode, no mask, full tile: every read is valid
 #pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i) {
-                const bool ok = label[i] >= 0 && label[i] < B;
-                ESL_CHK((int)((u64)st[i] >> cx.sgrid_shift) < cx.sgrid_n, "shared grid index");
-                const C *g = s_grid + 2 * ((ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift));
-                const C first = g[0], reach = g[1]; // first candidate's start; largest end a read from this bucket can meet
-                const C re = (C)(st[i] + L[i]);
-                if (ok && first < re && (!Src::kPoolLengths || st[i] < reach))
-                    tally_first_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), st[i], re, label[i], 1, s_hot);
+                for (int i = 0; i < kBulkIpt; ++i) {
+                    const C *g = s_grid + 2 * (int)((u64)st[i] >> cx.sgrid_shift);
+                    maybe |= (unsigned)(g[0] < (C)(st[i] + L[i]) && (!Src::kPoolLengths || st[i] < g[1])) << i;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kBulkIpt; ++i) {
+                    const bool ok = label[i] >= 0 && label[i] < B;
+                    ESL_CHK((int)((u64)st[i] >> cx.sgrid_shift) < cx.sgrid_n, "shared grid index");
+                    const C *g = s_grid + 2 * ((ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift));
+                    // g[0]: first candidate's start; g[1]: largest end a read from this bucket can meet
+                    maybe |= (unsigned)(ok && g[0] < (C)(st[i] + L[i]) && (!Src::kPoolLengths || st[i] < g[1])) << i;
+                }
+            }
+            if (maybe) {
+#pragma unroll
+                for (int i = 0; i < kBulkIpt; ++i)
+                    if (maybe >> i & 1)
+                        tally_first_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), st[i], (C)(st[i] + L[i]), label[i], 1, s_hot);
             }
             if (cx.any_extra) { // the pre-filter only covers first layers
 #pragma unroll
