@@ -306,19 +306,25 @@ int upload_index(esl_ctx *ctx)
     seg.insert(seg.end(), extra.begin(), extra.end());
     ctx->n_indexed = (i64)ts.size();
     std::vector<esl::TargetRec<C>> trec(ts.size());
-    std::vector<int32_t> hot_row; // rows of the targets that get a private shared-memory tally (first kHotSlots hot ones)
+    // hot targets: a read overlaps them with probability >= 1/512 (whole-chromosome ROIs and the like); the
+    // kHotSlots hottest get a private shared-memory tally per CTA (their record carries the slot, hot_row[] the row)
+    std::vector<int32_t> hot_row;
     {
-        size_t j = 0;
+        std::vector<std::pair<long double, int>> hot; // (-p_hit, record index): sorts hottest first, ties by position
         for (const esl::SegDesc &d : seg)
-            for (int k = d.lo; k < d.hi; ++k, ++j) {
-                esl::TargetRec<C> r{};
-                r.s = ts[k]; r.e = te[k]; r.row = trow[k];
-                // hot target: a read overlaps it with probability >= 1/512 (whole-chromosome ROIs and the like)
+            for (int k = d.lo; k < d.hi; ++k) {
                 const long double p_hit = ((long double)(te[k] - ts[k]) + ctx->pool_mean) / (long double)G;
-                if (p_hit >= 1.0L / 512 && (int)hot_row.size() < esl::kHotSlots) {
-                    r.row = (int)(0x80000000u | (uint32_t)hot_row.size()); // the record carries the slot, hot_row[] the row
-                    hot_row.push_back(trow[k]);
-                }
+                if (p_hit >= 1.0L / 512) hot.emplace_back(-p_hit, k);
+            }
+        std::sort(hot.begin(), hot.end());
+        if (hot.size() > (size_t)esl::kHotSlots) hot.resize(esl::kHotSlots);
+        std::vector<int> slot_of(ts.size(), -1);
+        for (size_t h = 0; h < hot.size(); ++h) { slot_of[hot[h].second] = (int)h; hot_row.push_back(trow[hot[h].second]); }
+        for (const esl::SegDesc &d : seg)
+            for (int k = d.lo; k < d.hi; ++k) {
+                esl::TargetRec<C> r{};
+                r.s = ts[k]; r.e = te[k];
+                r.row = slot_of[k] >= 0 ? (int)(0x80000000u | (uint32_t)slot_of[k]) : trow[k];
                 r.s_next = k + 1 < d.hi ? ts[k + 1] : (C) ~(C)0;
                 trec[k] = r;
             }
