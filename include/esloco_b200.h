@@ -92,7 +92,9 @@ int esl_set_blocked(esl_ctx *ctx, const int64_t *start, const int64_t *end, cons
 
 /* Read-length pool: the source distribution after the `> min_read_length` filter (read_operations.py:24-25,
  * config_handler.py:44).  A read length is a uniform pick from it (combined_calculations.py:57 +
- * read_operations.py:102 collapse to that). */
+ * read_operations.py:102 collapse to that).  Host memory; copied to the device and reduced there (mean, sd, max).
+ * The device index of small target sets carries bounds that assume the longest read, so a table whose longest
+ * read exceeds every earlier one (rounded up to a power of two) rebuilds that index on the next run. */
 int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n);
 
 /* Scratch bytes esl_run_batch / esl_replay_draws need for n_iter iterations at `coverage`
