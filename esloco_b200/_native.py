@@ -43,6 +43,7 @@ SYMBOLS = {
     "esl_replay_thin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
     "esl_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "esl_scan_read_lengths": (C.c_int64, [C.c_char_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]),
+    "esl_write_match_rows": (C.c_int64, [C.c_char_p, C.c_int32, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_char_p]),
     "esl_plan_target_layers": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "esl_set_hit_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "esl_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),

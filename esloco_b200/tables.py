@@ -53,22 +53,79 @@ def matches_table(keys, mode, combos, iteration_ids, tallies_per_combo, overlaps
     return df
 
 
+MATCH_COLUMNS = ["target_region", "full_matches", "partial_matches", "overlap", "on_target_bases", "mean_read_length",
+                 "coverage", "target", "barcode", "insertion", "iteration"]
+_NEEDS_QUOTING = ("\t", '"', "\n", "\r")
+
+
+def _field(v):
+    """Text pandas.to_csv writes for an object-column value."""
+    return "" if v is None else str(v)
+
+
 class MatchesWriter:
     """Streams `{exp}_matches_table.csv` to disk chunk by chunk (rows: iteration -> combination -> target), so a
     run with 10^8+ rows never holds more than one chunk of iterations in memory.  Each rank of a multi-GPU run writes
-    its own contiguous block of iterations to a part file; `merge_parts` concatenates them in rank order."""
+    its own contiguous block of iterations to a part file; `merge_parts` concatenates them in rank order.
 
-    def __init__(self, path, keys, mode, combos, write_header=True):
+    Rows go through the native writer (`esl_write_match_rows`): the text of a row that does not change between
+    iterations is prepared once per target here, the library formats the three integers next to it straight from
+    the tally array (tens of millions of rows per second instead of pandas' ~10^5).  The pandas path of
+    `matches_table` remains for per-read overlap lists and for keys that would need CSV quoting; both produce the
+    same bytes (tests)."""
+
+    def __init__(self, path, keys, mode, combos, write_header=True, native=True):
         self.path, self.keys, self.mode, self.combos = path, keys, mode, combos
         self.header = write_header
+        self._blobs = None
         open(path, "w").close()
+        if native:
+            self._prepare_native()
+
+    def _prepare_native(self):
+        kcols = split_target_keys(self.keys, self.mode)
+        names = [c for c in ("target", "barcode", "insertion") if c in kcols]
+        texts = [list(map(_field, kcols[c])) for c in names]
+        everything = "".join(self.keys) + "".join("".join(col) for col in texts)
+        if any(ch in everything for ch in _NEEDS_QUOTING):
+            return  # some field needs quoting: let pandas write
+        pre = [(k + "_").encode() for k in self.keys]
+        pre_off = np.zeros(len(pre) + 1, np.int64)
+        np.cumsum([len(b) for b in pre], out=pre_off[1:])
+        mids = []
+        for mrl, cov in self.combos:
+            head = f"\t{_field(mrl)}\t{_field(cov)}\t"
+            rows = [(head + "\t".join(vals) + "\t").encode() for vals in zip(*texts)]
+            off = np.zeros(len(rows) + 1, np.int64)
+            np.cumsum([len(b) for b in rows], out=off[1:])
+            mids.append((b"".join(rows), off))
+        self._blobs = (b"".join(pre), pre_off, mids)
+        self._columns = [c for c in MATCH_COLUMNS if c != "insertion" or "insertion" in kcols]
 
     def append(self, iteration_ids, tallies_per_combo, overlaps=None):
         if len(iteration_ids) == 0:
             return
-        df = matches_table(self.keys, self.mode, self.combos, iteration_ids, tallies_per_combo, overlaps)
-        df.to_csv(self.path, sep="\t", header=self.header, index=False, mode="a")
-        self.header = False
+        if self._blobs is None or overlaps is not None:
+            df = matches_table(self.keys, self.mode, self.combos, iteration_ids, tallies_per_combo, overlaps)
+            df.to_csv(self.path, sep="\t", header=self.header, index=False, mode="a")
+            self.header = False
+            return
+        from . import _native
+        lib = _native.load()
+        if self.header:
+            with open(self.path, "a") as fh:
+                fh.write("\t".join(self._columns) + "\n")
+            self.header = False
+        pre_blob, pre_off, mids = self._blobs
+        T = len(self.keys)
+        blocks = [np.ascontiguousarray(t, dtype=np.int64) for t in tallies_per_combo]  # [n_iter, T, 3] each
+        for i, it in enumerate(iteration_ids):
+            for c, (mid_blob, mid_off) in enumerate(mids):
+                rows = blocks[c][i]
+                rc = lib.esl_write_match_rows(self.path.encode(), 1, pre_blob, pre_off.ctypes.data, mid_blob, mid_off.ctypes.data,
+                                              b"[]", rows.ctypes.data, T, str(it).encode())
+                if rc < 0:
+                    raise OSError(f"esl_write_match_rows failed on {self.path} (status {rc})")
 
     @staticmethod
     def merge_parts(final_path, part_paths):

@@ -183,6 +183,17 @@ int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t 
 int64_t esl_scan_read_lengths(const char *path, int32_t is_fastq, int64_t min_read_length, uint32_t *out,
                               int64_t capacity, double *mean_out);
 
+/* Host helper (no GPU): append the rows of one (iteration, combination) block of `{exp}_matches_table.csv`
+ * (esloco.py:155-160,198-205) to `path` (append = 0 truncates first).  Row k is
+ *   pre[k] iteration \t full \t partial \t overlap_field \t on_target_bases mid[k] iteration \n
+ * where pre[k] = pre_blob[pre_off[k] .. pre_off[k+1]) is "<target key>_" and mid[k] the tab-framed columns that do
+ * not change between iterations (mean_read_length, coverage, target, barcode[, insertion]); tallies = host
+ * [n_targets][3] int64.  Returns the bytes written or a negative esl_status.  The caller guarantees that no field
+ * needs CSV quoting. */
+int64_t esl_write_match_rows(const char *path, int32_t append, const char *pre_blob, const int64_t *pre_off,
+                             const char *mid_blob, const int64_t *mid_off, const char *overlap_field,
+                             const int64_t *tallies, int64_t n_targets, const char *iteration);
+
 /* Host helper (no GPU): how the library would split one barcode's n targets into index layers over a genome of
  * size genome_size (a layer is scanned front to back, nesting is tolerated while it costs
  * reads at most a few wasted record loads).  layer_out[i] receives the layer of target i (-1 for an empty target,

@@ -3,5 +3,5 @@
 set -e
 n=$1; shift
 cd /root/repo/esloco_b200/csrc
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -cudart static "$@" -o ../_variants/$n.so esl_api.cu seqscan.cpp -lz
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -cudart static "$@" -o ../_variants/$n.so esl_api.cu seqscan.cpp tablewriter.cpp -lz
 echo built $n

@@ -138,3 +138,34 @@ def test_gaussian_filter_matches_scipy():
     for n in (1, 4, 13, 500, 3100):
         x = np.random.RandomState(n).rand(n) * 30
         assert np.allclose(gaussian_filter1d(x, 3), ref(x, 3))
+
+
+@pytest.mark.parametrize("mode", ["I", "ROI"])
+def test_native_row_writer_equals_pandas_bytes(tmp_path, mode):
+    """esl_write_match_rows (host helper of the library) writes the matches table byte for byte as pandas.to_csv does:
+    two combinations (an int and a float coverage), chunked appends, a part file without header, keys without a
+    barcode token, 13-digit tallies; keys that would need CSV quoting fall back to pandas."""
+    from esloco_b200.tables import MatchesWriter
+    rng = np.random.RandomState(3)
+    if mode == "I":
+        keys = [f"Barcode_{i % 5}_insertion_{i // 5}" for i in range(400)]
+    else:
+        keys = [f"R{i // 3}_{i % 3}" for i in range(300)] + ["weird", "a_b_c", "x_"]
+    T, its, combos = len(keys), [0, 1, 2, 10, 11], [(15000, 30), (8000, 0.5)]
+    tal = [rng.randint(0, 10**13, (len(its), T, 3)).astype(np.int64) for _ in combos]
+    tal[0][0, 0] = 0
+    out = {}
+    for native in (True, False):
+        for header in (True, False):
+            p = str(tmp_path / f"m_{native}_{header}.csv")
+            w = MatchesWriter(p, keys, mode, combos, write_header=header, native=native)
+            assert (w._blobs is not None) == native
+            w.append(its[:2], [x[:2] for x in tal]); w.append([], [x[:0] for x in tal]); w.append(its[2:], [x[2:] for x in tal])
+            out[native, header] = open(p, "rb").read()
+    assert out[True, True] == out[False, True] and out[True, False] == out[False, False]
+    assert out[True, True].count(b"\n") == 1 + len(its) * len(combos) * T
+    bad = keys[:3] + ['has"quote_1', "has\ttab_2"]
+    w = MatchesWriter(str(tmp_path / "q.csv"), bad, mode, combos)
+    assert w._blobs is None  # pandas path: it knows how to quote
+    w.append([0], [x[:1, :len(bad)] for x in tal])
+    assert b'"' in open(w.path, "rb").read()
