@@ -169,3 +169,23 @@ def test_native_row_writer_equals_pandas_bytes(tmp_path, mode):
     assert w._blobs is None  # pandas path: it knows how to quote
     w.append([0], [x[:1, :len(bad)] for x in tal])
     assert b'"' in open(w.path, "rb").read()
+
+
+def test_native_row_writer_errors(tmp_path):
+    """No exception crosses the ABI: a path that cannot be opened or a NULL argument gives a negative status, and the
+    Python writer turns it into OSError."""
+    from esloco_b200 import _native
+    from esloco_b200.tables import MatchesWriter
+    lib = _native.load()
+    off = np.zeros(2, np.int64); off[1] = 2
+    t = np.zeros((1, 3), np.int64)
+    bad = str(tmp_path / "no_such_dir" / "m.csv").encode()
+    assert lib.esl_write_match_rows(bad, 1, b"k_", off.ctypes.data, b"\t\t", off.ctypes.data, b"[]", t.ctypes.data, 1, b"0") < 0
+    assert lib.esl_write_match_rows(None, 1, b"k_", off.ctypes.data, b"\t\t", off.ctypes.data, b"[]", t.ctypes.data, 1, b"0") < 0
+    ok = str(tmp_path / "m.csv").encode()
+    assert lib.esl_write_match_rows(ok, 0, b"k_", off.ctypes.data, b"\t\t", off.ctypes.data, b"[]", t.ctypes.data, 1, b"7") == len(b"k_7\t0\t0\t[]\t0\t\t7\n")
+    assert open(ok, "rb").read() == b"k_7\t0\t0\t[]\t0\t\t7\n"
+    w = MatchesWriter(str(tmp_path / "w.csv"), ["a_0"], "ROI", [(1, 1)])
+    w.path = str(tmp_path / "gone" / "w.csv")
+    with pytest.raises(OSError):
+        w.append([0], [np.zeros((1, 1, 3), np.int64)])
