@@ -732,3 +732,54 @@ def test_native_longer_pool_rebuilds_prefilter(eng):
         assert int(res.n_reads[0]) == it["n_placed"]
         assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
         assert t[:, 2].sum() > 0
+
+
+def test_full_size_config3_consistency(eng):
+    """BASELINE.json configs[2] at FULL size -- the north star's headline shape: hg38-size genome, 30x, 24 barcodes with
+    barcode_weights {"0": 10, "1": 5}, 10 k insertions of 5 kb per barcode (240 k targets), ~6.2 M reads per iteration.
+    This shape takes the GENERAL kernel variant (global grids + per-warp candidate queues), which the toy-size tests
+    only brush.  Size-independent properties, all bit-exact (counting.py:19-57, read_operations.py:94-103):
+      * native tallies == level-1 replay of the materialised reads == the oracle's indexed CPU tally of those reads;
+      * the materialised reads, label counts, N_bases and reads placed == the numpy restatement of the native stream
+        (oracle/native_np.py) with the reference's cut-off rule;
+      * an iteration is the same alone and inside a batch; the cut-off is tight."""
+    from esloco_b200 import synthetic as S
+    from esloco_b200.read_operations import barcode_cdf, barcode_probabilities
+    from esloco_b200.utils import targets_to_arrays
+    G, _ = S.chromosome_dir(S.HG38)
+    B = 24
+    keys, ts, te, tb = targets_to_arrays(S.random_insertions(G, 10000, 5000, B, seed=3), B)
+    assert ts.size == 240_000 and np.array_equal(np.unique(tb), np.arange(B))
+    cdf = barcode_cdf(barcode_probabilities(B, {"0": 10, "1": 5}))
+    pool = S.lognormal_lengths(15000, 1, 1, seed=1)
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
+    eng.set_length_table(pool)
+    cov, seed = 30, 20261019
+    res = eng.run_batch(seed, 0, 40, 3, cov).cpu()
+    thr = cov * G
+    nb, nr = res.n_bases.numpy(), res.n_reads.numpy()
+    assert (nb >= thr).all() and (nb - thr < pool.max()).all() and (res.status.numpy() == 0).all()
+    assert np.array_equal(res.label_counts.numpy().sum(1), nr) and (res.label_counts[:, B:].numpy() == 0).all()
+    solo = eng.run_batch(seed, 0, 41, 1, cov).cpu()
+    assert np.array_equal(solo.tallies[0].numpy(), res.tallies[1].numpy()) and int(solo.n_bases[0]) == int(nb[1])
+    for i in (1, 2):
+        # the CPU restatement of the native stream: same reads, same cut-off, same label histogram
+        it = NN.native_iteration(seed, 0, 40 + i, G, cov, pool, cdf)
+        assert it["n_placed"] == int(nr[i]) and it["covered"] == int(nb[i])
+        assert np.array_equal(np.bincount(it["label"], minlength=B), res.label_counts[i, :B].numpy())
+        s, ln, lab = eng.materialize_reads(seed, 0, 40 + i, False, int(nr[i]))
+        sh, lh, labh = s.cpu().numpy(), ln.cpu().numpy(), lab.cpu().numpy()
+        assert np.array_equal(sh, it["start"]) and np.array_equal(lh, it["length"]) and np.array_equal(labh, it["label"])
+        # the same reads through the other two implementations
+        rep = eng.replay_reads(s, ln, lab, [0, int(nr[i])]).cpu()
+        t = res.tallies[i].numpy()
+        assert np.array_equal(rep.tallies[0].numpy(), t)
+        assert np.array_equal(rep.label_counts[0].numpy(), res.label_counts[i].numpy())
+        exp = O.count_matches_indexed(ts, te, tb, B, it["start"], it["start"] + it["length"], it["label"], 1)
+        assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+        # weighted barcodes: barcode 0 gets 10/37 of the reads, barcode 1 5/37, the others 1/37 each (README.md:204-210)
+        p = np.diff(np.concatenate(([0.0], cdf)))
+        depth = t[:, 2] / 5000.0
+        for b in (0, 1, 7, 23):
+            d = depth[tb == b]
+            assert abs(d.mean() - cov * p[b]) < 5 * d.std(ddof=1) / np.sqrt(d.size), (b, d.mean(), cov * p[b])
