@@ -1,5 +1,5 @@
 """Stand-in for the `intervaltree` package (absent from this image), used ONLY by
-tests/golden/make_golden.py to import the unmodified reference.
+tests/golden/make_*.py and bench.py (python_reference baseline) to import the unmodified reference.
 
 Implements the two calls the reference makes: `IntervalTree.addi(b, e, data)`
 (utils.py:100) and `IntervalTree.overlap(b, e)` (read_operations.py:63) with

@@ -47,7 +47,7 @@ def run_case(mode, tmp):
     else:
         text += "\n[I]\ninsertion_length = 2000\ninsertion_numbers = 4\n"
     open(ini, "w").write(text)
-    env = dict(os.environ, PYTHONPATH=os.path.join(HERE, "shims") + ":/root/reference/src")
+    env = dict(os.environ, PYTHONPATH=os.path.join(HERE, "..", "..", "baseline", "shims") + ":/root/reference/src")
     code = f"import sys; sys.argv=['esloco','--config',{ini!r}]; from esloco.esloco import main; main()"
     subprocess.run([sys.executable, "-c", code], env=env, check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     res = {"ini": text.replace(tmp, "{tmp}")}

@@ -7,7 +7,7 @@ import sys
 import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(HERE, "shims"))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "baseline", "shims"))
 sys.path.insert(0, "/root/reference/src")
 from esloco.config_handler import parse_config  # noqa: E402
 

@@ -8,7 +8,7 @@ the GPU box):
 
 The reference has no tests or fixtures of its own, so every
 fixture here is produced by importing /root/reference/src through the stand-in
-modules in tests/golden/shims/ (intervaltree, Bio.SeqIO, plotly, pyfiglet,
+modules in baseline/shims/ (intervaltree, Bio.SeqIO, plotly, pyfiglet,
 tqdm_joblib are not installed) and calling the reference's own hot-path
 functions in-process after `np.random.seed(seed)`:
 
@@ -35,7 +35,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/src"
-sys.path.insert(0, os.path.join(HERE, "shims"))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "baseline", "shims"))
 sys.path.insert(0, REF_SRC)
 
 import esloco.combined_calculations as cc  # noqa: E402

@@ -11,7 +11,7 @@ import tempfile
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(HERE, "shims"))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "baseline", "shims"))
 sys.path.insert(0, "/root/reference/src")
 sys.path.insert(0, HERE)
 from make_golden import write_bed, write_fasta  # noqa: E402
