@@ -22,7 +22,8 @@ SYMBOLS = {
     "esl_set_barcode_cdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "esl_set_targets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_blocked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
-    "esl_set_length_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "esl_set_length_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "esl_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esl_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_double, C.c_int64]),
     "esl_run_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_double, C.c_int32,
                                 C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -32,7 +33,8 @@ SYMBOLS = {
                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p]),
     "esl_replay_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
-                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
     "esl_replay_draws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int64, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -43,7 +45,10 @@ SYMBOLS = {
     "esl_replay_thin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
     "esl_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "esl_scan_read_lengths": (C.c_int64, [C.c_char_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]),
+    "esl_shift_insertions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "esl_write_match_rows": (C.c_int64, [C.c_char_p, C.c_int32, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_char_p]),
+    "esl_write_match_rows_batch": (C.c_int64, [C.c_char_p, C.c_int32, C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                               C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "esl_plan_target_layers": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "esl_set_hit_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "esl_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),

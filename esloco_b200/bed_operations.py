@@ -5,9 +5,6 @@ import sys
 
 import pandas as pd
 
-ALL_COLS = ["chrom", "start", "end", "id", "barcode", "weight"]
-
-
 def bedcheck(bed):
     """chrN / integer / integer in the first three columns (bed_operations.py:6-16)."""
     ok = (bed.iloc[:, 0].astype(str).str.startswith("chr").all()
@@ -18,52 +15,86 @@ def bedcheck(bed):
     return bool(ok)
 
 
-def _is_missing(x):
-    return x in ("", None) or (isinstance(x, float) and math.isnan(x))
+def _blank(cell):
+    return cell is None or cell == "" or (isinstance(cell, float) and math.isnan(cell))
+
+
+# Optional BED columns in the order they are completed (the default id is built from the weight, so weight first):
+#   name -> (value of a column the file does not have, given the columns so far; replacement for a blank cell or None)
+_OPTIONAL = (
+    ("weight", lambda cols, n: [1] * n, lambda: 1),
+    ("id", lambda cols, n: [f"{c}_{s}_{e}_{w}" for c, s, e, w in zip(cols["chrom"], cols["start"], cols["end"], cols["weight"])], None),
+    ("barcode", lambda cols, n: [[] for _ in range(n)], lambda: []),
+)
+
+
+def _parse_bed_text(bedpath):
+    """Tab-separated text -> (column names or None, list of rows of str cells); blank lines are skipped."""
+    with open(bedpath, "r") as fh:
+        rows = [line.rstrip("\r\n").split("\t") for line in fh if line.strip()]
+    if not rows:
+        raise ValueError("the file holds no rows")
+    head = rows[0]
+    if len(head) > 1 and "chr" in head[0].lower() and head[1].lower() == "start":
+        return head, rows[1:]
+    return None, rows
 
 
 def readbed(bedpath, list_of_chromosomes_in_reference, barcoding=False):
-    """Flexible BED reader (bed_operations.py:28-78): optional header (first cell contains "chr", second is
-    "start"), missing id / barcode / weight columns get defaults (id = chrom_start_end_weight, barcode = [],
-    weight = 1), rows on contigs absent from the reference are dropped.  With barcoding=True the contig names are
-    prefixed like the barcoded chromosome dict ("Barcode_k_")."""
+    """Flexible BED reader with the reference's rules (bed_operations.py:28-78) -> DataFrame with at least
+    chrom / start / end / id / barcode / weight, or None.
+      * header row: first cell contains "chr", second cell is "start" (any case); column names are lower-cased.
+        Without a header only the first three columns count (a header-less file loses its id column).
+      * start / end must be integers and every chrom must begin with "chr", else the file is not BED: None.
+      * columns the file lacks, and blank cells, get defaults: weight 1, barcode [], id "chrom_start_end_weight".
+      * barcoding=True prefixes contig names like the barcoded chromosome dict ("Barcode_k_chrN").
+      * rows on contigs absent from the reference are dropped.
+    A path that cannot be read or parsed ends the program (the reference does the same); bedpath None returns None."""
+    if bedpath is None:
+        logging.info("No BED path given.")
+        return None
     try:
-        bed = pd.read_csv(bedpath, sep="\t", header=None, dtype=str)
-        if "chr" in bed.iloc[0, 0].lower() and bed.iloc[0, 1].lower() == "start":
-            bed = pd.read_csv(bedpath, sep="\t", header=0, dtype=str)
-        else:
-            logging.info(f"No header in {bedpath}. Extracting columns 1-3 and assigning default column names.")
-            bed = bed.iloc[:, :3].copy()
-            bed.columns = ["chrom", "start", "end"]
-        bed["start"] = pd.to_numeric(bed["start"], errors="coerce")
-        bed["end"] = pd.to_numeric(bed["end"], errors="coerce")
-        if not bedcheck(bed):
+        names, rows = _parse_bed_text(bedpath)
+        if names is None:
+            logging.info(f"{bedpath} has no header row: using its first three columns as chrom, start, end.")
+            names, rows = ["chrom", "start", "end"], [r[:3] for r in rows]
+        width = len(names)
+        if any(len(r) > width for r in rows):
+            raise ValueError("a row has more cells than the header")
+        rows = [r + [None] * (width - len(r)) for r in rows]
+        if names[1] != "start" or names[2] != "end":
+            raise KeyError("the second and third columns must be named start and end")
+        cols = {nm: [r[k] if r[k] != "" else None for r in rows] for k, nm in enumerate(names)}
+        n = len(rows)
+        for nm in ("start", "end"):
+            try:
+                cols[nm] = [int(c) for c in cols[nm]]
+            except (TypeError, ValueError):
+                logging.info("The file does not seem to be in BED format. Make sure the data looks like: chrN integer integer")
+                return None
+        if not all(str(c).startswith("chr") for c in cols[names[0]]):
+            logging.info("The file does not seem to be in BED format. Make sure the data looks like: chrN integer integer")
             return None
-        bed.columns = bed.columns.str.lower()
-        missing = sorted(set(ALL_COLS) - set(bed.columns), reverse=True)  # weight before id: the id uses it
-        logging.info(f"Your BED is missing the following columns:{missing}. Trying to fill in default values where possible.")
-        for col in missing:
-            if col == "weight":
-                bed[col] = 1
-            elif col == "id":
-                bed[col] = (bed["chrom"].astype(str) + "_" + bed["start"].astype(str) + "_" + bed["end"].astype(str)
-                            + "_" + bed["weight"].astype(str))
-            else:
-                bed[col] = [[]] * len(bed)
-        bed["weight"] = bed["weight"].apply(lambda x: 1 if _is_missing(x) else x)
-        bed["barcode"] = bed["barcode"].apply(lambda x: [] if _is_missing(x) else x)
+        cols = {nm.lower(): v for nm, v in cols.items()}
+        if "chrom" not in cols:
+            raise KeyError("no chrom column")
+        absent = [nm for nm, _, _ in _OPTIONAL if nm not in cols]
+        logging.info(f"{bedpath}: columns filled with defaults: {absent or 'none'}.")
+        for nm, make, blank_value in _OPTIONAL:
+            if nm not in cols:
+                cols[nm] = make(cols, n)
+            elif blank_value is not None:
+                cols[nm] = [blank_value() if _blank(c) else c for c in cols[nm]]
         if barcoding:
             prefix = "_".join(list(list_of_chromosomes_in_reference)[0].split("_")[:-1])
-            bed["chrom"] = prefix + "_" + bed["chrom"].astype(str)
-        bed = bed[bed["chrom"].isin(list_of_chromosomes_in_reference)]
+            cols["chrom"] = [f"{prefix}_{c}" for c in cols["chrom"]]
+        keep = set(list_of_chromosomes_in_reference)
+        bed = pd.DataFrame({nm: pd.Series(v, dtype="int64" if nm in ("start", "end") else object) for nm, v in cols.items()})
+        return bed[bed["chrom"].isin(keep)]
     except Exception as e:
-        logging.info(f"Not defined or error reading the BED file: {e}")
-        if bedpath is not None:
-            logging.info(f"Exiting. Please check the file at: {bedpath}")
-            print(f"Exiting. Please check the file at: {bedpath}")
-            sys.exit()
-        return None
-    return bed
+        logging.info(f"Could not read the BED file {bedpath}: {e}")
+        print(f"Stopping: the BED file {bedpath} could not be read ({e}).")
+        sys.exit()
 
 
 def chromosome_to_global_coordinates(beddf, input_chromosome_dict):

@@ -43,10 +43,10 @@ def _fastq_lengths(handle, path):
 def _scan_native(fasta_file, is_fastq, min_read_length):
     """One streaming pass in the native library (esl_scan_read_lengths); None when the library is not built."""
     import ctypes as C
+    from . import _native
     try:
-        from . import _native
         lib = _native.load()
-    except Exception:
+    except _native.NativeLibraryError:  # library not built yet: the Python pass below does the same job, slower
         return None
     mean = C.c_double()
     n = lib.esl_scan_read_lengths(fasta_file.encode(), int(is_fastq), int(min_read_length), None, 0, C.byref(mean))

@@ -21,8 +21,19 @@ def _chromosome_of(positions, chromosome_dir):
 
 def _shifted_starts(positions, insertion_length):
     """Every new insertion pushes the earlier insertions that start at or after its position right by
-    insertion_length (create_insertion_genome.py:76-80)."""
+    insertion_length (create_insertion_genome.py:76-80).  Runs in the native host helper esl_shift_insertions; the
+    numpy loop below is the same recurrence and only serves a checkout whose library has not been built yet."""
+    positions = np.ascontiguousarray(positions, np.int64)
     starts = np.empty(len(positions), np.int64)
+    try:
+        from . import _native
+        lib = _native.load()
+    except _native.NativeLibraryError:
+        lib = None
+    if lib is not None:
+        if lib.esl_shift_insertions(positions.ctypes.data, positions.size, int(insertion_length), starts.ctypes.data) != 0:
+            raise ValueError("esl_shift_insertions rejected its arguments")
+        return starts
     for i, p in enumerate(positions):
         head = starts[:i]
         head[head >= p] += insertion_length

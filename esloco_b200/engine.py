@@ -113,7 +113,12 @@ class Engine:
             if a.size and (a.min() < 1 or a.max() > 0xFFFFFFFF):
                 raise ValueError("read lengths must be in [1, 2^32)")
         a = _np(a, np.uint32)
-        self._check(self.lib.esl_set_length_table(self.ctx, a.ctypes.data, a.size))
+        self._check(self.lib.esl_set_length_table(self.ctx, a.ctypes.data, a.size, self._stream()))
+
+    def prepare(self):
+        """Build / upload the device index for the inputs set so far (no-op when nothing changed).  The run methods
+        call it themselves, so the C-level rule "run calls never allocate or block" costs Python callers nothing."""
+        self._check(self.lib.esl_prepare(self.ctx, self._stream()))
 
     # ---- device buffers ------------------------------------------------------------------------------
     def _stream(self):
@@ -142,6 +147,7 @@ class Engine:
     # ---- hot path ------------------------------------------------------------------------------------
     def run_batch(self, seed, combo, iter_begin, n_iter, coverage, consuming=False, min_overlap=1, scaling=1.0, out=None):
         """Native Philox mode: iterations [iter_begin, iter_begin+n_iter) of one combination.  Asynchronous."""
+        self.prepare()
         out = out or self.alloc_outputs(n_iter)
         need = self.lib.esl_workspace_bytes(self.ctx, n_iter, float(coverage), 0)
         ws = self._workspace(max(need, 1))
@@ -153,6 +159,7 @@ class Engine:
 
     def run_batch_staged(self, seed, combo, iter_begin, n_iter, coverage, consuming=False, min_overlap=1, out=None):
         """The staged baseline pipeline (sort + sweep); same draws and outputs as run_batch, slower by design."""
+        self.prepare()
         out = out or self.alloc_outputs(n_iter)
         need = self.lib.esl_staged_workspace_bytes(self.ctx, float(coverage))
         if need < 0:
@@ -169,15 +176,17 @@ class Engine:
         t = self.torch
         seg = np.asarray(seg_offsets, np.int64)
         n_iter = seg.size - 1
+        self.prepare()
         out = out or self.alloc_outputs(n_iter)
         ds, dl, dlab = self._dev(start, t.int64), self._dev(length, t.int64), self._dev(label, t.int32)
         dseg = self._dev(seg, t.int64)
         self._keep = (ds, dl, dlab, dseg)
+        max_reads = int(np.max(np.diff(seg))) if n_iter else 0
+        ws = self._workspace(max(self.lib.esl_workspace_bytes(self.ctx, n_iter, 0.0, max(max_reads, 1)), 1))
         self._check(self.lib.esl_replay_reads(
-            self.ctx, ds.data_ptr(), dl.data_ptr(), dlab.data_ptr(), dseg.data_ptr(), int(seg[-1]),
-            int(np.max(np.diff(seg))) if n_iter else 0, n_iter,
+            self.ctx, ds.data_ptr(), dl.data_ptr(), dlab.data_ptr(), dseg.data_ptr(), int(seg[-1]), max_reads, n_iter,
             int(min_overlap), out.tallies.data_ptr(), out.label_counts.data_ptr(), out.n_bases.data_ptr(),
-            out.n_reads.data_ptr(), out.status.data_ptr(), self._stream()))
+            out.n_reads.data_ptr(), out.status.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
         return out
 
     def replay_draws(self, u_barcode, length, start, seg_offsets, coverage, consuming=False, min_overlap=1,
@@ -187,6 +196,7 @@ class Engine:
         seg = np.asarray(seg_offsets, np.int64)
         n_iter = seg.size - 1
         max_draws = int(np.max(np.diff(seg))) if n_iter else 0
+        self.prepare()
         out = out or self.alloc_outputs(n_iter)
         du, dl, ds = self._dev(u_barcode, t.float64), self._dev(length, t.int64), self._dev(start, t.int64)
         dseg = self._dev(seg, t.int64)
@@ -205,6 +215,7 @@ class Engine:
     def materialize_reads(self, seed, combo, iteration, consuming, n_reads):
         t = self.torch
         n_reads = int(n_reads)
+        self.prepare()
         s = t.empty(n_reads, dtype=t.int64, device=self.tdev)
         ln = t.empty(n_reads, dtype=t.int64, device=self.tdev)
         lab = t.empty(n_reads, dtype=t.int32, device=self.tdev)
@@ -281,6 +292,7 @@ class Engine:
         return int(self.lib.esl_launch_count(self.ctx))
 
     def target_layers(self):
+        self.prepare()
         return int(self.lib.esl_target_layers(self.ctx))
 
     def bulk_reads(self, coverage):

@@ -58,7 +58,7 @@ def run(param_dictionary):
     import torch
     import torch.distributed as dist
     from .combined_calculations import run_simulation_batch
-    from .distributed import gather_iterations, reduce_moments, shard_iterations, world
+    from .distributed import gather_iterations, reduce_moments, shard_iterations, sync_seed, world
     from .session import get_session
     from .tables import MatchesWriter, barcode_distribution_table, summary_table, write_tables
 
@@ -67,6 +67,7 @@ def run(param_dictionary):
     if ws > 1 and not dist.is_initialized():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sync_seed(p)  # one seed for all ranks, also when the INI leaves it to chance
     mode, output_path, experiment_name = p["mode"], p["output_path"], p["experiment_name"]
     log_file = os.path.join(output_path, f"{experiment_name}_log.log")
     setup_logging(log_file)
@@ -101,18 +102,31 @@ def run(param_dictionary):
     moments = [torch.zeros((n_targets, 8), dtype=torch.int64, device=dev) for _ in combos]
     labels = [[torch.zeros((0, p["n_barcodes"] + 2), dtype=torch.int64, device=dev)] for _ in combos]
     nbases = [[torch.zeros((0,), dtype=torch.int64, device=dev)] for _ in combos]
+    statuses = []
     # per-iteration rows are streamed to disk chunk by chunk; every rank writes the block of iterations it owns
     base = f"{output_path}{experiment_name}"
     part = f"{base}_matches_table.csv" if ws == 1 else f"{base}_matches_table.part{rank}.csv"
     writer = MatchesWriter(part, keys, mode, combos, write_header=rank == 0)
     want_lists = bool(p.get("overlap_lists", False))
     t_gpu = time.time()
-    for chunk in iteration_chunks(mine, n_targets, len(combos)) if len(mine) else []:
+    # Software pipeline over chunks of iterations: the GPU work of chunk k+1 (asynchronous launches) and the copy of its
+    # tallies into one of two page-locked staging buffers are issued BEFORE the host formats the rows of chunk k, so
+    # device time and PCIe time hide behind the row writer (which is what the wall clock of a large run is made of).
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [{}, {}]
+    pending = None
+
+    def flush(item):
+        if item is None:
+            return
+        chunk, host, done, overlaps = item
+        done.synchronize()
+        writer.append(list(chunk), [h.numpy() for h in host], overlaps)
+
+    for k, chunk in enumerate(iteration_chunks(mine, n_targets, len(combos)) if len(mine) else []):
         batches, keys = run_simulation_batch(chunk, p, genome_size, target_regions, masked_tree, device=local, to_host=False,
                                              overlap_lists=want_lists)
         for c, res in enumerate(batches):
-            if (res.status & 2).any().item():
-                raise RuntimeError("coverage not reached")
             if chunk[0] == 0 and not p["no_cov_plots"]:
                 # first iteration of every combination (combined_calculations.py:66-74): the binned track behind the
                 # reference's coverage plot, written as a table; drawing it is left to the plotting layer
@@ -125,11 +139,30 @@ def run(param_dictionary):
                 track = binned_coverage(sess.engine, int(p.get("seed", 0)), c, 0, p["consuming"], int(res.n_reads[0]))
                 write_coverage_track(os.path.join(p["output_path_plots"], f"{mrl}_{cov}_coverage.tsv"), *track)
             sess.engine.moments(res.tallies, moments[c])
-            labels[c].append(res.label_counts); nbases[c].append(res.n_bases)
+            labels[c].append(res.label_counts); nbases[c].append(res.n_bases); statuses.append(res.status)
         overlaps = None
         if want_lists:  # rows: iteration -> combination -> target
             overlaps = [batches[c].overlaps[i][j] for i in range(len(chunk)) for c in range(len(combos)) for j in range(n_targets)]
-        writer.append(list(chunk), [res.tallies.cpu().numpy() for res in batches], overlaps)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        host = []
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            for c, res in enumerate(batches):
+                slot = staging[k & 1]
+                hkey = (c, tuple(res.tallies.shape))
+                if hkey not in slot:
+                    slot[hkey] = torch.empty(res.tallies.shape, dtype=torch.int64, pin_memory=True)
+                slot[hkey].copy_(res.tallies, non_blocking=True)
+                res.tallies.record_stream(copy_stream)
+                host.append(slot[hkey])
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        flush(pending)  # rows of the previous chunk, while the GPU runs this one
+        pending = (chunk, host, done, overlaps)
+    flush(pending)
+    if statuses and (torch.cat(statuses) & 2).any().item():
+        raise RuntimeError("coverage not reached")
     for c in range(len(combos)):
         reduce_moments(moments[c])  # the one collective of the data path
         labels[c] = gather_iterations(torch.cat(labels[c]), p["iterations"])

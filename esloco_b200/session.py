@@ -1,6 +1,11 @@
-"""Per-process, per-GPU session: one Engine plus the identity of the inputs currently uploaded, so that
+"""Per-process, per-GPU session: one Engine plus a copy of the inputs currently uploaded, so that
 run_simulation_iteration can be called once per iteration (the reference's calling pattern, esloco.py:144-152)
-without re-uploading targets, mask and length table every time."""
+without re-uploading targets, mask and length table every time.
+
+Inputs are compared by CONTENT (the arrays that would be uploaded against the arrays that were), never by object
+identity: a caller that edits its target dict in place gets the new targets."""
+import logging
+
 import numpy as np
 
 from .engine import Engine
@@ -10,44 +15,74 @@ from .utils import mask_tree_to_arrays, targets_to_arrays
 _sessions = {}
 
 
+def _same(a, b):
+    return a is not None and len(a) == len(b) and all(x.shape == y.shape and np.array_equal(x, y) for x, y in zip(a, b))
+
+
 class Session:
     def __init__(self, device=0):
         self.engine = Engine(device)
         self.pinned = {}  # page-locked staging tensors for device -> host result copies (BatchResult.cpu)
+        self.outputs = {}  # device output buffers reused between chunks of iterations (run_simulation_batch)
         self.invalidate()
 
     def invalidate(self):
-        self._targets_key = None
-        self._mask_key = None
+        """Forget what is uploaded: the next configure / set_pool sends everything again."""
+        self._targets = None
+        self._mask = None
         self._bc_key = None
         self._pool_key = None
+        self._pool_copy = None
+        self.pool_mean = None
         self.keys = None
 
     def configure(self, genome_size, target_regions, masked_tree, n_barcodes, barcode_weights):
+        """Upload whatever differs from what the engine holds.  target_regions: the reference's dict or
+        utils.TargetColumns."""
         eng = self.engine
         if eng.genome_size != genome_size:
             eng.set_genome(genome_size)
+            self._pool_key = None  # the pool is filtered against the genome size
         bc_key = (n_barcodes, repr(barcode_weights))
         if bc_key != self._bc_key:
             eng.set_barcode_cdf(barcode_cdf(barcode_probabilities(n_barcodes, barcode_weights)))
             self._bc_key = bc_key
-            self._targets_key = self._mask_key = None
-        tkey = (id(target_regions), len(target_regions))
-        if tkey != self._targets_key:
-            self.keys, ts, te, tb = targets_to_arrays(target_regions, n_barcodes)
+            self._targets = self._mask = None
+        keys, ts, te, tb = targets_to_arrays(target_regions, n_barcodes)
+        self.keys = keys
+        if not _same(self._targets, (ts, te, tb)):
             eng.set_targets(ts, te, tb)
-            self._targets_key = tkey
-            self._targets_ref = target_regions  # keep alive: id() is the cache key
-        mkey = (id(masked_tree), len(masked_tree) if masked_tree else 0)
-        if mkey != self._mask_key:
-            eng.set_blocked(*mask_tree_to_arrays(masked_tree, n_barcodes))
-            self._mask_key = mkey
-            self._mask_ref = masked_tree
+            self._targets = (ts.copy(), te.copy(), tb.copy())
+        mask = mask_tree_to_arrays(masked_tree, n_barcodes)
+        if not _same(self._mask, mask):
+            eng.set_blocked(*mask)
+            self._mask = mask
+        eng.prepare()
 
     def set_pool(self, key, make_pool):
-        """Upload the length table unless `key` is the one already resident."""
+        """Upload the length table unless `key` is the one already resident (key None: the table itself is compared with
+        the resident one).  Entries that are not shorter than the
+        genome are dropped with a warning: the reference fails (numpy's randint raises "low >= high",
+        read_operations.py:103) only when such a length is actually drawn, which for a 1 M-entry log-normal pool on a
+        small genome is rare per iteration but certain per pool -- dropping them lets those runs complete, as they
+        almost always do in the reference.  The C library itself stays strict (esl_run_batch rejects such a table)."""
+        pool = None
+        if key is None:
+            pool = np.asarray(make_pool())
+            same = self._pool_copy is not None and pool.shape == self._pool_copy.shape and np.array_equal(pool, self._pool_copy)
+            key = self._pool_key if same and self._pool_key is not None else ("given", object())
         if key != self._pool_key:
-            self.engine.set_length_table(make_pool())
+            self._pool_copy = pool.copy() if pool is not None else None
+            pool = np.asarray(make_pool()) if pool is None else pool
+            G = self.engine.genome_size
+            if G and pool.size and int(pool.max()) >= G:
+                keep = pool < G
+                logging.warning(f"{int((~keep).sum())} of {pool.size} read lengths are not shorter than the genome "
+                                f"({G}) and were dropped from the length table.")
+                pool = pool[keep]
+            self.engine.set_length_table(pool)
+            self.engine.prepare()
+            self.pool_mean = float(pool.mean())
             self._pool_key = key
 
 

@@ -2,6 +2,8 @@
 sees contig LENGTHS, never sequence)."""
 import numpy as np
 
+from .create_insertion_genome import _shifted_starts
+
 # GRCh38 primary assembly contig lengths, chr1..chr22, chrX, chrY (sum 3,088,269,832)
 HG38 = [("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559), ("chr4", 190214555), ("chr5", 181538259),
         ("chr6", 170805979), ("chr7", 159345973), ("chr8", 145138636), ("chr9", 138394717), ("chr10", 133797422),
@@ -33,13 +35,9 @@ def random_insertions(genome_size, n_insertions, insertion_length, n_barcodes, s
     targets = {}
     for b in range(n_barcodes):
         pos = rng.integers(0, genome_size, size=n_insertions)
-        starts = np.empty(n_insertions, np.int64)
+        starts = _shifted_starts(pos, insertion_length).tolist()
         for i in range(n_insertions):
-            head = starts[:i]
-            head[head >= pos[i]] += insertion_length
-            starts[i] = pos[i]
-        for i in range(n_insertions):
-            targets[f"Barcode_{b}_insertion_{i}"] = [int(starts[i]), int(starts[i]) + insertion_length]
+            targets[f"Barcode_{b}_insertion_{i}"] = [starts[i], starts[i] + insertion_length]
     return targets
 
 

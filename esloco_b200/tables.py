@@ -3,6 +3,8 @@
 The reference builds one Python dict per (iteration, target) and splits strings per row with pandas; here the
 per-target name columns are derived once from the T keys and tiled over iterations, and the summary comes from the
 per-target moment accumulators (device kernel + NCCL reduce) instead of a groupby over all rows."""
+import ctypes as C
+
 import numpy as np
 import pandas as pd
 
@@ -119,13 +121,17 @@ class MatchesWriter:
         pre_blob, pre_off, mids = self._blobs
         T = len(self.keys)
         blocks = [np.ascontiguousarray(t, dtype=np.int64) for t in tallies_per_combo]  # [n_iter, T, 3] each
-        for i, it in enumerate(iteration_ids):
-            for c, (mid_blob, mid_off) in enumerate(mids):
-                rows = blocks[c][i]
-                rc = lib.esl_write_match_rows(self.path.encode(), 1, pre_blob, pre_off.ctypes.data, mid_blob, mid_off.ctypes.data,
-                                              b"[]", rows.ctypes.data, T, str(it).encode())
-                if rc < 0:
-                    raise OSError(f"esl_write_match_rows failed on {self.path} (status {rc})")
+        ids = np.ascontiguousarray(iteration_ids, dtype=np.int64)
+        n = len(mids)
+        # one library call for the whole chunk: it keeps a single open file and loops over iterations itself
+        ptr = C.c_void_p * n
+        mid_blobs = (C.c_char_p * n)(*[m[0] for m in mids])
+        mid_offs = ptr(*[m[1].ctypes.data for m in mids])
+        tall = ptr(*[b.ctypes.data for b in blocks])
+        rc = lib.esl_write_match_rows_batch(self.path.encode(), 1, pre_blob, pre_off.ctypes.data, n, mid_blobs, mid_offs,
+                                            b"[]", tall, T, ids.size, ids.ctypes.data)
+        if rc < 0:
+            raise OSError(f"esl_write_match_rows_batch failed on {self.path} (status {rc})")
 
     @staticmethod
     def merge_parts(final_path, part_paths):

@@ -72,11 +72,39 @@ def _target_barcode(token, n_barcodes):
     return -1
 
 
+class TargetColumns:
+    """Columnar form of the target dict for large target sets (config 3: 240 k insertions).  The reference's dict
+    `{key: [start, end]}` / `{key: {"start", "end", ...}}` (counting.py:19-30) costs one Python object walk per call;
+    callers that already hold arrays hand them over as they are: start / end = half-open interval per target in row
+    order, barcode = the barcode a read must carry to match (-1: matches nothing), keys = the dict keys (optional, only
+    needed where names are printed).  `from_dict` converts a reference-shaped dict once."""
+
+    def __init__(self, start, end, barcode, keys=None):
+        self.start = np.ascontiguousarray(start, np.int64)
+        self.end = np.ascontiguousarray(end, np.int64)
+        self.barcode = np.ascontiguousarray(barcode, np.int32)
+        if not (self.start.shape == self.end.shape == self.barcode.shape and self.start.ndim == 1):
+            raise ValueError("start, end and barcode must be 1-D arrays of one length")
+        if keys is not None and len(keys) != self.start.size:
+            raise ValueError("keys and columns differ in length")
+        self.keys = keys
+
+    @classmethod
+    def from_dict(cls, target_regions, n_barcodes):
+        keys, s, e, b = targets_to_arrays(target_regions, n_barcodes)
+        return cls(s, e, b, keys)
+
+    def __len__(self):
+        return int(self.start.size)
+
+
 def targets_to_arrays(target_regions, n_barcodes):
     """target dict (I: [start, end] lists; ROI: dicts with start/end, counting.py:24-30) -> keys, start, end and
     the barcode a read must carry: key.split("_")[1] compared as a string with the read label (counting.py:37).
     Written for dicts of 10^5..10^6 targets (config 3: 240 k): one pass per column, the barcode rule evaluated once per
     distinct token."""
+    if isinstance(target_regions, TargetColumns):
+        return target_regions.keys, target_regions.start, target_regions.end, target_regions.barcode
     keys = list(target_regions.keys())
     n = len(keys)
     vals = list(target_regions.values())

@@ -15,10 +15,15 @@
  * Conventions
  *   - plain C types only; every call returns 0 (ESL_OK) or a negative esl_status; no exceptions cross;
  *     esl_last_error(ctx) gives the message of the last failing call on that context.
- *   - esl_set_* take HOST pointers (small, one-off inputs) and build device-resident index structures.
- *   - esl_run_* / esl_replay_* / esl_moments take DEVICE pointers for bulk data and outputs, are
- *     asynchronous on the given CUDA stream (a cudaStream_t passed as void*), and do not allocate.
- *     Scratch is a caller-provided workspace of esl_workspace_bytes().
+ *   - SET-UP calls: esl_set_* take HOST pointers (small, one-off inputs) and only record them (esl_set_length_table
+ *     also uploads and reduces the table); esl_prepare builds the device-resident index from what was set.  Set-up
+ *     calls may allocate device memory and may block on the stream they are given.
+ *   - RUN calls: esl_run_batch / esl_replay_* / esl_moments / esl_materialize_reads / esl_coverage_bins take DEVICE
+ *     pointers for bulk data and outputs, are asynchronous on the given CUDA stream (a cudaStream_t passed as
+ *     void*), never allocate and never block.  They fail with ESL_ERR_STATE when an input changed since the last
+ *     esl_prepare.  Scratch is a caller-provided workspace of esl_workspace_bytes().  (The staged baseline
+ *     esl_run_batch_staged is a measuring stick, not a product call: its first use uploads the targets once more
+ *     in caller order.)
  *   - one host thread per context at a time.
  *   - there is no CPU fallback: esl_create fails if no sm_100 device is present.
  *
@@ -94,8 +99,17 @@ int esl_set_blocked(esl_ctx *ctx, const int64_t *start, const int64_t *end, cons
  * config_handler.py:44).  A read length is a uniform pick from it (combined_calculations.py:57 +
  * read_operations.py:102 collapse to that).  Host memory; copied to the device and reduced there (mean, sd, max).
  * The device index of small target sets carries bounds that assume the longest read, so a table whose longest
- * read exceeds every earlier one (rounded up to a power of two) rebuilds that index on the next run. */
-int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n);
+ * read exceeds every earlier one (rounded up to a power of two) makes the index stale: call esl_prepare again.
+ * Upload and reduction are ordered on `stream`; the call waits for them (the bulk range is planned on the host
+ * from mean / sd / max). */
+int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n, void *stream);
+
+/* Build and upload the device index (target layers + bucket grids per barcode, blocked groups, CDF tables) for the
+ * inputs set so far; a no-op when nothing changed since the last call.  This is where build_mask_tree's trees
+ * (utils.py:89-101) and the target dict of count_matches (counting.py:19-30) become device structures.  Uploads are
+ * ordered on `stream`, so run calls issued afterwards on the same stream see the new index.  Required before the
+ * first run call and after any esl_set_* that changes genome, CDF, targets or blocked intervals. */
+int esl_prepare(esl_ctx *ctx, void *stream);
 
 /* Scratch bytes esl_run_batch / esl_replay_draws need for n_iter iterations at `coverage`
  * (for replay pass the largest per-iteration draw count in max_draws_per_iter, else 0). */
@@ -125,12 +139,13 @@ int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t i
 /* Replay level 1: recorded reads (already cut off), iteration i owns reads [seg_offsets[i], seg_offsets[i+1]).
  * count_matches + count_barcode_occurrences over them (counting.py:7-71).  seg_offsets is a DEVICE array of
  * n_iter+1 int64; total_reads = seg_offsets[n_iter] and max_reads_per_iter = the largest segment (passed so the
- * host need not read them back; max_reads_per_iter <= 0 means "unknown", which only costs empty tiles). */
+ * host need not read them back; max_reads_per_iter <= 0 means "unknown", which only costs empty tiles).
+ * Workspace: esl_workspace_bytes(ctx, n_iter, 0, max_reads_per_iter) (total_reads when that is unknown). */
 int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_length, const int32_t *d_label,
                      const int64_t *d_seg_offsets, int64_t total_reads, int64_t max_reads_per_iter, int32_t n_iter,
                      int64_t min_overlap,
                      int64_t *d_tallies, int64_t *d_label_counts, int64_t *d_n_bases, int64_t *d_n_reads,
-                     int32_t *d_status, void *stream);
+                     int32_t *d_status, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Replay level 2: recorded RAW draws of an oversampled batch (read_operations.py:101-103,65): per draw the
  * barcode uniform, the picked length and the start; per visited blocked hit one uniform
@@ -183,6 +198,10 @@ int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t 
 int64_t esl_scan_read_lengths(const char *path, int32_t is_fastq, int64_t min_read_length, uint32_t *out,
                               int64_t capacity, double *mean_out);
 
+/* Host helper (no GPU): final start coordinates of n insertions placed one after the other, each pushing the earlier
+ * insertions at or after its position right by insertion_length (create_insertion_genome.py:60-64,76-80). */
+int esl_shift_insertions(const int64_t *positions, int64_t n, int64_t insertion_length, int64_t *starts);
+
 /* Host helper (no GPU): append the rows of one (iteration, combination) block of `{exp}_matches_table.csv`
  * (esloco.py:155-160,198-205) to `path` (append = 0 truncates first).  Row k is
  *   pre[k] iteration \t full \t partial \t overlap_field \t on_target_bases mid[k] iteration \n
@@ -194,11 +213,20 @@ int64_t esl_write_match_rows(const char *path, int32_t append, const char *pre_b
                              const char *mid_blob, const int64_t *mid_off, const char *overlap_field,
                              const int64_t *tallies, int64_t n_targets, const char *iteration);
 
+/* Host helper (no GPU): the same rows for n_iter iterations x n_combos combinations in ONE call -- one open file, one
+ * buffer sized to the text it will hold -- in the table's row order iteration -> combination -> target.
+ * mid_blobs / mid_offs / tallies are arrays of n_combos pointers; tallies[c] = host [n_iter][n_targets][3] int64;
+ * iteration_ids[i] is printed as the iteration column and key suffix of block i. */
+int64_t esl_write_match_rows_batch(const char *path, int32_t append, const char *pre_blob, const int64_t *pre_off,
+                                   int32_t n_combos, const char *const *mid_blobs, const int64_t *const *mid_offs,
+                                   const char *overlap_field, const int64_t *const *tallies, int64_t n_targets,
+                                   int64_t n_iter, const int64_t *iteration_ids);
+
 /* Host helper (no GPU): how the library would split one barcode's n targets into index layers over a genome of
  * size genome_size (a layer is scanned front to back, nesting is tolerated while it costs
  * reads at most a few wasted record loads).  layer_out[i] receives the layer of target i (-1 for an empty target,
  * end <= start, which is never indexed); returns the number of layers, or a negative esl_status.  For tests and for
- * sizing: the device index built by the first run after esl_set_targets uses exactly this split per barcode. */
+ * sizing: the device index esl_prepare builds uses exactly this split per barcode. */
 int32_t esl_plan_target_layers(uint64_t genome_size, const int64_t *start, const int64_t *end, int64_t n, int32_t *layer_out);
 
 /* Replay of the reference's pair thinning for scaling < 1 (counting.py:46,51: one rand() per qualifying pair, kept
@@ -217,7 +245,7 @@ int esl_get_timing(esl_ctx *ctx, float *bulk_ms, float *cutoff_ms);
 /* Introspection (for bench.py / DESIGN.md): number of kernel launches issued by this context so far. */
 int64_t esl_launch_count(const esl_ctx *ctx);
 /* Target index shape: total layers over all barcodes (1 per barcode unless targets nest deeply).  The index is
- * built by the first run after esl_set_targets / esl_set_genome, so query it after a run. */
+ * built by esl_prepare, so query it after that. */
 int32_t esl_target_layers(const esl_ctx *ctx);
 /* Reads per iteration the bulk kernel processes before the exact cut-off kernel takes over. */
 int64_t esl_bulk_reads(const esl_ctx *ctx, double coverage);

@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_loud_failure_without_gpu(lib):
-    assert lib.esl_abi_version() == 1
+    assert lib.esl_abi_version() == 2
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")

@@ -189,3 +189,59 @@ def test_native_row_writer_errors(tmp_path):
     w.path = str(tmp_path / "gone" / "w.csv")
     with pytest.raises(OSError):
         w.append([0], [np.zeros((1, 1, 3), np.int64)])
+
+
+def _seed_worker(rank, ws, port, ini, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    import numpy as np
+    import torch.distributed as dist
+    from esloco_b200.config_handler import parse_config
+    from esloco_b200.create_insertion_genome import add_insertions_to_genome_sequence_with_bed
+    from esloco_b200.distributed import sync_seed
+    p = parse_config(ini)  # no `seed` in the INI: every process draws its own (config_handler.py:53-57,102)
+    own = p["seed"]
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    common = sync_seed(p)
+    np.random.seed(p["seed"])  # what esloco.run does next (esloco.py:100): host set-up draws from this stream
+    sites = add_insertions_to_genome_sequence_with_bed(10_000_000, 500, 25, {"chr1": [0, 10_000_000]}, None, None)
+    q.put((rank, own, common, sorted((k, tuple(v)) for k, v in sites.items())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_seedless_ini_gets_one_seed(tmp_path):
+    """An INI without `seed` (the reference's config.ini default) under a 2-rank launch: both ranks must end up with
+    rank 0's seed and therefore build identical insertion sites -- otherwise rank 0 would sum moments of other ranks'
+    target sets under its own names."""
+    import torch.multiprocessing as mp
+    fa = tmp_path / "g.fa"
+    fa.write_text(">chr1\n" + "N" * 1000 + "\n")
+    ini = tmp_path / "c.ini"
+    ini.write_text(f"[COMMON]\nmode = I\nreference_genome_path = {fa}\noutput_path = {tmp_path}/out/\n[I]\ninsertion_numbers = 5\n")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seed_worker, args=(r, 2, port, str(ini), q)) for r in range(2)]
+    for p in procs: p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, own0, common0, sites0), (_, own1, common1, sites1) = got
+    assert own0 != own1  # 2 independent draws from [0, 2^32) -- the situation the broadcast is for
+    assert common0 == common1 == own0
+    assert sites0 == sites1 and len(sites0) == 25
+
+
+def test_target_columns_equal_dict_conversion():
+    from esloco_b200.utils import TargetColumns, targets_to_arrays
+    d = {f"Barcode_{i % 3}_insertion_{i}": [100 * i, 100 * i + 50] for i in range(30)}
+    d["odd_key"] = [5, 9]
+    keys, s, e, b = targets_to_arrays(d, 3)
+    tc = TargetColumns.from_dict(d, 3)
+    k2, s2, e2, b2 = targets_to_arrays(tc, 3)
+    assert k2 == keys and np.array_equal(s, s2) and np.array_equal(e, e2) and np.array_equal(b, b2)
+    assert b[-1] == -1 and len(tc) == 31
+    with pytest.raises(ValueError):
+        TargetColumns([1, 2], [3], [0, 0])
