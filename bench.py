@@ -1,17 +1,24 @@
 #!/usr/bin/env python3
 """Benchmark of the esloco hot path (read placement + target tally) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|chr]
 
 Metric (BASELINE.json): simulated reads placed per second (and iterations per second), hg38-size genome, 30x.
-Workload at N=1: BASELINE.json configs[1] -- I mode, synthetic hg38-size reference (3.1 Gb, 24 contigs),
-1 barcode, 30x, 100 random insertions of 5 kb, 100 iterations.  One STEP = one pass of the hot path over one
-batch = the config's 100 iterations in one esl_run_batch call (every rank runs its own 100 iterations: weak
-scaling over independent iterations; for N > 1 the per-target moment accumulators are combined by one NCCL
-reduce inside the step).
 
-Keys of the JSON line are described in DESIGN.md ("Measurement").  `--impl reference` times the CPU port of the
-reference's algorithm (oracle/, plain C, all host threads) on a bounded sample of the same workload.
+Headline line (N GPUs, WEAK scaling): BASELINE.json configs[1] -- I mode, synthetic hg38-size reference (3.1 Gb, 24
+contigs), 1 barcode, 30x, 100 random insertions of 5 kb, 100 iterations.  One STEP = `--batches-per-step` (16) passes of
+the hot path, each one esl_run_batch call over the config's 100 iterations with fresh iteration ids, every pass followed
+by the per-target moment kernel; a step is 16 passes rather than one so that the timed region lasts about a second
+(20 steps x 16 x 3.2 ms) instead of 64 ms.  Every rank runs its own iterations; for N > 1 the per-target moment
+accumulators are combined by ONE NCCL sum-reduce at the end of the step (`collective_ms`).
+
+`north_star_cfg3` block (same JSON line, STRONG scaling): BASELINE.json configs[2] -- 24 weighted barcodes, 10 k
+insertions per barcode (240 k targets), 1000 iterations IN TOTAL sharded over the N GPUs; one step = all 1000
+iterations, folded into moment accumulators chunk by chunk, one NCCL reduce.
+
+`--impl reference` times the CPU port of the reference's algorithm (oracle/, plain C, all host threads) on a bounded
+sample of the same workload; the unmodified Python reference itself is timed by the `cpu_baseline.python_reference`
+block of the default arm (baseline/pyref.py).  Keys of the JSON line are described in DESIGN.md ("Measurement").
 """
 import argparse
 import json
@@ -28,6 +35,8 @@ sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_READ = 96     # staged pipeline, u32 coordinates
 ALG_BYTES_PER_TARGET = 32   # per (target x iteration)
+METRIC = "simulated reads placed per second (hg38-size, 30x)"
+SM_COUNT, SCHEDULERS_PER_SM = 148, 4  # issue peak = 148 SMs x 4 warp schedulers x 1 warp instruction per cycle
 
 
 def make_workload(name):
@@ -65,6 +74,18 @@ def make_workload(name):
     return w
 
 
+def config_dict(w, world, batches_per_step):
+    """`config` of the JSON line -- the SAME dict in both arms (ours / reference), so the driver can see that they
+    measured one workload."""
+    return {"workload": w["desc"], "genome_size": w["genome_size"], "coverage": w["coverage"], "targets": len(w["targets"]),
+            "n_barcodes": w["n_barcodes"], "mean_read_length": w["mean_read_length"],
+            "step": f"{batches_per_step} pass(es) of the config's {w['iterations']} iterations per GPU (GPU arm); "
+                    "one iteration per host thread (CPU reference arm, a bounded sample of the same workload)",
+            "l2": "GPU arm: flushed between steps (256 MiB write) outside the per-step CUDA events; CPU arm: not applicable",
+            "parallelism": f"independent iterations sharded over {world} GPU(s) (weak scaling: every GPU runs the config's "
+                           "iterations), one NCCL sum-reduce of per-target moments per step when N > 1"}
+
+
 # ---------------------------------------------------------------------------------------------- clocks
 
 class ClockSampler:
@@ -93,27 +114,29 @@ class ClockSampler:
         while self.proc is not None and not self.rows and time.time() < t_end:
             time.sleep(0.01)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
+    def window(self, t0, t1):
         rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.06]
         if not rows and self.rows:  # region shorter than one sampling period: take the sample nearest to it
             rows = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[1]]
-        sm, smax, reasons = [], None, set()
+        sm, smax, power, reasons = [], None, [], set()
         for r in rows:
             try:
-                sm.append(float(r[1])); smax = float(r[2])
+                sm.append(float(r[1])); smax = float(r[2]); power.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
 
 
-# ---------------------------------------------------------------------------------------------- CPU baseline
+# ---------------------------------------------------------------------------------------------- CPU baselines
 
 def cpu_port_sample(w, n_threads, iters_per_thread=1, seed0=1000):
     """Reference algorithm on host cores: oracle.process_combination (numpy-legacy stream, 1 M log-normal pool,
@@ -144,8 +167,12 @@ def cpu_port_sample(w, n_threads, iters_per_thread=1, seed0=1000):
     return sum(reads), n_threads * iters_per_thread, dt
 
 
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def host_threads(w):
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = host_cores()
     per_iter_gb = 1.5 + 40e-9 * w["coverage"] * w["genome_size"] / w["mean_read_length"] * 10  # 10x resample + read arrays
     try:
         avail_gb = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) / 1e6
@@ -153,6 +180,17 @@ def host_threads(w):
     except Exception:
         pass
     return n
+
+
+def python_reference_block(w, reads_per_iteration):
+    """The unmodified Python reference under joblib on all host cores (baseline/pyref.py): measured at the config-2
+    shape on a 100 Mb genome, extrapolated to this workload's size with the fitted per-read / per-pair costs."""
+    try:
+        from baseline import pyref
+        return pyref.time_python_reference(host_cores(), reads_per_iteration, len(w["targets"]),
+                                           mean_read_length=w["mean_read_length"])
+    except Exception as e:  # a reported baseline must never take the GPU numbers down with it
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def run_reference_arm(args, w):
@@ -172,11 +210,12 @@ def run_reference_arm(args, w):
             break
     val = tot_reads / tot_t
     sample = f"{n_thr} iterations per step (one per thread) of the same workload, {done} of {args.steps} step(s) run (time-bounded)"
-    line = {"impl": "reference", "metric": "simulated reads placed per second (hg38-size, 30x)", "value": val,
+    line = {"impl": "reference", "metric": METRIC, "value": val,
             "unit": "reads/s", "iterations_per_s": tot_it / tot_t, "n_gpus": args.gpus, "steps": done,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, done), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": w["desc"], "impl": "CPU port of the reference algorithm (oracle/esloco_oracle.c), numpy-legacy MT19937 stream"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32" if w["genome_size"] <= 0xFFFFFFF0 else "u64", "data": "synthetic",
+            "config": config_dict(w, args.gpus, args.batches_per_step),
+            "reference_impl": "CPU port of the reference algorithm (oracle/esloco_oracle.c), numpy-legacy MT19937 stream, pinned by the reference's golden outputs",
             "cpu_baseline": {"value": val, "unit": "reads/s", "cores": n_thr, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -184,107 +223,156 @@ def run_reference_arm(args, w):
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 
-def run_ours(args, w):
+def load_ncu_facts(name):
+    """Static per-read facts of the dominant kernel from the committed ncu capture of the final build
+    (profiles/traffic.json, written by profiles/analyze.py): DRAM bytes per launch and warp instructions per read."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return {}
+    return json.load(open(tp)).get("workloads", {}).get(name, {})
+
+
+def measure(args, w, steps, warmup, batches, strong_total=None, e2e_mode="tallies"):
+    """Device-timed throughput + end-to-end throughput of one workload on this rank's GPU; rank 0 returns the result
+    dict.  strong_total: total iterations sharded over the ranks (one pass per step); else every rank runs
+    `batches` passes of w['iterations'] iterations per step (weak scaling)."""
     import torch
     import torch.distributed as dist
-    from esloco_b200.combined_calculations import run_simulation_batch
+    from esloco_b200.combined_calculations import TALLY_BUDGET_BYTES, run_simulation_batch
+    from esloco_b200.distributed import shard_iterations
+    from esloco_b200.engine import BatchResult
     from esloco_b200.session import get_session
-    from esloco_b200.utils import build_mask_tree
+    from esloco_b200.utils import TargetColumns, build_mask_tree
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     sess = get_session(local)
     eng = sess.engine
-    n_iter = w["iterations"]
-    params = dict(n_barcodes=w["n_barcodes"], barcode_weights=w["barcode_weights"], seed=w["seed"], scaling=w["scaling"],
+    B = w["n_barcodes"]
+    params = dict(n_barcodes=B, barcode_weights=w["barcode_weights"], seed=w["seed"], scaling=w["scaling"],
                   combinations=[(w["mean_read_length"], w["coverage"])], sequenced_data_path=None, sigma=w["sigma"],
                   min_read_length=w["min_read_length"], consuming=w["consuming"], min_overlap_for_detection=w["min_overlap"])
     masked_tree = build_mask_tree(w["mask"]) if w["mask"] else None
     # host inputs of the end-to-end leg live in pinned memory (the set-up calls copy straight from them)
-    pool_pinned = torch.from_numpy(w["pool"].astype(np.uint32)).pin_memory()
-    pool = pool_pinned.numpy()
-    sess.configure(w["genome_size"], w["targets"], masked_tree, w["n_barcodes"], w["barcode_weights"])
-    sess.set_pool(("bench", 0), lambda: pool)
+    pool = torch.from_numpy(w["pool"].astype(np.uint32)).pin_memory().numpy()
+    # large target sets are handed over as columns (arrays), small ones as the reference's dict
+    targets = TargetColumns.from_dict(w["targets"], B) if len(w["targets"]) > 10000 else w["targets"]
+    sess.invalidate()
+    sess.configure(w["genome_size"], targets, masked_tree, B, w["barcode_weights"])
+    sess.set_pool(None, lambda: pool)
     T = eng.n_targets
-    out = eng.alloc_outputs(n_iter)
+    if strong_total is None:
+        my_iters, passes = w["iterations"], batches
+        chunk = my_iters
+    else:
+        my_iters = len(shard_iterations(strong_total, rank, world))
+        chunk = max(1, min(my_iters, TALLY_BUDGET_BYTES // max(1, T * 24)))
+        passes = -(-my_iters // chunk)
+    iters_per_step = my_iters * (batches if strong_total is None else 1)
+    buf = eng.alloc_outputs(chunk)
+    n_reads_all = torch.zeros((passes, chunk), dtype=torch.int64, device=dev)
+    status_all = torch.zeros((passes, chunk), dtype=torch.int32, device=dev)
     acc = torch.zeros((T, 8), dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    coll_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
     def step(k):
-        # rank r owns iterations [r*n_iter + k*world*n_iter ...): disjoint iteration ids across ranks and steps
-        it0 = (k * world + rank) * n_iter
-        if args.path == "staged":
-            eng.run_batch_staged(w["seed"], 0, it0, n_iter, w["coverage"], w["consuming"], w["min_overlap"], out=out)
-        else:
-            eng.run_batch(w["seed"], 0, it0, n_iter, w["coverage"], w["consuming"], w["min_overlap"], w["scaling"], out=out)
-        if world > 1:
-            acc.zero_()
+        # disjoint iteration ids across ranks, passes and steps
+        base = (k * world + rank) * iters_per_step if strong_total is None else k * strong_total + shard_iterations(strong_total, rank, world).start
+        acc.zero_()
+        done = 0
+        for b in range(passes):
+            n = min(chunk, iters_per_step - done)
+            out = BatchResult(buf.tallies[:n], buf.label_counts[:n], buf.n_bases[:n], n_reads_all[b, :n], status_all[b, :n])
+            if args.path == "staged":
+                eng.run_batch_staged(w["seed"], 0, base + done, n, w["coverage"], w["consuming"], w["min_overlap"], out=out)
+            else:
+                eng.run_batch(w["seed"], 0, base + done, n, w["coverage"], w["consuming"], w["min_overlap"], w["scaling"], out=out)
             eng.moments(out.tallies, acc)
+            done += n
+        if world > 1:
+            coll_ev[0].record()
             dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+            coll_ev[1].record()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         sampler.wait_first_sample()  # before the warm-up, so the GPU does not idle between warm-up and timing
-    for k in range(args.warmup):
+    for k in range(warmup):
         step(k)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     eng.set_profiling(True)
     launches0 = eng.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    bulk_ms = cut_ms = 0.0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    bulk_ms = cut_ms = coll_ms = 0.0
     reads = 0
     t_wall0 = time.time()
     torch.cuda.synchronize()
-    for k in range(args.steps):
+    for k in range(steps):
         flush.fill_(k & 0xFF)  # L2 flush between timed steps, outside the step's events
         ev[k][0].record()
-        step(args.warmup + k)
+        step(warmup + k)
         ev[k][1].record()
-        b, c = eng.last_timing_ms()  # waits for the step
+        b, c = eng.last_timing_ms()  # the step's LAST pass (all passes launch the same work); waits for the step
         bulk_ms += b; cut_ms += c
-        reads += int(out.n_reads.sum().item())
-        assert not (out.status & 2).any().item()
+        if world > 1:
+            ev[k][1].synchronize()
+            coll_ms += coll_ev[0].elapsed_time(coll_ev[1])
+        reads += int(n_reads_all.sum().item())
+        assert not (status_all & 2).any().item()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
-    launches = eng.launch_count() - launches0 + (args.steps if world > 1 else 0)
+    launches = eng.launch_count() - launches0
     eng.set_profiling(False)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    stats = torch.tensor([dev_ms, float(reads)], dtype=torch.float64, device=dev)
+    clocks = sampler.window(t_wall0, t_wall1) if rank == 0 else None
+    stats = torch.tensor([dev_ms, float(reads), coll_ms], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, reads_all = mx[0].item(), sm[1].item()
+        dev_ms, reads_all, coll_ms = mx[0].item(), sm[1].item(), mx[2].item()
     else:
         reads_all = float(reads)
     value = reads_all / (dev_ms * 1e-3)
-    iters_all = n_iter * args.steps * world
+    iters_all = (strong_total if strong_total is not None else iters_per_step * world) * steps
 
     # ---- end to end through the public host API with HOST inputs: every step re-uploads targets / mask / length
-    # pool from host memory and reads all results back
-    h2d = int(T * (8 + 8 + 4) + pool.size * 4 + (len(w["mask"]) * 28 if w["mask"] else 0) + w["n_barcodes"] * 8)
-    d2h = int(n_iter * (T * 3 * 8 + (w["n_barcodes"] + 2) * 8 + 8 + 8 + 4))
+    # pool from host memory, rebuilds the device index, runs, reduces over the ranks and reads the results back
+    h2d = int(T * (8 + 8 + 4) + pool.size * 4 + (len(w["mask"]) * 28 if w["mask"] else 0) + B * 8)
+    small = iters_per_step * ((B + 2) * 8 + 8 + 8 + 4)
+    d2h = int(small + (T * 64 if e2e_mode == "moments" else iters_per_step * T * 24 + (T * 64 if world > 1 else 0)))
     e2e_reads = 0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         sess.invalidate()
-        its = range((10_000 + k * world + rank) * n_iter, (10_000 + k * world + rank) * n_iter + n_iter)
-        res, _ = run_simulation_batch(its, params, w["genome_size"], w["targets"], masked_tree, device=local, to_host=True,
-                                      length_pools={0: pool}, reuse_host_buffers=True)
-        e2e_reads += int(res[0].n_reads.sum())
+        first = (20_000 + k * world + rank) * iters_per_step
+        res, _ = run_simulation_batch(range(first, first + iters_per_step), params, w["genome_size"], targets, masked_tree,
+                                      device=local, to_host=False, length_pools={0: pool}, results=e2e_mode)
+        r = res[0]
+        mom = r.moments if e2e_mode == "moments" else (eng.moments(r.tallies) if world > 1 else None)
+        if world > 1:
+            dist.reduce(mom, dst=0, op=dist.ReduceOp.SUM)
+        fields = ["label_counts", "n_bases", "n_reads", "status"] + (["tallies"] if e2e_mode == "tallies" else [])
+        host = {}
+        for f in fields + (["moments"] if mom is not None and rank == 0 else []):
+            t = mom if f == "moments" else getattr(r, f)
+            key = ("bench", f, tuple(t.shape))
+            if key not in sess.pinned:
+                sess.pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            sess.pinned[key].copy_(t, non_blocking=True)
+            host[f] = sess.pinned[key]
+        torch.cuda.current_stream(dev).synchronize()
+        e2e_reads += int(host["n_reads"].sum())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e = torch.tensor([e2e_s, float(e2e_reads)], dtype=torch.float64, device=dev)
@@ -293,68 +381,107 @@ def run_ours(args, w):
         sm = e2e.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         e2e_s, e2e_reads = mx[0].item(), sm[1].item()
     e2e_val = e2e_reads / e2e_s
+    if rank != 0:
+        return None
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # Algorithmic bytes of what the bulk kernel processed in ONE launch (= one pass).  Single bulk pass: exactly n_bulk
+    # draws per iteration.  Masked + non-consuming runs add a second bulk pass whose per-iteration extent is decided on
+    # the device; there all placed reads of a pass are counted against both bulk passes AND the cut-off kernel's time.
+    two_pass = bool(w["mask"]) and not w["consuming"]
+    last_n = iters_per_step - (passes - 1) * chunk  # iterations of the step's last pass, the one that was timed
+    if two_pass or args.path == "staged":
+        reads_kernel = reads_all / world / steps / max(1, iters_per_step) * last_n
+        kernel_ms = (bulk_ms + cut_ms) / steps
+    else:
+        reads_kernel, kernel_ms = float(eng.bulk_reads(w["coverage"]) * last_n), bulk_ms / steps
+    alg_bytes = ALG_BYTES_PER_READ * reads_kernel + ALG_BYTES_PER_TARGET * T * last_n
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    facts = load_ncu_facts(w["name"]) if args.path == "fused" else {}
+    traffic = facts.get("dram_bytes_per_launch")
+    if traffic is not None and facts.get("reads_in_launch"):
+        traffic = traffic * reads_kernel / facts["reads_in_launch"]  # scaled to this launch's reads
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = SM_COUNT * SCHEDULERS_PER_SM * sm_mhz * 1e6  # warp instructions per second
+    issue = None
+    if facts.get("warp_inst_per_read"):
+        inst_s = facts["warp_inst_per_read"] * reads_kernel / (kernel_ms * 1e-3)
+        issue = {"warp_instructions_per_read": facts["warp_inst_per_read"], "thread_instructions_per_read": facts.get("thread_inst_per_read"),
+                 "achieved_gwarp_inst_per_s": inst_s / 1e9, "peak_gwarp_inst_per_s": issue_peak / 1e9, "sm_mhz": sm_mhz,
+                 "frac": inst_s / issue_peak,
+                 "source": f"instructions per read: ncu smsp__inst_executed.sum of this build ({facts.get('summary')}); reads, kernel time and SM clock: this run",
+                 "ncu_issue_active_pct": facts.get("issue_active_pct"), "ncu_fmaheavy_pct": facts.get("fmaheavy_pct")}
+    roofline = {"bound": "issue" if args.path == "fused" else "hbm",
+                "kernel": "k_place_tally_bulk" if args.path == "fused" else "staged pipeline (20 kernels per iteration)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_equivalent_gbs": achieved, "algorithmic_bytes_per_launch": alg_bytes,
+                "dram_gbs": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9,
+                "dram_frac": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9 / peak,
+                "issue_frac": None if issue is None else issue["frac"], "issue": issue,
+                "kernel_ms_per_launch": kernel_ms, "launches_per_step": passes * (2 if two_pass else 1),
+                "kernel_share_of_step": bulk_ms * passes / dev_ms if world == 1 and last_n == chunk else None,
+                "cutoff_kernel_ms_per_launch": cut_ms / steps,
+                "note": "achieved / frac follow the contract: ALGORITHMIC bytes of the staged design (96 B/read + 32 B/target/iteration, "
+                        "SURVEY 8d) / kernel time / measured HBM peak.  The fused kernel keeps reads in registers and moves `traffic` "
+                        "bytes of DRAM per launch (dram_frac of peak), so frac can exceed 1; what binds it is instruction issue: "
+                        "issue_frac = warp instructions / (148 SMs x 4 schedulers x SM clock x kernel time)."}
+    return {"value": value, "iterations_per_s": iters_all / (dev_ms * 1e-3), "ms_per_step": dev_ms / steps, "steps": steps, "warmup": warmup,
+            "timed_region_s": dev_ms * 1e-3, "targets": T, "iterations_per_step": strong_total if strong_total is not None else iters_per_step * world,
+            "iterations_per_step_per_gpu": iters_per_step, "passes_per_step": passes, "reads_per_iteration": reads_all / iters_all,
+            "roofline": roofline, "collective_ms": coll_ms / steps if world > 1 else 0.0,
+            "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / steps, "frac_of_value": e2e_val / value, "results": e2e_mode,
+                    "includes": "targets / mask / length-pool upload from pinned host memory, device index build, run, "
+                                + ("NCCL reduce of the moments, " if world > 1 else "") + "result copy to pinned host memory"},
+            "gpu_launches": int(launches), "clocks": clocks, "_sampler": sampler}
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    main = measure(args, w, args.steps, args.warmup, args.batches_per_step,
+                   e2e_mode="moments" if len(w["targets"]) > 10000 else "tallies")
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # Algorithmic bytes of what the bulk kernel processed in one step.  Single bulk pass: exactly n_bulk draws per
-        # iteration.  Masked + non-consuming runs add a second bulk pass whose per-iteration extent is decided on the
-        # device; there all placed reads are counted against the bulk passes AND the cut-off kernel's time.
-        two_pass = bool(w["mask"]) and not w["consuming"]
-        if two_pass or args.path == "staged":
-            reads_kernel, kernel_ms = reads_all / world / args.steps, (bulk_ms + cut_ms) / args.steps
-        else:
-            reads_kernel, kernel_ms = float(eng.bulk_reads(w["coverage"]) * n_iter), bulk_ms / args.steps
-        alg_bytes = ALG_BYTES_PER_READ * reads_kernel + ALG_BYTES_PER_TARGET * T * n_iter
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic, summary = None, None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp) and args.path == "fused":
-            tj = json.load(open(tp))
-            traffic = tj.get(w["name"])  # bytes per launch, from the committed ncu capture
-            summary = tj.get("summaries", {}).get(w["name"])
-        # what actually binds the fused kernel, from the committed ncu capture of this workload (not measured live)
-        binding = None
-        sp = os.path.join(ROOT, "profiles", summary or "none")
-        if os.path.exists(sp):
-            ps = json.load(open(sp))
-            binding = {"source": os.path.relpath(sp, ROOT), "warp_instructions_per_read": round(ps["warp_instructions_per_read"], 1),
-                       "issue_slots_busy_pct": float(ps["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
-                       "fmaheavy_pipe_pct": float(ps["sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"]),
-                       "dram_bytes_per_launch": sum(float(ps[k] or 0) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(ps["units"].get(k), 1)
-                                                    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))}
-        n_thr = host_threads(w)
-        if args.no_cpu_baseline or world > 1:  # the CPU baseline is reported at N = 1 only
-            cpu = None
-        else:
+        main.pop("_sampler").stop()
+    ns = None
+    if args.north_star and args.path == "fused":
+        w3 = make_workload("cfg3")
+        w3["desc"] = ("I mode, hg38-size, 24 barcodes (weights 0:10, 1:5), 30x, 10k insertions per barcode (240k targets), "
+                      "1000 iterations in total sharded over the GPUs")
+        ns = measure(args, w3, max(3, min(args.steps, 10)), 3, 1, strong_total=1000, e2e_mode="moments")
+        if rank == 0:
+            ns.pop("_sampler").stop()
+            ns.update(metric=METRIC, unit="reads/s", scaling="strong", n_gpus=world,
+                      config={"workload": w3["desc"], "l2": "flushed between steps", "results": "per-target moment accumulators "
+                              "(summary.csv) + per-iteration label counts / N_bases / reads placed; per-iteration tallies stay on the device"})
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:  # the CPU baselines are reported at N = 1 only
+            n_thr = host_threads(w)
             r, it, dt = cpu_port_sample(w, n_thr)
-            cpu = {"value": r / dt, "unit": "reads/s", "cores": n_thr, "kind": "port",
-                   "iterations_per_s": it / dt,
-                   "sample": f"{it} iterations (one per thread) of the same workload, C port of the reference algorithm"}
-        line = {"metric": "simulated reads placed per second (hg38-size, 30x)", "value": value, "unit": "reads/s",
-                "iterations_per_s": iters_all / (dev_ms * 1e-3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            cpu = {"value": r / dt, "unit": "reads/s", "cores": n_thr, "kind": "port", "iterations_per_s": it / dt,
+                   "sample": f"{it} iterations (one per thread) of the same workload, C port of the reference algorithm (oracle/)",
+                   "python_reference": python_reference_block(w, main["reads_per_iteration"])}
+        line = {"metric": METRIC, "value": main["value"], "unit": "reads/s", "iterations_per_s": main["iterations_per_s"],
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32" if w["genome_size"] <= 0xFFFFFFF0 else "u64", "data": "synthetic",
-                "config": {"workload": w["desc"], "path": args.path, "iterations_per_step_per_gpu": n_iter, "targets": T,
-                           "reads_per_iteration": reads_all / iters_all, "rng": "philox4x32-10",
-                           "l2": "flushed between steps (256 MiB write) outside the per-step CUDA events",
-                           "parallelism": f"iterations sharded over {world} GPU(s)" + (", one NCCL sum-reduce of per-target moments per step" if world > 1 else "")},
-                "roofline": {"bound": "hbm", "kernel": "k_place_tally_bulk" if args.path == "fused" else "staged pipeline (20 kernels per iteration)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": kernel_ms,
-                             "launches_per_step": 2 if two_pass else 1,
-                             "kernel_share_of_step": bulk_ms / dev_ms if world == 1 else None,
-                             "cutoff_kernel_ms_per_launch": cut_ms / args.steps,
-                             "note": "achieved = ALGORITHMIC bytes of the staged design (96 B/read + 32 B/target/iteration, SURVEY 8d) / kernel time; "
-                                     "the fused kernel keeps reads in registers, so its real DRAM traffic is `traffic` and frac may exceed 1",
-                             "binding_resource": binding},
-                "cpu_baseline": cpu,
-                "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "config": config_dict(w, world, args.batches_per_step),
+                "run": {"path": args.path, "rng": "philox4x32-10", "iterations_per_step_per_gpu": main["iterations_per_step_per_gpu"],
+                        "passes_per_step": main["passes_per_step"], "reads_per_iteration": main["reads_per_iteration"],
+                        "timed_region_s": main["timed_region_s"]},
+                "roofline": main["roofline"], "collective_ms": main["collective_ms"], "cpu_baseline": cpu, "e2e": main["e2e"],
+                "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "north_star_cfg3": ns}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -367,7 +494,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--batches-per-step", type=int, default=16,
+                    help="passes of the config's iterations per timed step (16 x 100 iterations ~ 51 ms per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-north-star", dest="north_star", action="store_false",
+                    help="skip the north_star_cfg3 block (config 3, 1000 iterations sharded over the GPUs)")
     ap.add_argument("--path", default="fused", choices=["fused", "staged"],
                     help="fused = the product kernels; staged = the north star's sort + sweep pipeline kept as a measured baseline")
     args = ap.parse_args()
@@ -377,6 +508,8 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3
+        if args.workload != "cfg2":
+            args.north_star = False
         run_ours(args, w)
 
 

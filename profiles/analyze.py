@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (read here, no GPU): key counters, opcode mix and stall reasons per read.
-usage: python profiles/analyze.py <report.ncu-rep> <reads in the profiled launch> [out.json]"""
+usage: python profiles/analyze.py <report.ncu-rep> <reads in the profiled launch> [out.json [workload]]
+With a workload name the facts bench.py reads live (DRAM bytes per launch, warp instructions per read) are also written
+to profiles/traffic.json under that name."""
 import collections
 import csv
 import io
@@ -43,10 +45,25 @@ for r in srows[2:]:
         except ValueError:
             pass
 wr = n_reads / 32
-out["warp_instructions_per_read"] = total / wr
+out["reads_in_launch"] = n_reads
+out["warp_instructions_per_read"] = total / n_reads  # warp-level instructions issued per read (a warp serves 32 reads)
+out["instructions_per_read"] = total / wr            # the same per thread: what one read costs in instructions
 out["opcode_mix_per_read"] = {k: round(v / wr, 2) for k, v in ops.most_common(24)}
 ts = sum(stalls.values()) or 1
 out["stall_pct"] = {k: round(100 * v / ts, 1) for k, v in stalls.most_common(8)}
 print(json.dumps(out, indent=1))
 if len(sys.argv) > 3:
     json.dump(out, open(sys.argv[3], "w"), indent=1)
+if len(sys.argv) > 4:
+    import os
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
+    tj = json.load(open(tp)) if os.path.exists(tp) else {}
+    tj.setdefault("workloads", {})[sys.argv[4]] = {
+        "summary": "profiles/" + os.path.basename(sys.argv[3]), "reads_in_launch": n_reads,
+        "dram_bytes_per_launch": sum(float(out[k] or 0) * scale.get(out["units"].get(k), 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")),
+        "warp_inst_per_read": float(out["smsp__inst_executed.sum"]) / n_reads, "thread_inst_per_read": out["instructions_per_read"],
+        "issue_active_pct": float(out["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+        "fmaheavy_pct": float(out["sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"]),
+        "kernel_ms_under_ncu": float(out["gpu__time_duration.sum"])}
+    json.dump(tj, open(tp, "w"), indent=1)
