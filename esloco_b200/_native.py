@@ -23,6 +23,7 @@ SYMBOLS = {
     "esl_set_targets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_blocked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_length_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "esl_pool_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
     "esl_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esl_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_double, C.c_int64]),
     "esl_run_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_double, C.c_int32,

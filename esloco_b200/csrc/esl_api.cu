@@ -1,9 +1,11 @@
 // C ABI of the engine (include/esloco_b200.h): context, host-side index construction, kernel launches.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -82,6 +84,7 @@ struct esl_ctx {
     DevBuf d_raw_ts, d_raw_te, d_raw_tb; // targets in caller order (staged baseline)
     DevBuf d_pool_stats;
     DevBuf d_sgrid;
+    struct esl_host_scratch *host = nullptr; // persistent host-side scratch of esl_prepare (defined below)
     int sgrid_n = 0, sgrid_shift = 0; // shared-memory copy of the first-layer grids (0 = does not fit)
     u64 sgrid_lmax = 0;               // longest read its upper bounds were built for
 
@@ -133,9 +136,9 @@ struct Rec { i64 s, e; int32_t row; };
 // (binary search), so pathological nesting stays O(n log n).
 constexpr int kDeadScan = 16;
 constexpr size_t kRelaxedLayers = 64;
-void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers, u64 G)
+void build_layers(Rec *first_rec, Rec *last_rec, std::vector<std::vector<Rec>> &layers, u64 G)
 {
-    std::sort(v.begin(), v.end(), [](const Rec &a, const Rec &b) {
+    std::sort(first_rec, last_rec, [](const Rec &a, const Rec &b) {
         if (a.s != b.s) return a.s < b.s;
         if (a.e != b.e) return a.e < b.e;
         return a.row < b.row;
@@ -148,7 +151,8 @@ void build_layers(std::vector<Rec> &v, std::vector<std::vector<Rec>> &layers, u6
     std::vector<Relaxed> relaxed;
     std::vector<i64> last; // last end of each strict layer (index kRelaxedLayers + k); decreasing under first-fit
     const long double budget = 0.25L * (long double)G;
-    for (const Rec &r : v) {
+    for (const Rec *it = first_rec; it != last_rec; ++it) {
+        const Rec &r = *it;
         bool placed = false;
         for (size_t l = 0; l < relaxed.size() && !placed; ++l) {
             Relaxed &o = relaxed[l];
@@ -191,21 +195,24 @@ template <typename C> C clampc(i64 v, u64 G) { return (C)((u64)v > G + 1 ? G + 1
 
 // Bucket grid over one sorted run: keys[lo..hi) ascending (the running max of the ends of a target layer or of a
 // group of blocked intervals), starts[lo..hi) the interval starts.  At least 8 buckets per interval, so a bucket
-// rarely holds more than one interval end; runs where some bucket holds more than
-// kCrowdedBucket ends are flagged so the device bisects inside the bucket.  Appends to `grid`.
-template <typename C>
-esl::SegDesc make_grid(const std::vector<C> &keys, const std::vector<C> &starts, int lo, int hi, u64 G,
-                       std::vector<esl::GridEntry<C>> &grid, int forced_shift = -1)
+// rarely holds more than one interval end; runs where some bucket holds more than kCrowdedBucket ends are flagged
+// so the device bisects inside the bucket.
+// Bucket width ~ min(G / (8 * intervals), 64 kb): fine enough that "first candidate starts before the read ends" is
+// rarely a false alarm even for sparse runs, yet at most 2^21 entries (16 MB) per run.
+inline int grid_shift(u64 n_intervals, u64 G)
 {
-    esl::SegDesc d;
-    d.lo = lo; d.hi = hi; d.grid_off = (int)grid.size();
-    // bucket width ~ min(G / (8 * intervals), 64 kb): fine enough that "first candidate starts before the read
-    // ends" is rarely a false alarm even for sparse runs, yet at most 2^21 entries (16 MB) per run
-    const u64 want = std::min<u64>(std::max<u64>(std::max<u64>(64, 8ull * (u64)(hi - lo)), (G >> 16) + 1), 1ull << 21);
+    const u64 want = std::min<u64>(std::max<u64>(std::max<u64>(64, 8ull * n_intervals), (G >> 16) + 1), 1ull << 21);
     int shift = 0;
     while (((G + 1) >> shift) + 2 > want) ++shift;
-    if (forced_shift >= 0) shift = forced_shift;
-    const u64 nb = ((G + 1) >> shift) + 2; // reads start below G: bucket index <= G >> shift; one more for the bound
+    return shift;
+}
+// reads start below G: bucket index <= G >> shift; one more entry for the upper bound of the last bucket
+inline u64 grid_buckets(int shift, u64 G) { return ((G + 1) >> shift) + 2; }
+
+// Writes the nb entries of one run's grid to out[]; returns 1 when some bucket is crowded.
+template <typename C>
+int fill_grid(const C *keys, const C *starts, int lo, int hi, int shift, u64 nb, esl::GridEntry<C> *out)
+{
     int j = lo, crowded = 0, prev = lo;
     for (u64 b = 0; b < nb; ++b) {
         const u64 edge = b << shift;
@@ -215,8 +222,22 @@ esl::SegDesc make_grid(const std::vector<C> &keys, const std::vector<C> &starts,
         esl::GridEntry<C> e{};
         e.j = j;
         e.s = j < hi ? starts[j] : (C) ~(C)0;
-        grid.push_back(e);
+        out[b] = e;
     }
+    return crowded;
+}
+
+// Vector form: appends the run's grid to `grid`.
+template <typename C>
+esl::SegDesc make_grid(const C *keys, const C *starts, int lo, int hi, u64 G, std::vector<esl::GridEntry<C>> &grid,
+                       int forced_shift = -1)
+{
+    esl::SegDesc d;
+    d.lo = lo; d.hi = hi; d.grid_off = (int)grid.size();
+    const int shift = forced_shift >= 0 ? forced_shift : grid_shift((u64)(hi - lo), G);
+    const u64 nb = grid_buckets(shift, G);
+    grid.resize(grid.size() + nb);
+    const int crowded = fill_grid<C>(keys, starts, lo, hi, shift, nb, grid.data() + d.grid_off);
     d.flags = shift | (crowded << 8);
     return d;
 }
@@ -232,108 +253,185 @@ esl::SegDesc empty_run(std::vector<esl::GridEntry<C>> &grid)
     return d;
 }
 
-// Index of ONE barcode's targets, built independently of the others (indices local to the barcode).
-template <typename C>
-struct BarcodeIndex {
-    std::vector<C> ts, te, tp; // starts, ends, running max of the ends inside each layer (grid / bisection keys)
-    std::vector<int32_t> trow;
-    std::vector<esl::GridEntry<C>> grid;
-    std::vector<esl::SegDesc> layers; // lo / hi / grid_off local to this barcode
-    bool too_deep = false;
+// ESL_TIMING=1 prints where esl_prepare's host time goes (stderr); off by default.
+struct PhaseTimer {
+    bool on = getenv("ESL_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[esl_prepare] %-40s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
 };
 
-template <typename C>
-void build_barcode_index(std::vector<Rec> &v, u64 G, BarcodeIndex<C> &o)
-{
-    std::vector<std::vector<Rec>> layers;
-    build_layers(v, layers, G);
-    if (layers.size() > 0xFFFF) { o.too_deep = true; return; }
-    o.ts.reserve(v.size()); o.te.reserve(v.size()); o.tp.reserve(v.size()); o.trow.reserve(v.size());
-    for (size_t l = 0; l < layers.size(); ++l) {
-        const int lo = (int)o.ts.size();
-        C run = 0;
-        for (const Rec &r : layers[l]) {
-            o.ts.push_back(clampc<C>(r.s, G)); o.te.push_back(clampc<C>(r.e, G)); o.trow.push_back(r.row);
-            run = std::max(run, o.te.back());
-            o.tp.push_back(run);
-        }
-        o.layers.push_back(make_grid<C>(o.tp, o.ts, lo, (int)o.ts.size(), G, o.grid));
+// Page-locked host staging buffer kept between esl_prepare calls: the index arrays are written straight into it by
+// the builder threads and copied from there (fresh pageable vectors cost more in first-touch page faults and staged
+// copies than the index build itself: 30 MB per call at 240 k targets).
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        const size_t want = n + n / 4 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
     }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+} // namespace
+
+struct esl_host_scratch {
+    std::vector<Rec> recs;               // targets bucketed by barcode
+    PinnedBuf trec, tp, tgrid, ts, te;   // index arrays in their final order (ts / te: host-only helpers)
+    cudaEvent_t uploaded = nullptr;      // the last esl_prepare's copies out of the pinned buffers
+    ~esl_host_scratch() { if (uploaded) cudaEventDestroy(uploaded); }
+};
+
+namespace {
+
+template <typename F>
+void parallel_for(int n, int n_thr, F f)
+{
+    std::atomic<int> next{0};
+    auto work = [&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i); };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_thr; ++t) pool.emplace_back(work);
+    work();
+    for (std::thread &t : pool) t.join();
 }
+
+struct LayerPlan { int barcode, lo, hi, grid_off, shift; u64 nb; const std::vector<Rec> *recs; };
 
 template <typename C>
 int upload_index(esl_ctx *ctx, cudaStream_t st)
 {
     const int B = ctx->B;
     const u64 G = ctx->G;
+    PhaseTimer tm;
+    esl_host_scratch &hs = *ctx->host;
+    if (!hs.uploaded) CU(cudaEventCreateWithFlags(&hs.uploaded, cudaEventDisableTiming));
+    CU(cudaEventSynchronize(hs.uploaded)); // an earlier prepare may still be copying out of the pinned buffers
     // targets: seg[b] = first layer of barcode b, extra layers appended behind the B first-layer descriptors.
-    // One counting pass buckets the targets by barcode; the barcodes are then indexed independently on a few host
-    // threads (config 3: 24 barcodes x 10 k targets) and concatenated.
-    std::vector<std::vector<Rec>> per_bc(B);
+    // (1) one counting pass buckets the targets by barcode; (2) the barcodes are sorted and split into layers
+    // independently on a few host threads (config 3: 24 barcodes x 10 k targets); (3) the layout of the final arrays
+    // follows from the layer sizes; (4) the threads write records and grids straight to their final places.
+    const size_t n_all = ctx->t_start.size();
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n_thr = (int)std::min<size_t>({(size_t)hw, (size_t)8, n_all / 4096 + 1});
+    std::vector<size_t> off(B + 1, 0);
     {
-        std::vector<size_t> cnt(B, 0);
-        const size_t n = ctx->t_start.size();
-        for (size_t i = 0; i < n; ++i) {
-            const int32_t b = ctx->t_bc[i];
-            if (b >= 0 && b < B && ctx->t_end[i] > ctx->t_start[i]) ++cnt[b];
+        // slice s of the targets counts its valid targets per barcode, the counts become write positions (barcode-major,
+        // slices in order, so the caller's order survives inside a barcode), then every slice scatters its own targets
+        const int n_sl = n_thr;
+        const size_t per = (n_all + n_sl - 1) / std::max(n_sl, 1);
+        std::vector<size_t> cnt((size_t)n_sl * B, 0);
+        auto valid = [&](size_t i) { const int32_t b = ctx->t_bc[i]; return b >= 0 && b < B && ctx->t_end[i] > ctx->t_start[i]; };
+        parallel_for(n_sl, n_thr, [&](int sl) {
+            size_t *c = cnt.data() + (size_t)sl * B;
+            for (size_t i = sl * per, e = std::min(n_all, (sl + 1) * per); i < e; ++i)
+                if (valid(i)) ++c[ctx->t_bc[i]];
+        });
+        size_t run = 0;
+        for (int b = 0; b < B; ++b) {
+            off[b] = run;
+            for (int sl = 0; sl < n_sl; ++sl) { const size_t c = cnt[(size_t)sl * B + b]; cnt[(size_t)sl * B + b] = run; run += c; }
         }
-        for (int b = 0; b < B; ++b) per_bc[b].reserve(cnt[b]);
-        for (size_t i = 0; i < n; ++i) {
-            const int32_t b = ctx->t_bc[i];
-            if (b >= 0 && b < B && ctx->t_end[i] > ctx->t_start[i]) per_bc[b].push_back(Rec{ctx->t_start[i], ctx->t_end[i], (int32_t)i});
-        }
+        off[B] = run;
+        hs.recs.resize(run);
+        parallel_for(n_sl, n_thr, [&](int sl) {
+            size_t *at = cnt.data() + (size_t)sl * B;
+            for (size_t i = sl * per, e = std::min(n_all, (sl + 1) * per); i < e; ++i)
+                if (valid(i)) hs.recs[at[ctx->t_bc[i]]++] = Rec{ctx->t_start[i], ctx->t_end[i], (int32_t)i};
+        });
     }
-    std::vector<BarcodeIndex<C>> bi(B);
-    {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const int n_thr = (int)std::min<size_t>({(size_t)hw, (size_t)8, (size_t)B, ctx->t_start.size() / 4096 + 1});
-        std::atomic<int> next{0};
-        auto work = [&]() {
-            for (int b = next.fetch_add(1); b < B; b = next.fetch_add(1)) build_barcode_index<C>(per_bc[b], G, bi[b]);
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < n_thr; ++t) pool.emplace_back(work);
-        work();
-        for (std::thread &t : pool) t.join();
-    }
-    std::vector<C> ts, te, tp;
-    std::vector<int32_t> trow, extra_off(B, 0);
-    std::vector<esl::GridEntry<C>> tgrid;
-    std::vector<esl::SegDesc> first(B), extra;
-    {
-        size_t n_rec = 0, n_grid = 0;
-        for (int b = 0; b < B; ++b) { n_rec += bi[b].ts.size(); n_grid += bi[b].grid.size() + 2; }
-        ts.reserve(n_rec); te.reserve(n_rec); tp.reserve(n_rec); trow.reserve(n_rec); tgrid.reserve(n_grid);
-    }
+    tm.mark("bucket by barcode");
+    std::vector<std::vector<std::vector<Rec>>> layers(B);
+    parallel_for(B, n_thr, [&](int b) { build_layers(hs.recs.data() + off[b], hs.recs.data() + off[b + 1], layers[b], G); });
+    tm.mark("sort + layers per barcode (threads)");
+    std::vector<LayerPlan> plan;
+    std::vector<int32_t> extra_off(B, 0);
+    std::vector<int> first_plan(B, -1);
+    size_t n_rec = 0, n_grid = 0, n_extra = 0;
     ctx->n_layers = 0;
     ctx->n_first_layers = 0;
     for (int b = 0; b < B; ++b) {
-        BarcodeIndex<C> &o = bi[b];
-        if (o.too_deep) return ctx->fail(ESL_ERR_UNSUPPORTED, "barcode %d needs more than 65535 nesting layers", b);
-        const int rec0 = (int)ts.size(), grid0 = (int)tgrid.size();
-        ts.insert(ts.end(), o.ts.begin(), o.ts.end());
-        te.insert(te.end(), o.te.begin(), o.te.end());
-        tp.insert(tp.end(), o.tp.begin(), o.tp.end());
-        trow.insert(trow.end(), o.trow.begin(), o.trow.end());
-        for (esl::GridEntry<C> e : o.grid) { e.j += rec0; tgrid.push_back(e); }
-        extra_off[b] = (int32_t)extra.size();
-        for (size_t l = 0; l < o.layers.size(); ++l) {
-            esl::SegDesc d = o.layers[l];
-            d.lo += rec0; d.hi += rec0; d.grid_off += grid0;
-            if (l == 0) { d.flags |= (int)((o.layers.size() - 1) << 16); first[b] = d; }
+        if (layers[b].size() > 0xFFFF) return ctx->fail(ESL_ERR_UNSUPPORTED, "barcode %d needs %zu nesting layers (max 65535)", b, layers[b].size());
+        extra_off[b] = (int32_t)n_extra;
+        for (size_t l = 0; l < layers[b].size(); ++l) {
+            const size_t n = layers[b][l].size();
+            const int shift = grid_shift(n, G);
+            const u64 nb = grid_buckets(shift, G);
+            if (l == 0) first_plan[b] = (int)plan.size(); else ++n_extra;
+            plan.push_back(LayerPlan{b, (int)n_rec, (int)(n_rec + n), (int)n_grid, shift, nb, &layers[b][l]});
+            n_rec += n; n_grid += nb;
+        }
+        if (layers[b].empty()) n_grid += 2; // two entries that reject every read (placed below)
+        ctx->n_layers += (int)layers[b].size();
+        ctx->n_first_layers += layers[b].empty() ? 0 : 1;
+    }
+    if (n_rec > 0x7fffffffull || n_grid > 0x7fffffffull) return ctx->fail(ESL_ERR_UNSUPPORTED, "target index too large");
+    if ((size_t)B + n_extra >= ((size_t)1 << esl::kQueueSegBits)) return ctx->fail(ESL_ERR_UNSUPPORTED, "too many target layers (barcodes + nesting levels must stay below 2^22)");
+    CU(hs.trec.reserve(std::max<size_t>(n_rec, 1) * sizeof(esl::TargetRec<C>)));
+    CU(hs.tp.reserve(std::max<size_t>(n_rec, 1) * sizeof(C)));
+    CU(hs.ts.reserve(std::max<size_t>(n_rec, 1) * sizeof(C)));
+    CU(hs.te.reserve(std::max<size_t>(n_rec, 1) * sizeof(C)));
+    CU(hs.tgrid.reserve(std::max<size_t>(n_grid, 1) * sizeof(esl::GridEntry<C>)));
+    esl::TargetRec<C> *trec = hs.trec.as<esl::TargetRec<C>>();
+    C *tp = hs.tp.as<C>(), *ts = hs.ts.as<C>(), *te = hs.te.as<C>(); // tp: running max of te inside each layer = grid / bisection keys
+    esl::GridEntry<C> *tgrid = hs.tgrid.as<esl::GridEntry<C>>();
+    std::vector<int> crowded(plan.size(), 0);
+    parallel_for((int)plan.size(), n_thr, [&](int i) {
+        const LayerPlan &pl = plan[i];
+        C run = 0;
+        int k = pl.lo;
+        for (const Rec &r : *pl.recs) {
+            ts[k] = clampc<C>(r.s, G); te[k] = clampc<C>(r.e, G);
+            run = std::max(run, te[k]);
+            tp[k] = run;
+            ++k;
+        }
+        k = pl.lo;
+        for (const Rec &r : *pl.recs) {
+            esl::TargetRec<C> t{};
+            t.s = ts[k]; t.e = te[k]; t.row = r.row;
+            t.s_next = k + 1 < pl.hi ? ts[k + 1] : (C) ~(C)0;
+            trec[k++] = t;
+        }
+        crowded[i] = fill_grid<C>(tp, ts, pl.lo, pl.hi, pl.shift, pl.nb, tgrid + pl.grid_off);
+    });
+    std::vector<esl::SegDesc> first(B), extra;
+    {
+        size_t empty_at = n_grid; // the empty runs' entries sit behind all real grids
+        for (int b = 0; b < B; ++b)
+            if (layers[b].empty()) {
+                empty_at -= 2;
+                esl::GridEntry<C> e{};
+                e.j = 0; e.s = (C) ~(C)0;
+                tgrid[empty_at] = e; tgrid[empty_at + 1] = e;
+                first[b] = esl::SegDesc{0, 0, (int)empty_at, 63}; // any position maps to bucket 0 (shift 63)
+            }
+        for (size_t i = 0; i < plan.size(); ++i) {
+            const LayerPlan &pl = plan[i];
+            esl::SegDesc d{pl.lo, pl.hi, pl.grid_off, pl.shift | (crowded[i] << 8)};
+            if ((int)i == first_plan[pl.barcode]) { d.flags |= (int)((layers[pl.barcode].size() - 1) << 16); first[pl.barcode] = d; }
             else extra.push_back(d);
         }
-        if (o.layers.empty()) first[b] = empty_run<C>(tgrid);
-        ctx->n_layers += (int)o.layers.size();
-        ctx->n_first_layers += o.layers.empty() ? 0 : 1;
-        o = BarcodeIndex<C>();
     }
+    tm.mark("records + grids in place (threads)");
     // Shared-memory pre-filter for small target sets (typical esloco runs: a handful of ROIs / insertions per
     // barcode): per first layer a coarser grid, all barcodes at one common bucket width, holding per bucket the
     // pair {start of the bucket's first candidate, largest end among the targets a read STARTING in the bucket can
     // reach}.  A read [rs, re) can only overlap something if first < re and rs < that end; the second test needs
     // the longest read, so it only serves draws from the length pool (rounded up to a power of two: a longer pool
-    // rebuilds the index, ensure_index).  Used if it fits ~36 KB with at least four buckets per target.
+    // makes the index stale, index_stale).  Used if it fits ~36 KB with at least four buckets per target.
     ctx->sgrid_n = 0;
     ctx->sgrid_lmax = 1;
     while (ctx->sgrid_lmax < (u64)ctx->pool_max) ctx->sgrid_lmax <<= 1;
@@ -367,44 +465,46 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
             ctx->sgrid_shift = sshift;
         }
     }
+    tm.mark("shared pre-filter grid");
     std::vector<esl::SegDesc> seg(first);
     seg.insert(seg.end(), extra.begin(), extra.end());
-    ctx->n_indexed = (i64)ts.size();
-    std::vector<esl::TargetRec<C>> trec(ts.size());
+    ctx->n_indexed = (i64)n_rec;
     // hot targets: a read overlaps them with probability >= 1/512 (whole-chromosome ROIs and the like); the
     // kHotSlots hottest get a private shared-memory tally per CTA (their record carries the slot, hot_row[] the row)
     std::vector<int32_t> hot_row;
     {
-        std::vector<std::pair<long double, int>> hot; // (-p_hit, record index): sorts hottest first, ties by position
-        for (const esl::SegDesc &d : seg)
-            for (int k = d.lo; k < d.hi; ++k) {
-                const long double p_hit = ((long double)(te[k] - ts[k]) + ctx->pool_mean) / (long double)G;
-                if (p_hit >= 1.0L / 512) hot.emplace_back(-p_hit, k);
-            }
+        // p_hit = (target length + mean read length) / G >= 1/512, compared without a division per target
+        std::vector<std::pair<double, int>> hot; // (-(length + mean read length), record index): hottest first, ties by position
+        const double hot_len = (double)G / 512.0 - ctx->pool_mean;
+        for (size_t k = 0; k < n_rec; ++k) {
+            const double len = (double)(te[k] - ts[k]);
+            if (len >= hot_len) hot.emplace_back(-(len + ctx->pool_mean), (int)k);
+        }
         std::sort(hot.begin(), hot.end());
         if (hot.size() > (size_t)esl::kHotSlots) hot.resize(esl::kHotSlots);
-        std::vector<int> slot_of(ts.size(), -1);
-        for (size_t h = 0; h < hot.size(); ++h) { slot_of[hot[h].second] = (int)h; hot_row.push_back(trow[hot[h].second]); }
-        for (const esl::SegDesc &d : seg)
-            for (int k = d.lo; k < d.hi; ++k) {
-                esl::TargetRec<C> r{};
-                r.s = ts[k]; r.e = te[k];
-                r.row = slot_of[k] >= 0 ? (int)(0x80000000u | (uint32_t)slot_of[k]) : trow[k];
-                r.s_next = k + 1 < d.hi ? ts[k + 1] : (C) ~(C)0;
-                trec[k] = r;
-            }
+        for (size_t h = 0; h < hot.size(); ++h) {
+            hot_row.push_back(trec[hot[h].second].row);
+            trec[hot[h].second].row = (int)(0x80000000u | (uint32_t)h);
+        }
     }
-    CU(ctx->d_trec.upload(trec.data(), trec.size() * sizeof(esl::TargetRec<C>), st));
+    tm.mark("hot targets");
+    auto copy_pinned = [&](DevBuf &d, const void *src, size_t n) -> cudaError_t {
+        cudaError_t e = d.reserve(std::max<size_t>(n, 1));
+        if (e != cudaSuccess || n == 0) return e;
+        return cudaMemcpyAsync(d.p, src, n, cudaMemcpyHostToDevice, st);
+    };
+    CU(copy_pinned(ctx->d_trec, trec, n_rec * sizeof(esl::TargetRec<C>)));
+    CU(copy_pinned(ctx->d_te, tp, n_rec * sizeof(C))); // bisection keys of crowded buckets
+    CU(copy_pinned(ctx->d_tgrid, tgrid, n_grid * sizeof(esl::GridEntry<C>)));
+    CU(cudaEventRecord(hs.uploaded, st));
     ctx->n_hot = (int)hot_row.size();
     hot_row.resize(esl::kHotSlots, 0);
     CU(ctx->d_hot_row.upload(hot_row.data(), hot_row.size() * sizeof(int32_t), st));
-    CU(ctx->d_te.upload(tp.data(), tp.size() * sizeof(C), st)); // bisection keys of crowded buckets
-    if (seg.size() >= ((size_t)1 << esl::kQueueSegBits)) return ctx->fail(ESL_ERR_UNSUPPORTED, "too many target layers (barcodes + nesting levels must stay below 2^22)");
-    ctx->n_seg = (int)seg.size(); ctx->n_tgrid = (int)tgrid.size(); ctx->n_trec = (int)trec.size();
+    ctx->n_seg = (int)seg.size(); ctx->n_tgrid = (int)n_grid; ctx->n_trec = (int)n_rec;
     ctx->raw_dirty = true; // targets in caller order: uploaded by the staged baseline only, on its first call
     CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc), st));
-    CU(ctx->d_tgrid.upload(tgrid.data(), tgrid.size() * sizeof(esl::GridEntry<C>), st));
     CU(ctx->d_extra_off.upload(extra_off.data(), extra_off.size() * sizeof(int32_t), st));
+    tm.mark("target uploads");
     // blocked intervals: group g < B = barcode g, group B = "ALL"; (start, end) order, running max of ends
     std::vector<C> ms, me, mp;
     std::vector<double> mw;
@@ -427,7 +527,7 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
             ms.push_back(s); me.push_back(e); mp.push_back(run); mw.push_back(ctx->m_w[i]);
         }
         if ((int)ms.size() == glo) grp.push_back(empty_run<C>(mgrid));
-        else grp.push_back(make_grid<C>(mp, ms, glo, (int)ms.size(), G, mgrid));
+        else grp.push_back(make_grid<C>(mp.data(), ms.data(), glo, (int)ms.size(), G, mgrid));
     }
     ctx->n_mask = (i64)ms.size();
     std::vector<esl::MaskRec<C>> mrec(ms.size());
@@ -458,6 +558,7 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
     CU(ctx->d_cdf.upload(ctx->cdf.data(), B * sizeof(double), st));
     CU(ctx->d_cdf_u32.upload(cu.data(), B * sizeof(uint32_t), st));
     CU(ctx->d_cdf_lut.upload(lut.data(), lut.size() * sizeof(uint16_t), st));
+    tm.mark("blocked groups + cdf");
     return ESL_OK;
 }
 
@@ -695,6 +796,7 @@ int esl_create(esl_ctx **out, int device)
     }
     if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return ESL_ERR_CUDA; }
     esl_ctx *c = new esl_ctx();
+    c->host = new esl_host_scratch();
     c->device = device;
     c->sm_count = p.multiProcessorCount;
     *out = c;
@@ -706,6 +808,7 @@ int esl_destroy(esl_ctx *ctx)
     if (!ctx) return ESL_ERR_INVALID;
     cudaSetDevice(ctx->device);
     for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
+    delete ctx->host;
     delete ctx;
     return ESL_OK;
 }
@@ -809,6 +912,15 @@ int esl_prepare(esl_ctx *ctx, void *stream)
     return ESL_OK;
 }
 
+int esl_pool_stats(const esl_ctx *ctx, double *mean, double *sd, uint32_t *longest)
+{
+    if (!ctx || !ctx->have_pool) return ESL_ERR_STATE;
+    if (mean) *mean = ctx->pool_mean;
+    if (sd) *sd = ctx->pool_sd;
+    if (longest) *longest = ctx->pool_max;
+    return ESL_OK;
+}
+
 int64_t esl_bulk_reads(const esl_ctx *ctx, double coverage) { return ctx ? bulk_reads(ctx, coverage) : 0; }
 
 int64_t esl_workspace_bytes(const esl_ctx *ctx, int32_t n_iter, double coverage, int64_t max_draws_per_iter)
@@ -863,7 +975,7 @@ int32_t esl_plan_target_layers(uint64_t genome_size, const int64_t *start, const
         if (end[i] > start[i]) v.push_back(Rec{start[i], end[i], (int32_t)i});
     }
     std::vector<std::vector<Rec>> layers;
-    build_layers(v, layers, genome_size);
+    build_layers(v.data(), v.data() + v.size(), layers, genome_size);
     for (size_t l = 0; l < layers.size(); ++l)
         for (const Rec &r : layers[l]) layer_out[r.row] = (int32_t)l;
     return (int32_t)layers.size();

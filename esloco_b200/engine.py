@@ -115,6 +115,12 @@ class Engine:
         a = _np(a, np.uint32)
         self._check(self.lib.esl_set_length_table(self.ctx, a.ctypes.data, a.size, self._stream()))
 
+    def pool_stats(self):
+        """(mean, sd, longest) of the resident length table, reduced on the device when it was uploaded."""
+        m, sd, mx = C.c_double(), C.c_double(), C.c_uint32()
+        self._check(self.lib.esl_pool_stats(self.ctx, C.byref(m), C.byref(sd), C.byref(mx)))
+        return m.value, sd.value, mx.value
+
     def prepare(self):
         """Build / upload the device index for the inputs set so far (no-op when nothing changed).  The run methods
         call it themselves, so the C-level rule "run calls never allocate or block" costs Python callers nothing."""

@@ -74,15 +74,18 @@ class Session:
         if key != self._pool_key:
             self._pool_copy = pool.copy() if pool is not None else None
             pool = np.asarray(make_pool()) if pool is None else pool
-            G = self.engine.genome_size
-            if G and pool.size and int(pool.max()) >= G:
+            eng = self.engine
+            eng.set_length_table(pool)
+            mean, _sd, longest = eng.pool_stats()  # reduced on the device during the upload: no host pass over the table
+            G = eng.genome_size
+            if G and longest >= G:
                 keep = pool < G
                 logging.warning(f"{int((~keep).sum())} of {pool.size} read lengths are not shorter than the genome "
                                 f"({G}) and were dropped from the length table.")
-                pool = pool[keep]
-            self.engine.set_length_table(pool)
-            self.engine.prepare()
-            self.pool_mean = float(pool.mean())
+                eng.set_length_table(pool[keep])
+                mean = eng.pool_stats()[0]
+            eng.prepare()
+            self.pool_mean = mean
             self._pool_key = key
 
 

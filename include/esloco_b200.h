@@ -104,6 +104,9 @@ int esl_set_blocked(esl_ctx *ctx, const int64_t *start, const int64_t *end, cons
  * from mean / sd / max). */
 int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n, void *stream);
 
+/* Statistics of the resident length table as the device reduced them (any pointer may be NULL). */
+int esl_pool_stats(const esl_ctx *ctx, double *mean, double *sd, uint32_t *longest);
+
 /* Build and upload the device index (target layers + bucket grids per barcode, blocked groups, CDF tables) for the
  * inputs set so far; a no-op when nothing changed since the last call.  This is where build_mask_tree's trees
  * (utils.py:89-101) and the target dict of count_matches (counting.py:19-30) become device structures.  Uploads are
