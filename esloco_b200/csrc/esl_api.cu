@@ -510,6 +510,7 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
     std::vector<double> mw;
     std::vector<esl::SegDesc> grp;
     std::vector<esl::GridEntry<C>> mgrid;
+    i64 n_real = 0;
     for (int g = 0; g <= B; ++g) {
         const int want = g < B ? g : -1;
         std::vector<size_t> idx;
@@ -528,8 +529,11 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
         }
         if ((int)ms.size() == glo) grp.push_back(empty_run<C>(mgrid));
         else grp.push_back(make_grid<C>(mp.data(), ms.data(), glo, (int)ms.size(), G, mgrid));
+        n_real += (i64)ms.size() - glo;
+        // sentinel behind the group (outside [lo, hi)): a start of all ones ends any walk without a bound check
+        ms.push_back((C) ~(C)0); me.push_back((C) ~(C)0); mp.push_back((C) ~(C)0); mw.push_back(0.0);
     }
-    ctx->n_mask = (i64)ms.size();
+    ctx->n_mask = n_real;
     std::vector<esl::MaskRec<C>> mrec(ms.size());
     for (size_t k = 0; k < ms.size(); ++k) { mrec[k] = esl::MaskRec<C>{}; mrec[k].s = ms[k]; mrec[k].e = me[k]; mrec[k].w = mw[k]; }
     ctx->n_mgrid = (int)mgrid.size(); ctx->n_mrec = (int)mrec.size();
@@ -598,6 +602,8 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.n_barcodes = ctx->B;
     d.consuming = consuming ? 1 : 0;
     d.has_mask = ctx->n_mask > 0;
+    d.mask_mode = 0;
+    for (int32_t b : ctx->m_bc) d.mask_mode |= b >= 0 ? 1 : 2;
     d.n_pool = ctx->n_pool;
     d.pool = ctx->d_pool.as<uint32_t>();
     d.cdf = ctx->d_cdf.as<double>();
@@ -644,12 +650,7 @@ i64 bulk_reads(const esl_ctx *ctx, double coverage)
 
 size_t bulk_smem(const esl_ctx *ctx)
 {
-    const int B = ctx->B;
-    const size_t entry = ctx->wide ? 8 : 4;
-    const size_t item = ctx->wide ? sizeof(esl::WalkItem<uint64_t>) : sizeof(esl::WalkItem<uint32_t>);
-    const size_t queues = ctx->sgrid_n ? 0 : (size_t)(esl::kBulkBlock / 32) * esl::kQueueCap * item; // per-warp candidate queues
-    return queues + (ctx->n_hot ? (size_t)esl::kHotWords * 4 : 0) + ((size_t)B * ctx->sgrid_n * entry * 2 + 15) / 16 * 16 + (size_t)(B <= esl::kSmemDescs ? B : 0) * 16 + (size_t)(2 * B + 2) * 4 +
-           (size_t)esl::kCdfLut * 2 + 32;
+    return esl::bulk_smem_layout(ctx->wide ? 8 : 4, ctx->n_mask > 0, ctx->sgrid_n > 0, ctx->n_hot > 0, ctx->B, ctx->sgrid_n).total;
 }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
 
@@ -684,12 +685,12 @@ struct BulkRange {
 
 template <typename C, typename Src>
 int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const esl::DevOut &out, const BulkRange &r,
-                int n_iter, cudaStream_t st)
+                int n_iter, u64 *d_sched, cudaStream_t st)
 {
     const i64 total_tiles = r.tiles * n_iter;
     if (total_tiles <= 0) return ESL_OK;
     // one instantiation per (blocked regions?, small target set with a shared pre-filter?, hot targets?)
-    using Kern = void (*)(esl::DevCtx<C>, Src, esl::DevOut, const i64 *, i64, const i64 *, i64, int, int, i64);
+    using Kern = void (*)(esl::DevCtx<C>, Src, esl::DevOut, const i64 *, i64, const i64 *, i64, int, int, i64, u64 *);
     static const Kern table[8] = {
         esl::k_place_tally_bulk<C, Src, false, false, false>, esl::k_place_tally_bulk<C, Src, false, false, true>,
         esl::k_place_tally_bulk<C, Src, false, true, false>,  esl::k_place_tally_bulk<C, Src, false, true, true>,
@@ -700,36 +701,58 @@ int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const es
     if (bulk_smem(ctx) > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem(ctx)));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx)));
     if (occ < 1) occ = 1;
-    const i64 grid = std::min<i64>(total_tiles, (i64)ctx->sm_count * occ);
+    const i64 grid = std::min<i64>((total_tiles + esl::kBulkClaim - 1) / esl::kBulkClaim, (i64)ctx->sm_count * occ);
     kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx), st>>>(dc, src, out, r.lo_arr, r.lo_const, r.hi_arr, r.hi_const,
-                                                                      (int)r.tile0, (int)r.tiles, total_tiles);
+                                                                      (int)r.tile0, (int)r.tiles, total_tiles, d_sched);
     CU(cudaGetLastError());
     ctx->launches++;
     return ESL_OK;
 }
 
+// Workspace layout: [tile sums: tiles * n_iter u64][second-pass ranges: 2 * n_iter i64][tile counters of the two bulk
+// launches: 2 u64]
+struct Workspace {
+    u64 *tile_sum;
+    i64 *range;
+    u64 *sched;
+    size_t tile_bytes;
+};
+size_t ws_tile_bytes(i64 cap, int n_iter) { return (size_t)((cap + esl::kBulkTile - 1) / esl::kBulkTile) * (size_t)n_iter * sizeof(u64); }
+size_t ws_total_bytes(i64 cap, int n_iter) { return ((ws_tile_bytes(cap, n_iter) + 15) & ~(size_t)15) + (size_t)(2 * n_iter + 2) * sizeof(i64) + 64; }
+Workspace ws_carve(void *d_ws, i64 cap, int n_iter)
+{
+    Workspace w;
+    w.tile_bytes = ws_tile_bytes(cap, n_iter);
+    w.tile_sum = (u64 *)d_ws;
+    w.range = (i64 *)((char *)d_ws + ((w.tile_bytes + 15) & ~(size_t)15));
+    w.sched = (u64 *)(w.range + 2 * n_iter);
+    return w;
+}
+
 // Bulk pass(es) + exact cut-off kernel.  n1 = draws per iteration of the first pass; n_cap >= n1 = bound of the
-// optional second pass (needs d_range = 2 * n_iter i64 of scratch); out.tile_sum must be zeroed and hold
-// ceil(n_cap / tile) entries per iteration.
+// optional second pass; ws.tile_sum holds ceil(max(n1, n_cap) / tile) entries per iteration and is zeroed by the
+// caller when the cut-off kernel will read it.
 template <typename C, typename Src>
 int launch_pipeline(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, esl::DevOut out, i64 n1, i64 n_cap,
-                    i64 *d_range, int n_iter, bool run_tail, cudaStream_t st)
+                    const Workspace &ws, bool second_pass, int n_iter, bool run_tail, cudaStream_t st)
 {
     const i64 T = esl::kBulkTile;
+    out.tile_sum = ws.tile_sum;
     out.tiles_per_iter = (int)((std::max(n1, n_cap) + T - 1) / T);
     const bool prof = ctx->profiling && ctx->ev[0];
     ctx->ev_valid = false;
+    CU(cudaMemsetAsync(ws.sched, 0, 2 * sizeof(u64), st));
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
-    int rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{nullptr, 0, nullptr, n1, 0, (n1 + T - 1) / T}, n_iter, st);
+    int rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{nullptr, 0, nullptr, n1, 0, (n1 + T - 1) / T}, n_iter, ws.sched, st);
     if (rc) return rc;
     const i64 *d_hi = nullptr;
-    if (n_cap > n1 && d_range && n1 > 0) {
-        i64 *d_lo = d_range, *d_hi2 = d_range + n_iter;
+    if (second_pass && n_cap > n1 && n1 > 0) {
+        i64 *d_lo = ws.range, *d_hi2 = ws.range + n_iter;
         const double m2 = ctx->pool_sd * ctx->pool_sd + ctx->pool_mean * ctx->pool_mean;
         esl::k_plan_second_pass<<<(n_iter + 127) / 128, 128, 0, st>>>(out.n_bases, n_iter, dc.thr, n1, n_cap, m2, 8.0, d_lo, d_hi2);
         CU(cudaGetLastError());
         ctx->launches++;
-        rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{d_lo, 0, d_hi2, 0, n1 / T, (n_cap - n1) / T}, n_iter, st);
+        rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{d_lo, 0, d_hi2, 0, n1 / T, (n_cap - n1) / T}, n_iter, ws.sched + 1, st);
         if (rc) return rc;
         d_hi = d_hi2;
     }
@@ -743,9 +766,6 @@ int launch_pipeline(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, esl:
     if (prof) { CU(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid = true; }
     return ESL_OK;
 }
-
-// Workspace layout: [tile sums: tiles * n_iter u64][second-pass ranges: 2 * n_iter i64]
-size_t ws_tile_bytes(i64 cap, int n_iter) { return (size_t)((cap + esl::kBulkTile - 1) / esl::kBulkTile) * (size_t)n_iter * sizeof(u64); }
 
 int zero_outputs(esl_ctx *ctx, int n_iter, int64_t *d_tallies, int64_t *d_label_counts, int64_t *d_n_bases,
                  int64_t *d_n_reads, int32_t *d_status, cudaStream_t st)
@@ -927,7 +947,7 @@ int64_t esl_workspace_bytes(const esl_ctx *ctx, int32_t n_iter, double coverage,
 {
     if (!ctx || n_iter < 0) return ESL_ERR_INVALID;
     const i64 cap = max_draws_per_iter > 0 ? max_draws_per_iter : bulk_cap(ctx, coverage);
-    return (int64_t)(ws_tile_bytes(cap, n_iter) + (size_t)(2 * n_iter + 2) * sizeof(i64)) + 256;
+    return (int64_t)ws_total_bytes(cap, n_iter) + 192;
 }
 
 int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t *d_count)
@@ -1005,12 +1025,11 @@ int esl_run_batch(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iter_beg
     esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iter_begin, philox_keys((uint32_t)seed, (uint32_t)(seed >> 32))};
     const i64 n1 = bulk_reads(ctx, coverage);
     const i64 cap = (ctx->n_mask > 0 && !consuming) ? bulk_cap(ctx, coverage) : n1;
-    const size_t tile_bytes = ws_tile_bytes(std::max(cap, n1), n_iter);
-    CU(cudaMemsetAsync(d_ws, 0, tile_bytes, st));
-    i64 *d_range = (i64 *)((char *)d_ws + ((tile_bytes + 15) & ~(size_t)15));
+    const Workspace ws = ws_carve(d_ws, std::max(cap, n1), n_iter);
+    CU(cudaMemsetAsync(d_ws, 0, ws.tile_bytes, st));
     if (ctx->wide)
-        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, n1, cap, d_range, n_iter, true, st);
-    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, n1, cap, d_range, n_iter, true, st);
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, n1, cap, ws, true, n_iter, true, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, scaling), src, out, n1, cap, ws, true, n_iter, true, st);
 }
 
 // ---- staged baseline ---------------------------------------------------------------------------------------------
@@ -1120,9 +1139,10 @@ int esl_replay_reads(esl_ctx *ctx, const int64_t *d_start, const int64_t *d_leng
     esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0, ctx->d_hits, (u64 *)ctx->d_hit_count, ctx->hit_cap};
     esl::ReadSrc src{d_start, d_length, d_label, d_seg};
     const i64 big = max_reads_per_iter; // every iteration's reads are all "bulk" (clipped to its own count on device)
+    const Workspace ws = ws_carve(d_ws, std::max<i64>(big, 1), n_iter);
     if (ctx->wide)
-        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, big, big, nullptr, n_iter, false, st);
-    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, big, big, nullptr, n_iter, false, st);
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, big, big, ws, false, n_iter, false, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, 0.0, 0, min_overlap, 1.0), src, out, big, big, ws, false, n_iter, false, st);
 }
 
 int esl_replay_draws(esl_ctx *ctx, const double *d_ubc, const int64_t *d_length, const int64_t *d_start,
@@ -1147,12 +1167,13 @@ int esl_replay_draws(esl_ctx *ctx, const double *d_ubc, const int64_t *d_length,
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = zero_outputs(ctx, n_iter, d_tallies, d_label_counts, d_n_bases, d_n_reads, d_status, st))) return rc;
     if (max_draws >= 0xFFFF0000ll) return ctx->fail(ESL_ERR_UNSUPPORTED, "more than 2^32 draws per iteration");
-    CU(cudaMemsetAsync(d_ws, 0, ws_tile_bytes(std::max<i64>(bulk_draws, 1), n_iter), st));
+    const Workspace ws = ws_carve(d_ws, std::max<i64>(bulk_draws, 1), n_iter);
+    CU(cudaMemsetAsync(d_ws, 0, ws.tile_bytes, st));
     esl::DevOut out{(u64 *)d_tallies, (u64 *)d_label_counts, (u64 *)d_n_bases, (u64 *)d_n_reads, d_status, (u64 *)d_ws, 0, ctx->d_hits, (u64 *)ctx->d_hit_count, ctx->hit_cap};
     esl::DrawSrc src{d_ubc, d_length, d_start, d_uoff, d_ublock, d_seg};
     if (ctx->wide)
-        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, bulk_draws, bulk_draws, nullptr, n_iter, true, st);
-    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, bulk_draws, bulk_draws, nullptr, n_iter, true, st);
+        return launch_pipeline<uint64_t>(ctx, make_devctx<uint64_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, bulk_draws, bulk_draws, ws, false, n_iter, true, st);
+    return launch_pipeline<uint32_t>(ctx, make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, 1.0), src, out, bulk_draws, bulk_draws, ws, false, n_iter, true, st);
 }
 
 int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t iteration, int32_t consuming,

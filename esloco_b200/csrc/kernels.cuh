@@ -32,14 +32,15 @@ typedef int64_t i64;
 #ifndef ESL_BULK_BLOCK
 #define ESL_BULK_BLOCK 256
 #endif
-#ifndef ESL_BULK_IPT
-#define ESL_BULK_IPT 3
-#endif
 constexpr int kBulkBlock = ESL_BULK_BLOCK; // threads per CTA of the bulk kernel
-constexpr int kBulkIpt = ESL_BULK_IPT;     // reads per thread and tile (256 x 3 with 5 CTAs/SM won the round-1 sweep)
+// Reads per thread and tile: FOUR CONSECUTIVE draws (n0 .. n0+3, n0 = base + 4 * tid).  With 32-bit coordinates one
+// Philox block serves two draws and one more block the barcodes of four (PhiloxSrc), so a thread spends 2 (+1) blocks
+// on its four reads instead of 4.
+constexpr int kBulkIpt = 4;
 constexpr int kBulkTile = kBulkBlock * kBulkIpt;
+constexpr int kBulkClaim = 8; // tiles a CTA claims from the launch's tile counter at a time
 #ifndef ESL_BULK_MIN_BLOCKS
-#define ESL_BULK_MIN_BLOCKS 5
+#define ESL_BULK_MIN_BLOCKS 4
 #endif
 constexpr int kBulkMinBlocks = ESL_BULK_MIN_BLOCKS; // register cap: 65536 / (256 * min blocks)
 #ifndef ESL_BULK_MIN_BLOCKS_GENERAL
@@ -151,6 +152,7 @@ struct DevCtx {
     int n_barcodes;
     int consuming;
     int has_mask;
+    int mask_mode; // bit 0: some barcode has a tree of its own, bit 1: the "ALL" tree holds intervals
     uint32_t n_pool;
     const uint32_t *__restrict__ pool;    // length table (K2)
     const double *__restrict__ cdf;       // numpy-style cdf, replay path
@@ -207,7 +209,15 @@ struct DevOut {
 
 // ---------------------------------------------------------------- draw sources
 
-// Native stream.
+// Native stream.  Counter layout (philox.cuh): c2 = iteration, c3 = combination << 4 | slot, key = seed.
+//   32-bit coordinates (G < 2^32): draw n takes 64 bits (a, b) of block (c0 = n >> 1, c1 = 0) -- words (x, y) for even
+//     n, (z, w) for odd n:
+//        length = pool[ floor((b >> 8) * n_pool / 2^24) ]                     24 bits: uniform pick from the pool
+//        start  = floor( (a * 2^32 + (b & 0xff) * 2^24) * (G - L) / 2^64 )    40 bits: U{0 .. G-L-1}
+//     (a position's probability deviates from uniform by < (G - L) / 2^40 = 0.3 % of itself at hg38 size, a window of
+//     w positions by 1/w of that; a pool entry's by < n_pool / 2^24) and, with more than one barcode, word n & 3 of
+//     block (c0 = n >> 2, c1 = 1) for searchsorted(cdf, u, 'right').
+//   64-bit coordinates: draw n owns block (c0 = n, c1 = 0): (x, y) = 64-bit start, z = length pick, w = barcode.
 struct PhiloxSrc {
     uint32_t k0, k1, combo, iter_begin;
     PhiloxKeys keys; // round keys of (k0, k1), filled by the host
@@ -216,30 +226,77 @@ struct PhiloxSrc {
     static constexpr bool kPoolLengths = true; // no read is longer than the pool's longest entry
     __device__ __forceinline__ i64 count(int) const { return 0x7fffffffffffffffLL; }
 
+    __device__ __forceinline__ Philox4 block(uint32_t c0, uint32_t c1, int it) const
+    {
+        return philox4x32_10(c0, c1, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, keys);
+    }
+    template <typename C>
+    static __device__ __forceinline__ int barcode_of(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint16_t *s_lut, uint32_t w)
+    {
+        // searchsorted(cdf, u, side='right') on integer thresholds: table start + short walk.  A slice of the start
+        // table holds at most cx.cdf_walk thresholds: one branch-free step covers almost every CDF; the loop only
+        // exists for more than ~1000 barcodes or pathological weights
+        int k = s_lut[w >> 22];
+        k += (k < cx.n_barcodes - 1 && s_cdf[k] <= w) ? 1 : 0;
+        if (cx.cdf_walk > 1)
+            while (k < cx.n_barcodes - 1 && s_cdf[k] <= w) ++k;
+        return k;
+    }
+    static __device__ __forceinline__ void place32(const DevCtx<uint32_t> &cx, uint32_t a, uint32_t b, uint32_t &L, uint32_t &start)
+    {
+        L = __ldg(cx.pool + __umulhi(b & 0xFFFFFF00u, cx.n_pool)); // index < n_pool by construction
+        ESL_CHK((u64)L < cx.G, "read not shorter than the genome");
+        const uint32_t rg = (uint32_t)(cx.G - (u64)L); // two 32x32->64 products instead of a 64x64 high multiply
+        start = (uint32_t)(((u64)a * rg + (((u64)(b << 24) * rg) >> 32)) >> 32);
+    }
+    static __device__ __forceinline__ void place64(const DevCtx<uint64_t> &cx, const Philox4 &r, uint32_t &L, uint64_t &start)
+    {
+        L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool));
+        ESL_CHK((u64)L < cx.G, "read not shorter than the genome");
+        start = __umul64hi(((u64)r.x << 32) | r.y, cx.G - (u64)L);
+    }
+
+    // One draw (cut-off kernel, partial tiles, materialisation).
     template <typename C>
     __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint16_t *s_lut, int it, i64 n,
                                          uint32_t &L, C &start, int &bc) const
     {
-        const Philox4 r = philox4x32_10((uint32_t)n, 0u, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, keys);
-        L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool)); // uniform pick from the pool (index < n_pool by construction)
-        ESL_CHK((u64)L < cx.G, "read not shorter than the genome");
-        const u64 range = cx.G - (u64)L;               // start ~ U{0 .. G-L-1} = floor(u64 * range / 2^64)
-        if (sizeof(C) == 4) { // range < 2^32: two 32x32->64 products instead of a 64x64 high multiply
-            const uint32_t rg = (uint32_t)range;
-            start = (C)(((u64)r.x * rg + (((u64)r.y * rg) >> 32)) >> 32);
+        bc = 0;
+        if constexpr (sizeof(C) == 4) {
+            const Philox4 r = block((uint32_t)n >> 1, 0u, it);
+            place32(cx, (n & 1) ? r.z : r.x, (n & 1) ? r.w : r.y, L, start);
+            if (cx.n_barcodes > 1) {
+                const Philox4 q = block((uint32_t)n >> 2, 1u, it);
+                const uint32_t w = (n & 2) ? ((n & 1) ? q.w : q.z) : ((n & 1) ? q.y : q.x);
+                bc = barcode_of(cx, s_cdf, s_lut, w);
+            }
         } else {
-            start = (C)__umul64hi(((u64)r.x << 32) | r.y, range);
+            const Philox4 r = block((uint32_t)n, 0u, it);
+            place64(cx, r, L, start);
+            if (cx.n_barcodes > 1) bc = barcode_of(cx, s_cdf, s_lut, r.w);
         }
-        int k = 0;
-        if (cx.n_barcodes > 1) { // searchsorted(cdf, u, side='right') on integer thresholds: table start + short walk
-            k = s_lut[r.w >> 22];
-            // a slice of the start table holds at most cx.cdf_walk thresholds: one branch-free step covers almost
-            // every CDF; the loop only exists for more than ~1000 barcodes or pathological weights
-            k += (k < cx.n_barcodes - 1 && s_cdf[k] <= r.w) ? 1 : 0;
-            if (cx.cdf_walk > 1)
-                while (k < cx.n_barcodes - 1 && s_cdf[k] <= r.w) ++k;
+    }
+    // Four consecutive draws n0 .. n0+3 (n0 a multiple of 4): the bulk kernel's full tiles.
+    template <typename C>
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint16_t *s_lut, int it, uint32_t n0,
+                                          uint32_t (&L)[4], C (&start)[4], int (&bc)[4]) const
+    {
+        if constexpr (sizeof(C) == 4) {
+            const Philox4 r0 = block(n0 >> 1, 0u, it), r1 = block((n0 >> 1) + 1u, 0u, it);
+            place32(cx, r0.x, r0.y, L[0], start[0]);
+            place32(cx, r0.z, r0.w, L[1], start[1]);
+            place32(cx, r1.x, r1.y, L[2], start[2]);
+            place32(cx, r1.z, r1.w, L[3], start[3]);
+            bc[0] = bc[1] = bc[2] = bc[3] = 0;
+            if (cx.n_barcodes > 1) {
+                const Philox4 q = block(n0 >> 2, 1u, it);
+                bc[0] = barcode_of(cx, s_cdf, s_lut, q.x); bc[1] = barcode_of(cx, s_cdf, s_lut, q.y);
+                bc[2] = barcode_of(cx, s_cdf, s_lut, q.z); bc[3] = barcode_of(cx, s_cdf, s_lut, q.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) draw(cx, s_cdf, s_lut, it, (i64)(n0 + i), L[i], start[i], bc[i]);
         }
-        bc = k;
     }
     __device__ __forceinline__ double block_u(int it, i64 n, int j) const
     {
@@ -280,6 +337,13 @@ struct DrawSrc {
         while (k < cx.n_barcodes - 1 && cx.cdf[k] <= u) ++k;
         bc = k;
     }
+    template <typename C>
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *c, const uint16_t *l, int it, uint32_t n0,
+                                          uint32_t (&L)[4], C (&st)[4], int (&bc)[4]) const
+    {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) draw(cx, c, l, it, (i64)(n0 + i), L[i], st[i], bc[i]);
+    }
     __device__ __forceinline__ double block_u(int it, i64 n, int j) const { return ublock[uoff[seg[it] + n] + j]; }
     __device__ __forceinline__ double scale_u(int, i64, int) const { return 0.0; }
 };
@@ -303,6 +367,13 @@ struct ReadSrc {
         L = (uint32_t)length[g];
         st = (C)start[g];
         bc = label[g];
+    }
+    template <typename C>
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *c, const uint16_t *l, int it, uint32_t n0,
+                                          uint32_t (&L)[4], C (&st)[4], int (&bc)[4]) const
+    {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) draw(cx, c, l, it, (i64)(n0 + i), L[i], st[i], bc[i]);
     }
     __device__ __forceinline__ double block_u(int, i64, int) const { return 0.0; }
     __device__ __forceinline__ double scale_u(int, i64, int) const { return 0.0; }
@@ -368,12 +439,51 @@ __device__ __forceinline__ bool is_blocked(const DevCtx<C> &cx, const Src &src, 
 constexpr int kHotSlots = 64;               // "hot" targets with a private shared-memory tally per CTA
 constexpr int kHotWords = kHotSlots * 4 + kHotSlots; // {full, partial, overlap & 0xffff, overlap >> 16} per slot, then the slots' rows
 static_assert(kHotWords % 4 == 0, "the hot-target block must keep 16-byte alignment behind it");
-constexpr int kHotFlushTiles = 64;          // 64 tiles x 768 reads x 0xffff < 2^32: the 32-bit shared sums cannot overflow
+constexpr int kHotFlushTiles = 32;          // 32 tiles x 1024 reads x 0xffff < 2^32: the 32-bit shared sums cannot overflow
 static_assert((unsigned long long)kHotFlushTiles * kBulkTile * 0xffffull < (1ull << 32), "hot-target sums must fit 32 bits between flushes");
 
-// K6 + K7 for one layer whose first candidate starts before the read's end: walk the candidates and add
-// (sign = +1) or take back (sign = -1) the read's contribution (counting.py:40-57).  s_hot = the CTA's private tallies
-// of the hot targets (bulk kernel) or null (cut-off kernel: plain atomics, it sees 0.4 % of the reads).
+// K6 + K7 for ONE target record a read [rs, re) was found to overlap (r.s < re and r.e > rs): add (sign = +1) or take
+// back (sign = -1) the read's contribution (counting.py:40-57).  s_hot = the CTA's private tallies of the hot targets
+// (bulk kernel) or null (cut-off kernel: plain atomics, it sees 0.4 % of the reads).
+template <typename C, typename Src>
+__device__ __forceinline__ void tally_hit(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it, i64 n,
+                                          const TargetRec<C> &r, C rs, C re, i64 sign, uint32_t *s_hot)
+{
+    const C ov = (r.e < re ? r.e : re) - (r.s > rs ? r.s : rs);
+    // "hot" target (flagged by the host: a read hits it with probability >= 1/512, e.g. a whole-chromosome
+    // ROI): the record carries a slot number instead of the row
+    int row = r.row & 0x7fffffff;
+    const int slot = row;
+    if (r.row < 0) row = s_hot ? (int)s_hot[kHotSlots * 4 + slot] : __ldg(cx.hot_row + slot);
+    ESL_CHK(row < cx.n_targets, "target row");
+    if ((u64)ov >= (u64)cx.min_ov32 && !(cx.thin && !(src.scale_u(it, n, row) <= cx.scaling))) {
+        const int kind = (rs <= r.s && r.e <= re) ? 0 : 1;
+        if (r.row < 0 && s_hot) {
+            // bulk kernel: hits go to the CTA's private 32-bit sums in shared memory (flushed to the global
+            // tallies every kHotFlushTiles tiles) -- thousands of atomics per iteration on one global address
+            // serialise in L2, and combining lanes first (match.any + REDUX per group) cost more than it saved
+            uint32_t *h = s_hot + slot * 4;
+            atomicAdd(h + kind, 1u);
+            atomicAdd(h + 2, (uint32_t)ov & 0xffffu); // ov <= read length < 2^32
+            atomicAdd(h + 3, (uint32_t)((u64)ov >> 16));
+        } else {
+            u64 *t = tallies_it + (i64)row * 3;
+            atomicAdd(t + kind, (u64)sign);
+            atomicAdd(t + 2, (u64)(sign * (i64)ov));
+        }
+        if (out.hits && sign > 0) { // draws beyond the cut-off are dropped on the host by their index
+            const u64 slot_h = atomicAdd(out.hit_count, 1ull);
+            if ((i64)slot_h < out.hit_cap) {
+                i64 *h = out.hits + slot_h * 4;
+                h[0] = it; h[1] = row; h[2] = n;
+                h[3] = (i64)ov | (kind == 0 ? (i64)0x8000000000000000ULL : 0); // sign bit = full match
+            }
+        }
+    }
+}
+
+// One layer whose first candidate starts before the read's end, walked where it was found (cut-off kernel, and the
+// rare candidate of the small-target-set path).
 template <typename C, typename Src>
 __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it, i64 n,
                                          int sg, int a, C rs, C re, i64 sign, uint32_t *s_hot = nullptr)
@@ -383,39 +493,7 @@ __device__ __forceinline__ void tally_layer(const DevCtx<C> &cx, const Src &src,
         ESL_CHK(j >= 0 && j < cx.n_trec, "target record index");
         const TargetRec<C> r = load_rec(cx.trec + j);
         if (r.s >= re) break; // starts ascend: nothing further overlaps
-        if (r.e > rs) {       // (an end inside the bucket but before the read does not overlap)
-            const C ov = (r.e < re ? r.e : re) - (r.s > rs ? r.s : rs);
-            // "hot" target (flagged by the host: a read hits it with probability >= 1/512, e.g. a whole-chromosome
-            // ROI): the record carries a slot number instead of the row
-            int row = r.row & 0x7fffffff;
-            const int slot = row;
-            if (r.row < 0) row = s_hot ? (int)s_hot[kHotSlots * 4 + slot] : __ldg(cx.hot_row + slot);
-            ESL_CHK(row < cx.n_targets, "target row");
-            if ((u64)ov >= (u64)cx.min_ov32 && !(cx.thin && !(src.scale_u(it, n, row) <= cx.scaling))) {
-                const int kind = (rs <= r.s && r.e <= re) ? 0 : 1;
-                if (r.row < 0 && s_hot) {
-                    // bulk kernel: hits go to the CTA's private 32-bit sums in shared memory (flushed to the global
-                    // tallies every kHotFlushTiles tiles) -- thousands of atomics per iteration on one global address
-                    // serialise in L2, and combining lanes first (match.any + REDUX per group) cost more than it saved
-                    uint32_t *h = s_hot + slot * 4;
-                    atomicAdd(h + kind, 1u);
-                    atomicAdd(h + 2, (uint32_t)ov & 0xffffu); // ov <= read length < 2^32
-                    atomicAdd(h + 3, (uint32_t)((u64)ov >> 16));
-                } else {
-                    u64 *t = tallies_it + (i64)row * 3;
-                    atomicAdd(t + kind, (u64)sign);
-                    atomicAdd(t + 2, (u64)(sign * (i64)ov));
-                }
-                if (out.hits && sign > 0) { // draws beyond the cut-off are dropped on the host by their index
-                    const u64 slot_h = atomicAdd(out.hit_count, 1ull);
-                    if ((i64)slot_h < out.hit_cap) {
-                        i64 *h = out.hits + slot_h * 4;
-                        h[0] = it; h[1] = row; h[2] = n;
-                        h[3] = (i64)ov | (kind == 0 ? (i64)0x8000000000000000ULL : 0); // sign bit = full match
-                    }
-                }
-            }
-        }
+        if (r.e > rs) tally_hit(cx, src, out, tallies_it, it, n, r, rs, re, sign, s_hot); // (an end before the read does not overlap)
         if (r.s_next >= re) break; // known without touching the next record
     }
 }
@@ -459,8 +537,7 @@ __device__ __forceinline__ void tally_first_layer(const DevCtx<C> &cx, const Src
 }
 
 // All layers of the read's barcode: probe each layer, walk its candidates when the first one starts before
-// the read's end.  Out of line: the bulk kernel only calls it for the few reads whose first-layer probe says
-// "maybe" (or when some barcode has nesting targets), the cut-off kernel for every read.
+// the read's end (cut-off kernel).
 template <typename C, typename Src>
 __device__ __forceinline__ void tally_read(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it,
                                         i64 n, C rs, C re, int bc, i64 sign)
@@ -531,89 +608,175 @@ __device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
     return v;
 }
 
-// ---------------------------------------------------------------- per-warp candidate queue
+// ---------------------------------------------------------------- per-warp work queues
 //
-// Only a few lanes of a warp have a target candidate for a given read (config 3: 6 %, config 4: about half), so
-// walking the candidates where they are found runs the whole walk at a few lanes' occupancy, once per read slot
-// and layer.  Instead every (read, layer, first candidate) whose probe says "maybe" is pushed to a queue in shared
-// memory owned by the warp, and the warp drains the queue 32 items at a time with all lanes busy.
-template <typename C> struct WalkItem;
-template <> struct __align__(16) WalkItem<uint32_t> { uint32_t st, L; int a; uint32_t sg_n; };
-template <> struct __align__(8) WalkItem<uint64_t> { uint64_t st; uint32_t L; int a; uint32_t sg_n, pad; };
-constexpr int kQueueCap = 128;    // items per warp; drained early when a tile row (32 lanes x kBulkIpt reads) may not fit
-constexpr int kQueueSegBits = 22; // sg_n = run index | (draw offset inside the tile << 22); host checks n_seg < 2^22
-static_assert(kBulkTile <= (1 << (32 - kQueueSegBits)), "draw offset must fit above the run index");
+// Only a few lanes of a warp have a target candidate for a given read (config 3: 6 %, config 4: about half), and a
+// candidate walk visits one to a handful of records, so walking where the candidate is found runs at a few lanes'
+// occupancy.  Instead every (read, layer, candidate record) is an ITEM in a queue in shared memory owned by the
+// warp, and the warp works the queue in ROUNDS: 32 items are popped, every lane visits exactly ONE record, and an
+// item whose walk goes on is pushed back with the next record.  Rounds only run while 32 items are there (what is
+// left waits for the next tile), so every round has all lanes busy; the queue is emptied when the CTA moves to
+// another iteration.  The same queue type carries the reads whose blocked-interval probe said "maybe" (drained once
+// per tile: the labels are needed before the targets are looked at).
+template <typename C>
+struct WalkItem { // 20 bytes (32-bit coordinates) / 24 bytes
+    C st;         // read start
+    uint32_t L;   // read length
+    int a;        // record index; bit 30 = the run is crowded and the walk has not yet skipped ahead (first visit)
+    uint32_t sg;  // run (layer) index            | mask items: first candidate in the "ALL" tree (or -1)
+    uint32_t n;   // draw index in the iteration  | mask items: barcode | slot in the warp's tile row << 16
+};
+constexpr int kQueueCap = 96;      // target items per warp: < 32 carried over + <= 32 pushed + <= 32 pushed back
+constexpr int kMaskQueueCap = 128; // mask items per warp: one per read of a tile row
+constexpr int kQueueSegBits = 22;  // the host keeps the number of runs below 2^22
+constexpr int kCrowdedBit = 1 << 30;
 
 // Called by all 32 lanes; n (the queue length) is warp-uniform.
 template <typename C>
-__device__ __forceinline__ void queue_push(WalkItem<C> *q, int &n, bool want, C st, uint32_t L, int a, uint32_t sg_n)
+__device__ __forceinline__ void queue_push(WalkItem<C> *q, int &n, bool want, C st, uint32_t L, int a, uint32_t sg, uint32_t dn)
 {
     const unsigned m = __ballot_sync(0xffffffffu, want);
     if (want) {
         WalkItem<C> w;
-        w.st = st; w.L = L; w.a = a; w.sg_n = sg_n;
-        ESL_CHK(n + __popc(m) <= kQueueCap, "candidate queue overflow");
+        w.st = st; w.L = L; w.a = a; w.sg = sg; w.n = dn;
         q[n + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = w;
     }
     n += __popc(m);
 }
+
+// One round: pop up to 32 items, one record visit per lane, push the walks that go on.
 template <typename C, typename Src>
-__device__ __forceinline__ void queue_drain(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
-                                            int it, uint32_t base, const WalkItem<C> *q, int &n, uint32_t *s_hot)
+__device__ __forceinline__ void queue_round(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
+                                            int it, WalkItem<C> *q, int &n, uint32_t *s_hot)
 {
+    const int lane = threadIdx.x & 31;
+    const int take = n < 32 ? n : 32;
+    const bool on = lane < take;
+    WalkItem<C> w;
+    if (on) w = q[n - take + lane];
     __syncwarp();
-    for (int k = threadIdx.x & 31; k < n; k += 32) {
-        const WalkItem<C> w = q[k];
-        tally_layer(cx, src, out, tallies_it, it, (i64)(base + (w.sg_n >> kQueueSegBits)), (int)(w.sg_n & ((1u << kQueueSegBits) - 1u)),
-                    w.a, w.st, (C)(w.st + w.L), 1, s_hot);
+    n -= take;
+    bool more = false;
+    if (on) {
+        const C rs = w.st, re = (C)(w.st + w.L);
+        int j = w.a & ~kCrowdedBit;
+        bool live = true;
+        if (w.a & kCrowdedBit) { // crowded run, first visit: bisect to the first record that can overlap
+            const SegDesc d = load_desc(cx.seg + w.sg);
+            j = skip_crowded(d, cx.tgrid, cx.te, j, rs);
+            live = j < d.hi;
+        }
+        if (live) {
+            ESL_CHK(j >= 0 && j < cx.n_trec, "target record index");
+            const TargetRec<C> r = load_rec(cx.trec + j);
+            if (r.s < re) { // else: starts ascend, nothing further overlaps
+                if (r.e > rs) tally_hit(cx, src, out, tallies_it, it, (i64)w.n, r, rs, re, 1, s_hot);
+                more = r.s_next < re; // known without touching the next record (all ones behind a run's last record)
+            }
+            w.a = j + 1;
+        }
     }
+    const unsigned m = __ballot_sync(0xffffffffu, more);
+    if (more) q[n + __popc(m & ((1u << lane) - 1u))] = w;
+    n += __popc(m);
     __syncwarp();
-    n = 0;
+}
+
+// Blocked test of a queued read, starting from the first candidates its probes found (a < 0: that tree has none).
+// Trees: the barcode's own, then "ALL"; hits in (start, end) order; one uniform per visited hit; u < weight blocks
+// (read_operations.py:59-67).  Every group of blocked records ends with a sentinel whose start is all ones.
+template <typename C, typename Src>
+__device__ __forceinline__ bool blocked_from(const DevCtx<C> &cx, const Src &src, int it, i64 n, int bc, C rs, C re, int a_bc, int a_all)
+{
+    int j = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        int k = pass == 0 ? a_bc : a_all;
+        if (k < 0) continue;
+        if (k & kCrowdedBit) {
+            const SegDesc d = load_desc(cx.grp + (pass == 0 ? bc : cx.n_barcodes));
+            k = skip_crowded(d, cx.mgrid, cx.mpmax, k & ~kCrowdedBit, rs);
+        }
+        for (;; ++k) {
+            ESL_CHK(k >= 0 && k < cx.n_mrec, "blocked record index");
+            const MaskRec<C> r = load_rec(cx.mrec + k);
+            if (r.s >= re) break; // (the sentinel ends every group)
+            if (r.e > rs) {
+                if (!Src::kBounded && r.w >= 1.0) return true; // u < 1 <= w for every u: no need to draw it
+                const double u = src.block_u(it, n, j++);
+                if (u < r.w) return true;
+            }
+        }
+    }
+    return false;
+}
+
+// Shared-memory layout of the bulk kernel, in 8-byte words, one definition for host (size) and device (offsets).
+// The arrays of compile-time size come first, so the hot ones sit at constant addresses.
+struct BulkSmem {
+    size_t queue, mqueue, mflags, hot, lut, sched, sgrid, desc, hist, cdf, total; // word offsets; total in BYTES
+};
+__host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool mask, bool shared, bool hot, int B, int sgrid_n)
+{
+    const size_t item = coord_bytes == 4 ? 20 : 24, warps = kBulkBlock / 32;
+    BulkSmem o;
+    size_t w = 0;
+    o.queue = w; w += shared ? 0 : (warps * kQueueCap * item + 7) / 8;
+    o.mqueue = w; w += mask ? (warps * kMaskQueueCap * item + 7) / 8 : 0;
+    o.mflags = w; w += mask ? warps * kBulkIpt * 4 / 8 : 0;
+    o.hot = w; w += hot ? kHotWords / 2 : 0;
+    o.lut = w; w += kCdfLut * 2 / 8;
+    o.sched = w; w += 2;
+    o.sgrid = w; w += ((size_t)(shared ? 2 * B * sgrid_n : 0) * coord_bytes + 15) / 16 * 2;
+    o.desc = w; w += (size_t)(B <= kSmemDescs ? B : 0) * 2;
+    o.hist = w; w += ((size_t)(B + 2) * 4 + 7) / 8;
+    o.cdf = w; w += ((size_t)B * 4 + 7) / 8;
+    o.total = w * 8;
+    return o;
 }
 
 // ---------------------------------------------------------------- bulk kernel
 
-// Persistent flat grid; CTA c owns a contiguous run of (iteration, tile) pairs.  One launch covers the absolute
-// tiles [tile0, tile0 + tiles_launch) of every iteration; inside that window iteration `it` owns the draws
-// [lo(it), hi(it)) (lo is a multiple of the tile size).  Draw indices are < 2^32 (checked on the host).
+// One launch covers the absolute tiles [tile0, tile0 + tiles_launch) of every iteration; inside that window iteration
+// `it` owns the draws [lo(it), hi(it)) (lo is a multiple of the tile size).  Draw indices are < 2^32 (checked on the
+// host).  The (iteration, tile) pairs are numbered iteration-major and handed out IN ORDER, kBulkClaim at a time, from
+// a counter in global memory (`sched`, zeroed by the host call): all CTAs work on neighbouring tiles, i.e. on one or
+// two iterations at a time, so the tally rows the atomics hit (config 3: 5.8 MB per iteration) stay in L2 instead of
+// being read-modified-written in HBM, and no CTA is left with a long tail.
 //
-// A thread resolves kBulkIpt reads per tile in PHASES, each phase running over all its reads before the next
-// starts, so the dependent memory accesses of different reads overlap (pool gather -> start -> grid entry are
-// two L2 round trips per read; the reads of a thread being in flight together hides them):
-//   1 draw  2 blocked probes / slow path  3 label histogram  4 target probes / slow path  5 tile sum
-// There is no block barrier inside the tile loop: warps only meet when the CTA moves to the next iteration and
-// flushes its shared label histogram.
+// A thread resolves its four consecutive draws in PHASES, each phase running over all its reads before the next
+// starts, so the dependent memory accesses of different reads overlap (pool gather -> start -> grid entry are two L2
+// round trips per read; the reads of a thread being in flight together hides them):
+//   1 draw  2 blocked probes, queue, drain  3 label histogram  4 target probes, queue, rounds  5 tile sum
+// Warps only meet when the CTA claims tiles or moves to the next iteration and flushes its shared label histogram.
 template <typename C, typename Src, bool kMask, bool kShared, bool kHot>
 __global__ void __launch_bounds__(kBulkBlock, bulk_min_blocks<C, kShared>())
 k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src src, const DevOut out, const i64 *__restrict__ lo_arr,
                    const i64 lo_const, const i64 *__restrict__ hi_arr, const i64 hi_const, const int tile0,
-                   const int tiles_launch, const i64 total_tiles)
+                   const int tiles_launch, const i64 total_tiles, u64 *__restrict__ sched)
 {
     extern __shared__ u64 smem[];
     const int B = cx.n_barcodes;
-    const int n_sgrid = kShared ? 2 * B * cx.sgrid_n : 0; // kShared: small target sets with a shared-memory pre-filter grid (pairs)
-    // Shared-memory layout: the arrays of compile-time size come first, so the hot ones sit at constant addresses
-    // (at 48 registers the compiler otherwise recomputes their bases from the kernel parameters on every use):
-    //   [candidate queues (general variant)] [hot-target tallies (kHot)] [barcode start table] [pre-filter grid
-    //   (shared variant)] then, 16-byte aligned, [first-layer descriptors] [label histogram] [CDF thresholds]
-    WalkItem<C> *queue = (WalkItem<C> *)smem + (threadIdx.x >> 5) * kQueueCap;
-    constexpr size_t queue_words = kShared ? 0 : (size_t)(kBulkBlock / 32) * kQueueCap * sizeof(WalkItem<C>) / 8;
+    const BulkSmem lay = bulk_smem_layout(sizeof(C), kMask, kShared, kHot, B, kShared ? cx.sgrid_n : 0);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    WalkItem<C> *const queue = (WalkItem<C> *)(smem + lay.queue) + wid * kQueueCap;
+    WalkItem<C> *const mqueue = (WalkItem<C> *)(smem + lay.mqueue) + wid * kMaskQueueCap;
+    uint32_t *const mflags = (uint32_t *)(smem + lay.mflags) + wid * kBulkIpt; // bit l of word i: read i of lane l is blocked
     // private tallies of the hot targets + their rows (kHot: the host flagged some; otherwise the null pointer is a
     // compile-time constant and every hot-target branch below folds away)
-    uint32_t *const s_hot = kHot ? (uint32_t *)(smem + queue_words) : nullptr;
-    constexpr size_t lut_words = queue_words + (kHot ? kHotWords / 2 : 0);
-    uint16_t *s_lut = (uint16_t *)(smem + lut_words);           // [kCdfLut]
-    constexpr size_t grid_words = lut_words + kCdfLut * 2 / 8;
-    C *s_grid = (C *)(smem + grid_words);                       // [B][sgrid_n] pairs
-    const size_t desc_words = grid_words + ((size_t)n_sgrid * sizeof(C) + 15) / 16 * 2;
-    int4 *s_desc = (int4 *)(smem + desc_words);                 // [min(B, kSmemDescs)] first-layer descriptors
+    uint32_t *const s_hot = kHot ? (uint32_t *)(smem + lay.hot) : nullptr;
+    uint16_t *const s_lut = (uint16_t *)(smem + lay.lut);       // [kCdfLut]
+    i64 *const s_sched = (i64 *)(smem + lay.sched);             // the claimed range, broadcast to the CTA
+    C *const s_grid = (C *)(smem + lay.sgrid);                  // [B][sgrid_n] pairs (small target sets)
+    int4 *const s_desc = (int4 *)(smem + lay.desc);             // [min(B, kSmemDescs)] first-layer descriptors
     const int n_sdesc = B <= kSmemDescs ? B : 0;
-    int *s_hist = (int *)(s_desc + n_sdesc);                    // [B + 2] reads per label since the last flush
-    uint32_t *s_cdf = (uint32_t *)(s_hist + B + 2);             // [B]
-    const int tid = threadIdx.x, lane = tid & 31;
+    int *const s_hist = (int *)(smem + lay.hist);               // [B + 2] reads per label since the last flush
+    uint32_t *const s_cdf = (uint32_t *)(smem + lay.cdf);       // [B]
+    const int n_sgrid = kShared ? 2 * B * cx.sgrid_n : 0;
     for (int i = tid; i < n_sgrid; i += kBulkBlock) s_grid[i] = cx.sgrid[i];
     for (int i = tid; i < n_sdesc; i += kBulkBlock) s_desc[i] = __ldg(reinterpret_cast<const int4 *>(cx.seg + i));
     for (int i = tid; i < B + 2; i += kBulkBlock) s_hist[i] = 0;
+    if (kMask && lane < kBulkIpt) mflags[lane] = 0;
     if (s_hot)
         for (int i = tid; i < kHotWords; i += kBulkBlock)
             s_hot[i] = i >= kHotSlots * 4 && i - kHotSlots * 4 < cx.n_hot ? (uint32_t)cx.hot_row[i - kHotSlots * 4] : 0u;
@@ -621,205 +784,222 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
         for (int i = tid; i < B; i += kBulkBlock) s_cdf[i] = cx.cdf_u32[i];
         for (int i = tid; i < kCdfLut; i += kBulkBlock) s_lut[i] = cx.cdf_lut[i];
     }
-    __syncthreads();
 
-    const i64 per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const i64 t0 = (i64)blockIdx.x * per_cta;
-    const i64 t1 = t0 + per_cta < total_tiles ? t0 + per_cta : total_tiles;
-    if (t0 >= t1) return;
     const bool plain_labels = !Src::kHasLabel && B == 1 && !kMask; // every read is label 0
     u64 acc_bases = 0, acc_reads = 0; // lane 0 of each warp / thread 0
     uint32_t lo = 0, hi = 0;
     u64 *tallies_it = nullptr;
     u64 *tile_sum_it = nullptr;
-    // (iteration, tile) of the first work item by one division; afterwards they advance incrementally
-    int it = (int)(t0 / tiles_launch);
-    int t = (int)(t0 - (i64)it * tiles_launch) + tile0;
-    bool new_it = true;
+    int it = -1, qn = 0, hot_tiles = 0;
 
-    for (i64 left_tiles = t1 - t0; left_tiles > 0; --left_tiles, ++t) {
-        if (s_hot && (left_tiles & (kHotFlushTiles - 1)) == 0 && t != tile0 + tiles_launch) { // (block-uniform)
-            __syncthreads();
-            flush_hot(s_hot, cx.n_hot, tallies_it);
-            __syncthreads();
+    // what the CTA gathered for iteration `it`: empty the walk queues, flush histogram / sums (all threads)
+    auto leave_iteration = [&]() {
+        if (it < 0) return;
+        if (!kShared)
+            while (qn > 0) queue_round(cx, src, out, tallies_it, it, queue, qn, s_hot);
+        __syncthreads();
+        if (s_hot) { flush_hot(s_hot, cx.n_hot, tallies_it); hot_tiles = 0; }
+        for (int i = tid; i < B + 2; i += kBulkBlock)
+            if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
+        if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
+        if (tid == 0 && acc_reads) {
+            atomicAdd(out.n_reads + it, acc_reads);
+            if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
         }
-        if (t == tile0 + tiles_launch) { // wrapped into the next iteration: flush what the CTA gathered for this one
-            __syncthreads();
-            if (s_hot) flush_hot(s_hot, cx.n_hot, tallies_it);
-            for (int i = tid; i < B + 2; i += kBulkBlock)
-                if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
-            if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
-            if (tid == 0) {
-                atomicAdd(out.n_reads + it, acc_reads);
-                if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
-            }
-            acc_bases = acc_reads = 0;
-            __syncthreads();
-            ++it;
-            t = tile0;
-            new_it = true;
-        }
-        if (new_it) {
-            new_it = false;
-            i64 l = lo_arr ? lo_arr[it] : lo_const, h = hi_arr ? hi_arr[it] : hi_const;
-            if (Src::kBounded) { const i64 c = src.count(it); h = h < c ? h : c; }
-            lo = (uint32_t)l;
-            hi = (uint32_t)(h > l ? h : l);
-            tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
-            tile_sum_it = out.tile_sum + (i64)it * out.tiles_per_iter;
-        }
-        const uint32_t base = (uint32_t)t * kBulkTile;
-        if (base < lo || base >= hi) continue; // tile outside this iteration's range (block-uniform)
+        acc_bases = acc_reads = 0;
+        __syncthreads();
+    };
 
-        uint32_t L[kBulkIpt];
-        C st[kBulkIpt];
-        int label[kBulkIpt];
-        // phase 1: draws (Philox, pool gather, start, barcode)
-        if (hi - base >= (uint32_t)kBulkTile) { // full tile (block-uniform; all but the last tile of a range)
-#pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i)
-                src.draw(cx, s_cdf, s_lut, it, (i64)(base + i * kBulkBlock + tid), L[i], st[i], label[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i) {
-                // branch-free tail handling: a thread past the end of the range redraws the range's last draw and is
-                // masked out afterwards (label = invalid, length 0)
-                const uint32_t n = base + i * kBulkBlock + tid;
-                src.draw(cx, s_cdf, s_lut, it, (i64)(n < hi ? n : hi - 1), L[i], st[i], label[i]);
-                if (n >= hi) { L[i] = 0; label[i] = kLabelInvalid; }
+    for (;;) {
+        __syncthreads(); // (also orders the set-up above before the first tile)
+        if (tid == 0) s_sched[0] = (i64)atomicAdd(sched, (u64)kBulkClaim);
+        __syncthreads();
+        const i64 g0 = s_sched[0];
+        if (g0 >= total_tiles) break;
+        const i64 g1 = g0 + kBulkClaim < total_tiles ? g0 + kBulkClaim : total_tiles;
+        int git = (int)(g0 / tiles_launch);
+        int t = (int)(g0 - (i64)git * tiles_launch) + tile0;
+        for (i64 g = g0; g < g1; ++g, ++t) {
+            if (t == tile0 + tiles_launch) { ++git; t = tile0; } // the claim runs on into the next iteration
+            if (git != it) { // (block-uniform)
+                leave_iteration();
+                it = git;
+                i64 l = lo_arr ? lo_arr[it] : lo_const, h = hi_arr ? hi_arr[it] : hi_const;
+                if (Src::kBounded) { const i64 c = src.count(it); h = h < c ? h : c; }
+                lo = (uint32_t)l;
+                hi = (uint32_t)(h > l ? h : l);
+                tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
+                tile_sum_it = out.tile_sum + (i64)it * out.tiles_per_iter;
             }
-        }
-        u64 my = 0;
-        if (!Src::kHasLabel && kMask) { // phase 2: blocked regions -- probe both trees for all reads, then the slow path
-            C first[kBulkIpt]; // smallest start among the first candidates of the barcode tree and the "ALL" tree
-#pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i) {
-                const Probe<C> pa = probe(cx.grp, label[i] >= 0 ? label[i] : 0, cx.mgrid, st[i]);
-                const Probe<C> pb = probe(cx.grp, B, cx.mgrid, st[i]);
-                first[i] = pa.s < pb.s ? pa.s : pb.s;
+            const uint32_t base = (uint32_t)t * kBulkTile;
+            if (base < lo || base >= hi) continue; // tile outside this iteration's range (block-uniform)
+            if (s_hot && ++hot_tiles == kHotFlushTiles) { // (block-uniform)
+                __syncthreads();
+                flush_hot(s_hot, cx.n_hot, tallies_it);
+                hot_tiles = 0;
+                __syncthreads();
             }
-#pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i) {
-                const C re = (C)(st[i] + L[i]);
-                uint32_t counted = L[i];
-                if (label[i] >= 0 && first[i] < re &&
-                    is_blocked(cx, src, it, (i64)(base + i * kBulkBlock + tid), label[i], st[i], re)) {
-                    label[i] = cx.consuming ? kLabelBlockedConsuming : kLabelBlockedNotConsuming;
-                    counted = cx.consuming ? L[i] : 0u;
-                }
-                my += counted;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i) my += (Src::kHasLabel && label[i] == kLabelBlockedNotConsuming) ? 0u : L[i];
-        }
-        if (!plain_labels) { // phase 3: label histogram
-#pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i)
-                hist_add(s_hist, label[i] != kLabelInvalid && label[i] < B ? label_slot(label[i], B) : -1, 1, B + 2);
-        }
-        if (kShared) { // phase 4, small target sets: shared-memory pre-filter, exact path for the rest
-            unsigned maybe = 0; // bit i: read i may overlap a first-layer target
-            if (plain_labels && hi - base >= (uint32_t)kBulkTile) { // one barcode, no mask, full tile: every read is valid
-#pragma unroll
-                for (int i = 0; i < kBulkIpt; ++i) {
-                    const C *g = s_grid + 2 * (int)((u64)st[i] >> cx.sgrid_shift);
-                    maybe |= (unsigned)(g[0] < (C)(st[i] + L[i]) && (!Src::kPoolLengths || st[i] < g[1])) << i;
-                }
+
+            const uint32_t n0 = base + (uint32_t)tid * kBulkIpt; // this thread's draws: n0 .. n0 + 3
+            uint32_t L[kBulkIpt];
+            C st[kBulkIpt];
+            int label[kBulkIpt];
+            // phase 1: draws (Philox, pool gather, start, barcode)
+            if (hi - base >= (uint32_t)kBulkTile) { // full tile (block-uniform; all but the last tile of a range)
+                src.draw4(cx, s_cdf, s_lut, it, n0, L, st, label);
             } else {
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i) {
-                    const bool ok = label[i] >= 0 && label[i] < B;
-                    ESL_CHK((int)((u64)st[i] >> cx.sgrid_shift) < cx.sgrid_n, "shared grid index");
-                    const C *g = s_grid + 2 * ((ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift));
-                    // g[0]: first candidate's start; g[1]: largest end a read from this bucket can meet
-                    maybe |= (unsigned)(ok && g[0] < (C)(st[i] + L[i]) && (!Src::kPoolLengths || st[i] < g[1])) << i;
+                    // branch-free tail handling: a thread past the end of the range redraws the range's last draw and is
+                    // masked out afterwards (label = invalid, length 0)
+                    const uint32_t n = n0 + i;
+                    src.draw(cx, s_cdf, s_lut, it, (i64)(n < hi ? n : hi - 1), L[i], st[i], label[i]);
+                    if (n >= hi) { L[i] = 0; label[i] = kLabelInvalid; }
                 }
             }
-            if (maybe) {
+            u64 my = 0;
+            if (!Src::kHasLabel && kMask) {
+                // phase 2: blocked regions -- probe the barcode's tree (if any barcode has one) and the "ALL" tree for all
+                // reads, queue the reads with a candidate, let the warp test them with all lanes busy, read the verdicts
+                int mn = 0;
+#pragma unroll
+                for (int i = 0; i < kBulkIpt; ++i) {
+                    const C re = (C)(st[i] + L[i]);
+                    int a_bc = -1, a_all = -1;
+                    if (cx.mask_mode & 1) {
+                        const int2 d = __ldg(reinterpret_cast<const int2 *>(cx.grp + (label[i] >= 0 ? label[i] : 0)) + 1);
+                        const GridEntry<C> e = load_entry(cx.mgrid + d.x + (int)((u64)st[i] >> (d.y & 0xff)));
+                        if (e.s < re) a_bc = e.j | ((d.y & 0x100) ? kCrowdedBit : 0);
+                    }
+                    if (cx.mask_mode & 2) {
+                        const int2 d = __ldg(reinterpret_cast<const int2 *>(cx.grp + B) + 1);
+                        const GridEntry<C> e = load_entry(cx.mgrid + d.x + (int)((u64)st[i] >> (d.y & 0xff)));
+                        if (e.s < re) a_all = e.j | ((d.y & 0x100) ? kCrowdedBit : 0);
+                    }
+                    queue_push(mqueue, mn, label[i] >= 0 && (a_bc >= 0 || a_all >= 0), st[i], L[i], a_bc, (uint32_t)a_all,
+                               (uint32_t)label[i] | (uint32_t)(i * 32 + lane) << 16);
+                }
+                __syncwarp();
+                for (int k = lane; k < mn; k += 32) {
+                    const WalkItem<C> w = mqueue[k];
+                    const int slot = (int)(w.n >> 16);
+                    const int owner = slot & 31; // the draw index follows from the slot: lane `owner`, read slot >> 5
+                    const uint32_t nd = base + (uint32_t)((wid * 32 + owner) * kBulkIpt + (slot >> 5));
+                    if (blocked_from(cx, src, it, (i64)nd, (int)(w.n & 0xffffu), w.st, (C)(w.st + w.L), w.a, (int)w.sg))
+                        atomicOr(mflags + (slot >> 5), 1u << owner);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < kBulkIpt; ++i) {
+                    uint32_t counted = L[i];
+                    if (mflags[i] >> lane & 1) {
+                        label[i] = cx.consuming ? kLabelBlockedConsuming : kLabelBlockedNotConsuming;
+                        counted = cx.consuming ? L[i] : 0u;
+                    }
+                    my += counted;
+                }
+                __syncwarp();
+                if (lane < kBulkIpt) mflags[lane] = 0;
+            } else {
+#pragma unroll
+                for (int i = 0; i < kBulkIpt; ++i) my += (Src::kHasLabel && label[i] == kLabelBlockedNotConsuming) ? 0u : L[i];
+            }
+            if (!plain_labels) { // phase 3: label histogram
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i)
-                    if (maybe >> i & 1)
-                        tally_first_layer(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), st[i], (C)(st[i] + L[i]), label[i], 1, s_hot);
+                    hist_add(s_hist, label[i] != kLabelInvalid && label[i] < B ? label_slot(label[i], B) : -1, 1, B + 2);
             }
-            if (cx.any_extra) { // the pre-filter only covers first layers
+            if (kShared) { // phase 4, small target sets: shared-memory pre-filter, exact path for the rest
+                unsigned maybe = 0; // bit i: read i may overlap a first-layer target
+                if (plain_labels && hi - base >= (uint32_t)kBulkTile) { // one barcode, no mask, full tile: every read is valid
 #pragma unroll
-                for (int i = 0; i < kBulkIpt; ++i) {
-                    if (label[i] < 0 || label[i] >= B) continue;
-                    const int n_extra = (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16);
-                    if (n_extra)
-                        tally_extra_layers(cx, src, out, tallies_it, it, (i64)(base + i * kBulkBlock + tid), label[i], n_extra,
-                                           st[i], (C)(st[i] + L[i]), 1, s_hot);
+                    for (int i = 0; i < kBulkIpt; ++i) {
+                        const C *g = s_grid + 2 * (int)((u64)st[i] >> cx.sgrid_shift);
+                        maybe |= (unsigned)(g[0] < (C)(st[i] + L[i]) && (!Src::kPoolLengths || st[i] < g[1])) << i;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kBulkIpt; ++i) {
+                        const bool ok = label[i] >= 0 && label[i] < B;
+                        ESL_CHK((int)((u64)st[i] >> cx.sgrid_shift) < cx.sgrid_n, "shared grid index");
+                        const C *g = s_grid + 2 * ((ok ? label[i] : 0) * cx.sgrid_n + (int)((u64)st[i] >> cx.sgrid_shift));
+                        // g[0]: first candidate's start; g[1]: largest end a read from this bucket can meet
+                        maybe |= (unsigned)(ok && g[0] < (C)(st[i] + L[i]) && (!Src::kPoolLengths || st[i] < g[1])) << i;
+                    }
                 }
-            }
-        } else { // phase 4: targets -- probe the layers for all reads, queue the "maybe"s, drain the queue converged
-            Probe<C> pt[kBulkIpt];
+                if (maybe) {
 #pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i) {
-                const bool ok = label[i] >= 0 && label[i] < B;
-                const int b = ok ? label[i] : 0;
-                const int4 dv = n_sdesc ? s_desc[b] : __ldg(reinterpret_cast<const int4 *>(cx.seg + b));
-                ESL_CHK(dv.z + (int)((u64)st[i] >> (dv.w & 0xff)) + 1 < cx.n_tgrid, "target grid index");
-                const GridEntry<C> e = load_entry(cx.tgrid + dv.z + (int)((u64)st[i] >> (dv.w & 0xff)));
-                pt[i] = Probe<C>{e.j, ok ? e.s : (C) ~(C)0};
-            }
-            int qn = 0;
+                    for (int i = 0; i < kBulkIpt; ++i)
+                        if (maybe >> i & 1)
+                            tally_first_layer(cx, src, out, tallies_it, it, (i64)(n0 + i), st[i], (C)(st[i] + L[i]), label[i], 1, s_hot);
+                }
+                if (cx.any_extra) { // the pre-filter only covers first layers
 #pragma unroll
-            for (int i = 0; i < kBulkIpt; ++i)
-                queue_push(queue, qn, pt[i].s < (C)(st[i] + L[i]), st[i], L[i], pt[i].a,
-                           (uint32_t)label[i] | (uint32_t)(i * kBulkBlock + tid) << kQueueSegBits);
-            if (cx.any_extra) { // nesting targets somewhere: layer k of every read's barcode, k ascending
-                int ne_max = 0;
+                    for (int i = 0; i < kBulkIpt; ++i) {
+                        if (label[i] < 0 || label[i] >= B) continue;
+                        const int n_extra = (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16);
+                        if (n_extra)
+                            tally_extra_layers(cx, src, out, tallies_it, it, (i64)(n0 + i), label[i], n_extra,
+                                               st[i], (C)(st[i] + L[i]), 1, s_hot);
+                    }
+                }
+            } else { // phase 4: targets -- probe the layers for all reads, queue the "maybe"s, work the queue in full rounds
+                Probe<C> pt[kBulkIpt];
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i) {
                     const bool ok = label[i] >= 0 && label[i] < B;
-                    const int ne = ok ? (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16) : 0;
-                    ne_max = ne > ne_max ? ne : ne_max;
+                    const int b = ok ? label[i] : 0;
+                    const int4 dv = n_sdesc ? s_desc[b] : __ldg(reinterpret_cast<const int4 *>(cx.seg + b));
+                    ESL_CHK(dv.z + (int)((u64)st[i] >> (dv.w & 0xff)) + 1 < cx.n_tgrid, "target grid index");
+                    const GridEntry<C> e = load_entry(cx.tgrid + dv.z + (int)((u64)st[i] >> (dv.w & 0xff)));
+                    pt[i] = Probe<C>{e.j | ((dv.w & 0x100) ? kCrowdedBit : 0), ok ? e.s : (C) ~(C)0};
                 }
-                ne_max = __reduce_max_sync(0xffffffffu, ne_max);
-                for (int k = 0; k < ne_max; ++k) {
-                    Probe<C> pe[kBulkIpt];
-                    int sg[kBulkIpt];
 #pragma unroll
-                    for (int i = 0; i < kBulkIpt; ++i) { // (layer counts re-read from shared memory: keeping them live spills)
+                for (int i = 0; i < kBulkIpt; ++i) {
+                    queue_push(queue, qn, pt[i].s < (C)(st[i] + L[i]), st[i], L[i], pt[i].a, (uint32_t)label[i], n0 + i);
+                    while (qn >= 32) queue_round(cx, src, out, tallies_it, it, queue, qn, s_hot);
+                }
+                if (cx.any_extra) { // nesting targets somewhere: layer k of every read's barcode, k ascending
+                    int ne_max = 0;
+#pragma unroll
+                    for (int i = 0; i < kBulkIpt; ++i) {
                         const bool ok = label[i] >= 0 && label[i] < B;
                         const int ne = ok ? (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16) : 0;
-                        pe[i] = Probe<C>{0, (C) ~(C)0};
-                        sg[i] = 0;
-                        if (k < ne) {
-                            sg[i] = B + __ldg(cx.extra_off + label[i]) + k;
-                            pe[i] = probe(cx.seg, sg[i], cx.tgrid, st[i]);
+                        ne_max = ne > ne_max ? ne : ne_max;
+                    }
+                    ne_max = __reduce_max_sync(0xffffffffu, ne_max);
+                    for (int k = 0; k < ne_max; ++k) {
+#pragma unroll
+                        for (int i = 0; i < kBulkIpt; ++i) { // (layer counts re-read from shared memory: keeping them live spills)
+                            const bool ok = label[i] >= 0 && label[i] < B;
+                            const int ne = ok ? (int)((uint32_t)(n_sdesc ? s_desc[label[i]].w : __ldg(&cx.seg[label[i]].flags)) >> 16) : 0;
+                            Probe<C> pe{0, (C) ~(C)0};
+                            int sg = 0;
+                            if (k < ne) {
+                                sg = B + __ldg(cx.extra_off + label[i]) + k;
+                                const int2 d = __ldg(reinterpret_cast<const int2 *>(cx.seg + sg) + 1);
+                                const GridEntry<C> e = load_entry(cx.tgrid + d.x + (int)((u64)st[i] >> (d.y & 0xff)));
+                                pe = Probe<C>{e.j | ((d.y & 0x100) ? kCrowdedBit : 0), e.s};
+                            }
+                            queue_push(queue, qn, pe.s < (C)(st[i] + L[i]), st[i], L[i], pe.a, (uint32_t)sg, n0 + i);
+                            while (qn >= 32) queue_round(cx, src, out, tallies_it, it, queue, qn, s_hot);
                         }
                     }
-                    if (qn > kQueueCap - 32 * kBulkIpt) queue_drain(cx, src, out, tallies_it, it, base, queue, qn, s_hot);
-#pragma unroll
-                    for (int i = 0; i < kBulkIpt; ++i)
-                        queue_push(queue, qn, pe[i].s < (C)(st[i] + L[i]), st[i], L[i], pe[i].a,
-                                   (uint32_t)sg[i] | (uint32_t)(i * kBulkBlock + tid) << kQueueSegBits);
                 }
             }
-            queue_drain(cx, src, out, tallies_it, it, base, queue, qn, s_hot);
-        }
-        my = warp_sum_redux(my); // phase 5: tile sum (read only when the cut-off has to be taken back)
-        if (lane == 0) {
-            ESL_CHK(t >= 0 && t < out.tiles_per_iter, "tile sum index");
-            if (my) atomicAdd(tile_sum_it + t, my);
-            acc_bases += my;
-        }
-        if (tid == 0) {
-            const uint32_t left = hi - base;
-            acc_reads += left < (uint32_t)kBulkTile ? left : (uint32_t)kBulkTile;
+            my = warp_sum_redux(my); // phase 5: tile sum (read only when the cut-off has to be taken back)
+            if (lane == 0) {
+                ESL_CHK(t >= 0 && t < out.tiles_per_iter, "tile sum index");
+                if (my) atomicAdd(tile_sum_it + t, my);
+                acc_bases += my;
+            }
+            if (tid == 0) {
+                const uint32_t left = hi - base;
+                acc_reads += left < (uint32_t)kBulkTile ? left : (uint32_t)kBulkTile;
+            }
         }
     }
-    __syncthreads();
-    if (s_hot) flush_hot(s_hot, cx.n_hot, tallies_it);
-    for (int i = tid; i < B + 2; i += kBulkBlock)
-        if (s_hist[i]) atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]);
-    if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
-    if (tid == 0 && acc_reads) {
-        atomicAdd(out.n_reads + it, acc_reads);
-        if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
-    }
+    leave_iteration();
 }
 
 // With blocked regions and consuming = False a blocked draw adds nothing to the covered length

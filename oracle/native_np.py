@@ -50,16 +50,30 @@ def cdf_thresholds(cdf):
 
 
 def native_draws(seed, combo, iteration, n, genome_size, pool, cdf):
-    """Draws 0..n-1 of one iteration: (length, start, barcode) as int64 arrays."""
+    """Draws 0..n-1 of one iteration: (length, start, barcode) as int64 arrays (kernels.cuh PhiloxSrc).
+    32-bit coordinates (genome_size <= 2^32 - 16): draw n takes the 64 bits (a, b) = words (x, y) / (z, w) of block
+    (n >> 1, 0) for even / odd n -- length = pool[(b >> 8) * n_pool >> 24], start = floor((a * 2^32 + (b & 0xff) * 2^24)
+    * (G - L) / 2^64) -- and its barcode uniform is word n & 3 of block (n >> 2, 1).  64-bit coordinates: draw n owns
+    block (n, 0): (x, y) = start, z = length pick, w = barcode."""
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     idx = np.arange(n, dtype=np.uint64)
-    x, y, z, w = philox4x32_10(idx, 0, iteration, (combo << 4) | SLOT_PLACE, k0, k1)
     pool = np.asarray(pool, np.uint64)
-    L = pool[((z * np.uint64(pool.size)) >> np.uint64(32)).astype(np.int64)]
-    start = mulhi64((x << np.uint64(32)) | y, np.uint64(genome_size) - L)
+    slot = (combo << 4) | SLOT_PLACE
+    if genome_size <= 0xFFFFFFF0:
+        x, y, z, w = philox4x32_10(idx >> np.uint64(1), 0, iteration, slot, k0, k1)
+        odd = (idx & np.uint64(1)).astype(bool)
+        a, b = np.where(odd, z, x), np.where(odd, w, y)
+        L = pool[(((b & np.uint64(0xFFFFFF00)) * np.uint64(pool.size)) >> np.uint64(32)).astype(np.int64)]
+        start = mulhi64((a << np.uint64(32)) | ((b & np.uint64(0xFF)) << np.uint64(24)), np.uint64(genome_size) - L)
+        q = philox4x32_10(idx >> np.uint64(2), 1, iteration, slot, k0, k1)
+        u = np.choose((idx & np.uint64(3)).astype(np.int64), q)
+    else:
+        x, y, z, u = philox4x32_10(idx, 0, iteration, slot, k0, k1)
+        L = pool[((z * np.uint64(pool.size)) >> np.uint64(32)).astype(np.int64)]
+        start = mulhi64((x << np.uint64(32)) | y, np.uint64(genome_size) - L)
     thr = cdf_thresholds(cdf)
     B = thr.size
-    bc = np.minimum(np.searchsorted(thr[:B - 1], w, side="right"), B - 1) if B > 1 else np.zeros(n, np.int64)
+    bc = np.minimum(np.searchsorted(thr[:B - 1], u, side="right"), B - 1) if B > 1 else np.zeros(n, np.int64)
     return L.astype(np.int64), start.astype(np.int64), bc.astype(np.int64)
 
 
