@@ -333,7 +333,13 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
         const int n_sl = n_thr;
         const size_t per = (n_all + n_sl - 1) / std::max(n_sl, 1);
         std::vector<size_t> cnt((size_t)n_sl * B, 0);
-        auto valid = [&](size_t i) { const int32_t b = ctx->t_bc[i]; return b >= 0 && b < B && ctx->t_end[i] > ctx->t_start[i]; };
+        // indexed: targets some read can overlap -- a known barcode, not empty, and starting inside the genome (a read ends
+        // before G; insertion coordinates pushed past G by later insertions, create_insertion_genome.py:60-64, keep their
+        // all-zero rows but would crowd the last grid bucket)
+        auto valid = [&](size_t i) {
+            const int32_t b = ctx->t_bc[i];
+            return b >= 0 && b < B && ctx->t_end[i] > ctx->t_start[i] && (u64)ctx->t_start[i] < G;
+        };
         parallel_for(n_sl, n_thr, [&](int sl) {
             size_t *c = cnt.data() + (size_t)sl * B;
             for (size_t i = sl * per, e = std::min(n_all, (sl + 1) * per); i < e; ++i)
@@ -547,12 +553,12 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
         const double v = std::ceil(ctx->cdf[k] * 4294967296.0);
         cu[k] = v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
     }
-    std::vector<uint16_t> lut(esl::kCdfLut);
+    std::vector<uint2> lut(esl::kCdfLut);
     int k = 0, walk = 0;
     for (int q = 0; q < esl::kCdfLut; ++q) {
         const uint32_t w = (uint32_t)q << 22; // lowest draw of the slice
         while (k < B - 1 && cu[k] <= w) ++k;
-        lut[q] = (uint16_t)k;
+        lut[q] = make_uint2((uint32_t)k | (k < B - 1 ? 0x10000u : 0u), k < B - 1 ? cu[k] : 0xFFFFFFFFu);
         const uint32_t w_hi = w | 0x3FFFFFu; // highest draw of the slice
         int k2 = k;
         while (k2 < B - 1 && cu[k2] <= w_hi) ++k2;
@@ -561,7 +567,7 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
     ctx->cdf_walk = walk;
     CU(ctx->d_cdf.upload(ctx->cdf.data(), B * sizeof(double), st));
     CU(ctx->d_cdf_u32.upload(cu.data(), B * sizeof(uint32_t), st));
-    CU(ctx->d_cdf_lut.upload(lut.data(), lut.size() * sizeof(uint16_t), st));
+    CU(ctx->d_cdf_lut.upload(lut.data(), lut.size() * sizeof(uint2), st));
     tm.mark("blocked groups + cdf");
     return ESL_OK;
 }
@@ -608,7 +614,7 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.pool = ctx->d_pool.as<uint32_t>();
     d.cdf = ctx->d_cdf.as<double>();
     d.cdf_u32 = ctx->d_cdf_u32.as<uint32_t>();
-    d.cdf_lut = ctx->d_cdf_lut.as<uint16_t>();
+    d.cdf_lut = ctx->d_cdf_lut.as<uint2>();
     d.cdf_walk = ctx->cdf_walk;
     d.min_ov32 = min_overlap <= 0 ? 0u : (min_overlap > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)min_overlap);
     d.thin = scaling < 1.0;
@@ -652,7 +658,7 @@ size_t bulk_smem(const esl_ctx *ctx)
 {
     return esl::bulk_smem_layout(ctx->wide ? 8 : 4, ctx->n_mask > 0, ctx->sgrid_n > 0, ctx->n_hot > 0, ctx->B, ctx->sgrid_n).total;
 }
-size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 2 + 16; }
+size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 8 + 24; }
 
 // Upper bound on the draws per iteration any bulk pass may cover.  Without a mask (or with consuming = True)
 // every draw counts and the first-pass bound n1 is already tight.  With a mask a blocked draw may count nothing,
@@ -690,7 +696,7 @@ int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const es
     const i64 total_tiles = r.tiles * n_iter;
     if (total_tiles <= 0) return ESL_OK;
     // one instantiation per (blocked regions?, small target set with a shared pre-filter?, hot targets?)
-    using Kern = void (*)(esl::DevCtx<C>, Src, esl::DevOut, const i64 *, i64, const i64 *, i64, int, int, i64, u64 *);
+    using Kern = void (*)(esl::DevCtx<C>, Src, esl::DevOut, const i64 *, i64, const i64 *, i64, int, int, int, u64 *);
     static const Kern table[8] = {
         esl::k_place_tally_bulk<C, Src, false, false, false>, esl::k_place_tally_bulk<C, Src, false, false, true>,
         esl::k_place_tally_bulk<C, Src, false, true, false>,  esl::k_place_tally_bulk<C, Src, false, true, true>,
@@ -703,14 +709,14 @@ int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const es
     if (occ < 1) occ = 1;
     const i64 grid = std::min<i64>((total_tiles + esl::kBulkClaim - 1) / esl::kBulkClaim, (i64)ctx->sm_count * occ);
     kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx), st>>>(dc, src, out, r.lo_arr, r.lo_const, r.hi_arr, r.hi_const,
-                                                                      (int)r.tile0, (int)r.tiles, total_tiles, d_sched);
+                                                                      (int)r.tile0, (int)r.tiles, n_iter, d_sched);
     CU(cudaGetLastError());
     ctx->launches++;
     return ESL_OK;
 }
 
-// Workspace layout: [tile sums: tiles * n_iter u64][second-pass ranges: 2 * n_iter i64][tile counters of the two bulk
-// launches: 2 u64]
+// Workspace layout: [tile sums: tiles * n_iter u64][second-pass ranges: 2 * n_iter i64][per-iteration tile counters of
+// the two bulk launches: 2 * n_iter u64]
 struct Workspace {
     u64 *tile_sum;
     i64 *range;
@@ -718,7 +724,7 @@ struct Workspace {
     size_t tile_bytes;
 };
 size_t ws_tile_bytes(i64 cap, int n_iter) { return (size_t)((cap + esl::kBulkTile - 1) / esl::kBulkTile) * (size_t)n_iter * sizeof(u64); }
-size_t ws_total_bytes(i64 cap, int n_iter) { return ((ws_tile_bytes(cap, n_iter) + 15) & ~(size_t)15) + (size_t)(2 * n_iter + 2) * sizeof(i64) + 64; }
+size_t ws_total_bytes(i64 cap, int n_iter) { return ((ws_tile_bytes(cap, n_iter) + 15) & ~(size_t)15) + (size_t)(4 * n_iter + 2) * sizeof(i64) + 64; }
 Workspace ws_carve(void *d_ws, i64 cap, int n_iter)
 {
     Workspace w;
@@ -741,7 +747,7 @@ int launch_pipeline(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, esl:
     out.tiles_per_iter = (int)((std::max(n1, n_cap) + T - 1) / T);
     const bool prof = ctx->profiling && ctx->ev[0];
     ctx->ev_valid = false;
-    CU(cudaMemsetAsync(ws.sched, 0, 2 * sizeof(u64), st));
+    CU(cudaMemsetAsync(ws.sched, 0, 2 * (size_t)n_iter * sizeof(u64), st));
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
     int rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{nullptr, 0, nullptr, n1, 0, (n1 + T - 1) / T}, n_iter, ws.sched, st);
     if (rc) return rc;
@@ -752,7 +758,7 @@ int launch_pipeline(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, esl:
         esl::k_plan_second_pass<<<(n_iter + 127) / 128, 128, 0, st>>>(out.n_bases, n_iter, dc.thr, n1, n_cap, m2, 8.0, d_lo, d_hi2);
         CU(cudaGetLastError());
         ctx->launches++;
-        rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{d_lo, 0, d_hi2, 0, n1 / T, (n_cap - n1) / T}, n_iter, ws.sched + 1, st);
+        rc = launch_bulk<C, Src>(ctx, dc, src, out, BulkRange{d_lo, 0, d_hi2, 0, n1 / T, (n_cap - n1) / T}, n_iter, ws.sched + n_iter, st);
         if (rc) return rc;
         d_hi = d_hi2;
     }
@@ -1085,7 +1091,7 @@ int esl_run_batch_staged(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t i
     int *n_dev = (int *)(digit_tot + 256);
     const esl::DevCtx<uint32_t> dc = make_devctx<uint32_t>(ctx, coverage, consuming, min_overlap, 1.0);
     const i64 T = (i64)ctx->t_start.size();
-    const size_t gen_smem = (size_t)ctx->B * 4 + (size_t)esl::kCdfLut * 2 + 16;
+    const size_t gen_smem = (size_t)ctx->B * 4 + (size_t)esl::kCdfLut * 8 + 24;
     const bool prof = ctx->profiling && ctx->ev[0];
     ctx->ev_valid = false;
     if (prof) CU(cudaEventRecord(ctx->ev[0], st));
@@ -1188,7 +1194,7 @@ int esl_materialize_reads(esl_ctx *ctx, uint64_t seed, uint32_t combo, uint32_t 
     cudaStream_t st = (cudaStream_t)stream;
     esl::PhiloxSrc src{(uint32_t)seed, (uint32_t)(seed >> 32), combo, iteration, philox_keys((uint32_t)seed, (uint32_t)(seed >> 32))};
     const unsigned grid = (unsigned)std::min<i64>((n_reads + 255) / 256, (i64)ctx->sm_count * 8);
-    const size_t sm = (size_t)ctx->B * 4 + (size_t)esl::kCdfLut * 2 + 16;
+    const size_t sm = (size_t)ctx->B * 4 + (size_t)esl::kCdfLut * 8 + 24;
     if (ctx->wide)
         esl::k_materialize<uint64_t><<<grid, 256, sm, st>>>(make_devctx<uint64_t>(ctx, 0.0, consuming, 1, 1.0), src, n_reads, d_start, d_length, d_label);
     else

@@ -157,7 +157,7 @@ struct DevCtx {
     const uint32_t *__restrict__ pool;    // length table (K2)
     const double *__restrict__ cdf;       // numpy-style cdf, replay path
     const uint32_t *__restrict__ cdf_u32; // ceil(cdf * 2^32) saturated, native path
-    const uint16_t *__restrict__ cdf_lut; // [kCdfLut] barcode of the lowest u32 in each of kCdfLut equal slices
+    const uint2 *__restrict__ cdf_lut;    // [kCdfLut] per slice of 2^22 draws: {barcode k of the slice's lowest draw | (k < B-1) << 16, threshold cdf_u32[k]}
     int cdf_walk;                         // most thresholds inside one slice (steps the walk after the table needs)
     uint32_t min_ov32;                    // min_overlap clamped to [0, 2^32-1] (an overlap never exceeds a read length)
     int thin;                             // scaling < 1: draw a thinning uniform per qualifying pair
@@ -231,13 +231,13 @@ struct PhiloxSrc {
         return philox4x32_10(c0, c1, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, keys);
     }
     template <typename C>
-    static __device__ __forceinline__ int barcode_of(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint16_t *s_lut, uint32_t w)
+    static __device__ __forceinline__ int barcode_of(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint2 *s_lut, uint32_t w)
     {
         // searchsorted(cdf, u, side='right') on integer thresholds: table start + short walk.  A slice of the start
         // table holds at most cx.cdf_walk thresholds: one branch-free step covers almost every CDF; the loop only
         // exists for more than ~1000 barcodes or pathological weights
-        int k = s_lut[w >> 22];
-        k += (k < cx.n_barcodes - 1 && s_cdf[k] <= w) ? 1 : 0;
+        const uint2 e = s_lut[w >> 22]; // one 8-byte load: start barcode, whether a step is possible, and its threshold
+        int k = (int)(e.x & 0xffffu) + (int)((e.x >> 16) & (e.y <= w ? 1u : 0u));
         if (cx.cdf_walk > 1)
             while (k < cx.n_barcodes - 1 && s_cdf[k] <= w) ++k;
         return k;
@@ -258,7 +258,7 @@ struct PhiloxSrc {
 
     // One draw (cut-off kernel, partial tiles, materialisation).
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint16_t *s_lut, int it, i64 n,
+    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint2 *s_lut, int it, i64 n,
                                          uint32_t &L, C &start, int &bc) const
     {
         bc = 0;
@@ -278,7 +278,7 @@ struct PhiloxSrc {
     }
     // Four consecutive draws n0 .. n0+3 (n0 a multiple of 4): the bulk kernel's full tiles.
     template <typename C>
-    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint16_t *s_lut, int it, uint32_t n0,
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint2 *s_lut, int it, uint32_t n0,
                                           uint32_t (&L)[4], C (&start)[4], int (&bc)[4]) const
     {
         if constexpr (sizeof(C) == 4) {
@@ -326,7 +326,7 @@ struct DrawSrc {
     __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
 
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *, const uint16_t *, int it, i64 n, uint32_t &L,
+    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *, const uint2 *, int it, i64 n, uint32_t &L,
                                          C &st, int &bc) const
     {
         const i64 g = seg[it] + n;
@@ -338,7 +338,7 @@ struct DrawSrc {
         bc = k;
     }
     template <typename C>
-    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *c, const uint16_t *l, int it, uint32_t n0,
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *c, const uint2 *l, int it, uint32_t n0,
                                           uint32_t (&L)[4], C (&st)[4], int (&bc)[4]) const
     {
 #pragma unroll
@@ -360,7 +360,7 @@ struct ReadSrc {
     __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
 
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &, const uint32_t *, const uint16_t *, int it, i64 n, uint32_t &L,
+    __device__ __forceinline__ void draw(const DevCtx<C> &, const uint32_t *, const uint2 *, int it, i64 n, uint32_t &L,
                                          C &st, int &bc) const
     {
         const i64 g = seg[it] + n;
@@ -369,7 +369,7 @@ struct ReadSrc {
         bc = label[g];
     }
     template <typename C>
-    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *c, const uint16_t *l, int it, uint32_t n0,
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *c, const uint2 *l, int it, uint32_t n0,
                                           uint32_t (&L)[4], C (&st)[4], int (&bc)[4]) const
     {
 #pragma unroll
@@ -725,7 +725,7 @@ __host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool ma
     o.mqueue = w; w += mask ? (warps * kMaskQueueCap * item + 7) / 8 : 0;
     o.mflags = w; w += mask ? warps * kBulkIpt * 4 / 8 : 0;
     o.hot = w; w += hot ? kHotWords / 2 : 0;
-    o.lut = w; w += kCdfLut * 2 / 8;
+    o.lut = w; w += kCdfLut;
     o.sched = w; w += 2;
     o.sgrid = w; w += ((size_t)(shared ? 2 * B * sgrid_n : 0) * coord_bytes + 15) / 16 * 2;
     o.desc = w; w += (size_t)(B <= kSmemDescs ? B : 0) * 2;
@@ -739,21 +739,25 @@ __host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool ma
 
 // One launch covers the absolute tiles [tile0, tile0 + tiles_launch) of every iteration; inside that window iteration
 // `it` owns the draws [lo(it), hi(it)) (lo is a multiple of the tile size).  Draw indices are < 2^32 (checked on the
-// host).  The (iteration, tile) pairs are numbered iteration-major and handed out IN ORDER, kBulkClaim at a time, from
-// a counter in global memory (`sched`, zeroed by the host call): all CTAs work on neighbouring tiles, i.e. on one or
-// two iterations at a time, so the tally rows the atomics hit (config 3: 5.8 MB per iteration) stay in L2 instead of
-// being read-modified-written in HBM, and no CTA is left with a long tail.
+// host).  Scheduling: every iteration has a tile counter in global memory (`sched[it]`, zeroed by the host call) from
+// which CTAs claim kBulkClaim tiles at a time.  The CTAs are split into kIterSlots groups; group s works through the
+// iterations s, s + kIterSlots, ... one after the other, so only a handful of iterations are in flight at any time:
+// the tally rows their atomics hit (config 3: 5.8 MB per iteration) stay in L2 instead of being read-modified-written
+// in HBM, a CTA changes iteration (flushes its histogram, empties its queue) only every few hundred tiles, and the
+// dynamic claims leave no CTA with a long tail.  A group that runs out of iterations takes what is left of the others'.
 //
 // A thread resolves its four consecutive draws in PHASES, each phase running over all its reads before the next
 // starts, so the dependent memory accesses of different reads overlap (pool gather -> start -> grid entry are two L2
 // round trips per read; the reads of a thread being in flight together hides them):
 //   1 draw  2 blocked probes, queue, drain  3 label histogram  4 target probes, queue, rounds  5 tile sum
-// Warps only meet when the CTA claims tiles or moves to the next iteration and flushes its shared label histogram.
+// Warps only meet when the CTA claims tiles (one barrier, the next claim is fetched while the current one is worked
+// on) or moves to the next iteration and flushes its shared label histogram.
+constexpr int kIterSlots = 4;
 template <typename C, typename Src, bool kMask, bool kShared, bool kHot>
 __global__ void __launch_bounds__(kBulkBlock, bulk_min_blocks<C, kShared>())
 k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src src, const DevOut out, const i64 *__restrict__ lo_arr,
                    const i64 lo_const, const i64 *__restrict__ hi_arr, const i64 hi_const, const int tile0,
-                   const int tiles_launch, const i64 total_tiles, u64 *__restrict__ sched)
+                   const int tiles_launch, const int n_iter, u64 *__restrict__ sched)
 {
     extern __shared__ u64 smem[];
     const int B = cx.n_barcodes;
@@ -765,8 +769,8 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     // private tallies of the hot targets + their rows (kHot: the host flagged some; otherwise the null pointer is a
     // compile-time constant and every hot-target branch below folds away)
     uint32_t *const s_hot = kHot ? (uint32_t *)(smem + lay.hot) : nullptr;
-    uint16_t *const s_lut = (uint16_t *)(smem + lay.lut);       // [kCdfLut]
-    i64 *const s_sched = (i64 *)(smem + lay.sched);             // the claimed range, broadcast to the CTA
+    uint2 *const s_lut = (uint2 *)(smem + lay.lut);             // [kCdfLut]
+    i64 *const s_sched = (i64 *)(smem + lay.sched);             // [2] the claimed tile, broadcast to the CTA
     C *const s_grid = (C *)(smem + lay.sgrid);                  // [B][sgrid_n] pairs (small target sets)
     int4 *const s_desc = (int4 *)(smem + lay.desc);             // [min(B, kSmemDescs)] first-layer descriptors
     const int n_sdesc = B <= kSmemDescs ? B : 0;
@@ -784,55 +788,37 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
         for (int i = tid; i < B; i += kBulkBlock) s_cdf[i] = cx.cdf_u32[i];
         for (int i = tid; i < kCdfLut; i += kBulkBlock) s_lut[i] = cx.cdf_lut[i];
     }
+    __syncthreads();
 
     const bool plain_labels = !Src::kHasLabel && B == 1 && !kMask; // every read is label 0
     u64 acc_bases = 0, acc_reads = 0; // lane 0 of each warp / thread 0
-    uint32_t lo = 0, hi = 0;
-    u64 *tallies_it = nullptr;
-    u64 *tile_sum_it = nullptr;
-    int it = -1, qn = 0, hot_tiles = 0;
+    int qn = 0, hot_tiles = 0, parity = 0;
 
-    // what the CTA gathered for iteration `it`: empty the walk queues, flush histogram / sums (all threads)
-    auto leave_iteration = [&]() {
-        if (it < 0) return;
-        if (!kShared)
-            while (qn > 0) queue_round(cx, src, out, tallies_it, it, queue, qn, s_hot);
-        __syncthreads();
-        if (s_hot) { flush_hot(s_hot, cx.n_hot, tallies_it); hot_tiles = 0; }
-        for (int i = tid; i < B + 2; i += kBulkBlock)
-            if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
-        if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
-        if (tid == 0 && acc_reads) {
-            atomicAdd(out.n_reads + it, acc_reads);
-            if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
-        }
-        acc_bases = acc_reads = 0;
-        __syncthreads();
-    };
-
-    for (;;) {
-        __syncthreads(); // (also orders the set-up above before the first tile)
-        if (tid == 0) s_sched[0] = (i64)atomicAdd(sched, (u64)kBulkClaim);
-        __syncthreads();
-        const i64 g0 = s_sched[0];
-        if (g0 >= total_tiles) break;
-        const i64 g1 = g0 + kBulkClaim < total_tiles ? g0 + kBulkClaim : total_tiles;
-        int git = (int)(g0 / tiles_launch);
-        int t = (int)(g0 - (i64)git * tiles_launch) + tile0;
-        for (i64 g = g0; g < g1; ++g, ++t) {
-            if (t == tile0 + tiles_launch) { ++git; t = tile0; } // the claim runs on into the next iteration
-            if (git != it) { // (block-uniform)
-                leave_iteration();
-                it = git;
-                i64 l = lo_arr ? lo_arr[it] : lo_const, h = hi_arr ? hi_arr[it] : hi_const;
-                if (Src::kBounded) { const i64 c = src.count(it); h = h < c ? h : c; }
-                lo = (uint32_t)l;
-                hi = (uint32_t)(h > l ? h : l);
-                tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
-                tile_sum_it = out.tile_sum + (i64)it * out.tiles_per_iter;
-            }
+    // Claim and process tiles of iteration `it` until its counter runs out; returns whether this CTA got any (all threads).
+    auto run_iteration = [&](const int it) -> bool {
+        i64 l = lo_arr ? lo_arr[it] : lo_const, h = hi_arr ? hi_arr[it] : hi_const;
+        if (Src::kBounded) { const i64 c = src.count(it); h = h < c ? h : c; }
+        const uint32_t lo = (uint32_t)l, hi = (uint32_t)(h > l ? h : l);
+        u64 *const tallies_it = out.tallies + (i64)it * cx.n_targets * 3;
+        u64 *const tile_sum_it = out.tile_sum + (i64)it * out.tiles_per_iter;
+        // tiles of the window that hold draws of this iteration: [t_lo, t_hi) relative to tile0
+        const int t_lo = lo > (uint32_t)tile0 * kBulkTile ? (int)(lo / kBulkTile) - tile0 : 0;
+        i64 t_end = ((i64)hi + kBulkTile - 1) / kBulkTile - tile0;
+        const int t_hi = (int)(t_end < 0 ? 0 : (t_end > tiles_launch ? tiles_launch : t_end));
+        bool any = false;
+        i64 next = 0;
+        if (tid == 0) next = t_lo + (i64)atomicAdd(sched + it, (u64)kBulkClaim);
+        for (;;) {
+            if (tid == 0) s_sched[parity] = next;
+            __syncthreads();
+            const i64 g0 = s_sched[parity];
+            parity ^= 1;
+            if (g0 >= t_hi) break;
+            if (tid == 0) next = t_lo + (i64)atomicAdd(sched + it, (u64)kBulkClaim); // fetched while this claim is worked on
+            any = true;
+            const int g1 = (int)(g0 + kBulkClaim < t_hi ? g0 + kBulkClaim : t_hi);
+            for (int t = (int)g0 + tile0; t < g1 + tile0; ++t) {
             const uint32_t base = (uint32_t)t * kBulkTile;
-            if (base < lo || base >= hi) continue; // tile outside this iteration's range (block-uniform)
             if (s_hot && ++hot_tiles == kHotFlushTiles) { // (block-uniform)
                 __syncthreads();
                 flush_hot(s_hot, cx.n_hot, tallies_it);
@@ -997,9 +983,36 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 const uint32_t left = hi - base;
                 acc_reads += left < (uint32_t)kBulkTile ? left : (uint32_t)kBulkTile;
             }
+            } // tiles of the claim
         }
+        if (!any) return false; // (block-uniform: nothing gathered, nothing to flush)
+        // what the CTA gathered for this iteration: empty the walk queue, flush histogram / sums
+        if (!kShared)
+            while (qn > 0) queue_round(cx, src, out, tallies_it, it, queue, qn, s_hot);
+        __syncthreads();
+        if (s_hot) { flush_hot(s_hot, cx.n_hot, tallies_it); hot_tiles = 0; }
+        for (int i = tid; i < B + 2; i += kBulkBlock)
+            if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
+        if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
+        if (tid == 0 && acc_reads) {
+            atomicAdd(out.n_reads + it, acc_reads);
+            if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
+        }
+        acc_bases = acc_reads = 0;
+        __syncthreads();
+        return true;
+    };
+
+    const int n_slots = n_iter < kIterSlots ? n_iter : kIterSlots;
+    const int slot = (int)(blockIdx.x % (unsigned)n_slots);
+    for (int it = slot; it < n_iter; it += n_slots) run_iteration(it);
+    // leftovers of the other groups: their iterations are consumed in order, so walking a group's list backwards until an
+    // iteration yields nothing visits everything that can still hold unclaimed tiles
+    for (int s2 = 1; s2 < n_slots; ++s2) {
+        const int other = (slot + s2) % n_slots;
+        for (int it = other + (n_iter - 1 - other) / n_slots * n_slots; it >= 0; it -= n_slots)
+            if (!run_iteration(it)) break;
     }
-    leave_iteration();
 }
 
 // With blocked regions and consuming = False a blocked draw adds nothing to the covered length
@@ -1059,7 +1072,7 @@ k_cutoff_tail(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src 
     u64 *s_warp = smem;                         // [33]
     int *s_hist = (int *)(smem + 40);           // [B + 2] signed deltas to the label counts
     uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2);
-    uint16_t *s_lut = (uint16_t *)(s_cdf + cx.n_barcodes);
+    uint2 *s_lut = (uint2 *)(((uintptr_t)(s_cdf + cx.n_barcodes) + 7) & ~(uintptr_t)7);
     __shared__ i64 s_cut_tile;
     __shared__ u64 s_cut_prefix;
     const int tid = threadIdx.x;
@@ -1180,7 +1193,7 @@ k_materialize(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Phil
 {
     extern __shared__ u64 smem[];
     uint32_t *s_cdf = (uint32_t *)smem;
-    uint16_t *s_lut = (uint16_t *)(s_cdf + cx.n_barcodes);
+    uint2 *s_lut = (uint2 *)(((uintptr_t)(s_cdf + cx.n_barcodes) + 7) & ~(uintptr_t)7);
     for (int i = threadIdx.x; i < cx.n_barcodes; i += blockDim.x) s_cdf[i] = cx.cdf_u32[i];
     for (int i = threadIdx.x; i < kCdfLut; i += blockDim.x) s_lut[i] = cx.cdf_lut[i];
     __syncthreads();

@@ -25,7 +25,7 @@ k_stage_generate(const __grid_constant__ DevCtx<uint32_t> cx, const __grid_const
 {
     extern __shared__ u64 smem[];
     uint32_t *s_cdf = (uint32_t *)smem;
-    uint16_t *s_lut = (uint16_t *)(s_cdf + cx.n_barcodes);
+    uint2 *s_lut = (uint2 *)(((uintptr_t)(s_cdf + cx.n_barcodes) + 7) & ~(uintptr_t)7);
     __shared__ u64 s_part[kStageBlock / 32];
     if (cx.n_barcodes > 1) {
         for (int i = threadIdx.x; i < cx.n_barcodes; i += kStageBlock) s_cdf[i] = cx.cdf_u32[i];
