@@ -86,6 +86,8 @@ struct esl_ctx {
     DevBuf d_sgrid;
     struct esl_host_scratch *host = nullptr; // persistent host-side scratch of esl_prepare (defined below)
     int sgrid_n = 0, sgrid_shift = 0; // shared-memory copy of the first-layer grids (0 = does not fit)
+    DevBuf d_mbits;
+    int mbits_shift = 0, mbits_words = 0; // blocked-bucket bitmap (kernels.cuh DevCtx::mbits)
     u64 sgrid_lmax = 0;               // longest read its upper bounds were built for
 
     // optional hit-record buffer (esl_set_hit_buffer)
@@ -540,6 +542,20 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
         ms.push_back((C) ~(C)0); me.push_back((C) ~(C)0); mp.push_back((C) ~(C)0); mw.push_back(0.0);
     }
     ctx->n_mask = n_real;
+    {   // blocked-bucket bitmap: at most 64 Ki buckets (8 KB of shared memory), at least 64 kb wide
+        int sh = 16;
+        while (((G + 1) >> sh) + 1 > 65536) ++sh;
+        const size_t nbits = (size_t)((G + 1) >> sh) + 2;
+        std::vector<uint32_t> bits((nbits + 31) / 32, 0u);
+        for (size_t i = 0; i < ctx->m_start.size(); ++i) {
+            const u64 a = (u64)std::max<i64>(ctx->m_start[i], 0), e = (u64)std::max<i64>(ctx->m_end[i], 0);
+            if (e <= a || a > G) continue;
+            for (u64 b = a >> sh, b1 = (std::min<u64>(e, G + 1) - 1) >> sh; b <= b1; ++b) bits[b >> 5] |= 1u << (b & 31);
+        }
+        ctx->mbits_shift = sh;
+        ctx->mbits_words = (int)bits.size();
+        CU(ctx->d_mbits.upload(bits.data(), bits.size() * sizeof(uint32_t), st));
+    }
     std::vector<esl::MaskRec<C>> mrec(ms.size());
     for (size_t k = 0; k < ms.size(); ++k) { mrec[k] = esl::MaskRec<C>{}; mrec[k].s = ms[k]; mrec[k].e = me[k]; mrec[k].w = mw[k]; }
     ctx->n_mgrid = (int)mgrid.size(); ctx->n_mrec = (int)mrec.size();
@@ -610,6 +626,9 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.has_mask = ctx->n_mask > 0;
     d.mask_mode = 0;
     for (int32_t b : ctx->m_bc) d.mask_mode |= b >= 0 ? 1 : 2;
+    d.mbits = ctx->d_mbits.as<uint32_t>();
+    d.mbits_shift = ctx->mbits_shift;
+    d.mbits_words = ctx->mbits_words;
     d.n_pool = ctx->n_pool;
     d.pool = ctx->d_pool.as<uint32_t>();
     d.cdf = ctx->d_cdf.as<double>();
@@ -656,7 +675,7 @@ i64 bulk_reads(const esl_ctx *ctx, double coverage)
 
 size_t bulk_smem(const esl_ctx *ctx)
 {
-    return esl::bulk_smem_layout(ctx->wide ? 8 : 4, ctx->n_mask > 0, ctx->sgrid_n > 0, ctx->n_hot > 0, ctx->B, ctx->sgrid_n).total;
+    return esl::bulk_smem_layout(ctx->wide ? 8 : 4, ctx->n_mask > 0, ctx->sgrid_n > 0, ctx->n_hot > 0, ctx->B, ctx->sgrid_n, ctx->mbits_words).total;
 }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 8 + 24; }
 

@@ -153,6 +153,11 @@ struct DevCtx {
     int consuming;
     int has_mask;
     int mask_mode; // bit 0: some barcode has a tree of its own, bit 1: the "ALL" tree holds intervals
+    // coarse bitmap over the genome, staged in shared memory by the bulk kernel: bit b is set when ANY blocked interval
+    // (of any tree) touches bucket b = position >> mbits_shift.  A read spanning at most two buckets whose bits are
+    // clear is certainly not blocked -- no global load for the bulk of the reads; everything else takes the exact test.
+    const uint32_t *__restrict__ mbits;
+    int mbits_shift, mbits_words;
     uint32_t n_pool;
     const uint32_t *__restrict__ pool;    // length table (K2)
     const double *__restrict__ cdf;       // numpy-style cdf, replay path
@@ -619,41 +624,72 @@ __device__ __forceinline__ u64 warp_incl_scan(u64 v, int lane)
 // another iteration.  The same queue type carries the reads whose blocked-interval probe said "maybe" (drained once
 // per tile: the labels are needed before the targets are looked at).
 template <typename C>
-struct WalkItem { // 20 bytes (32-bit coordinates) / 24 bytes
+struct WalkItem {
     C st;         // read start
     uint32_t L;   // read length
     int a;        // record index; bit 30 = the run is crowded and the walk has not yet skipped ahead (first visit)
     uint32_t sg;  // run (layer) index            | mask items: first candidate in the "ALL" tree (or -1)
     uint32_t n;   // draw index in the iteration  | mask items: barcode | slot in the warp's tile row << 16
 };
-constexpr int kQueueCap = 96;      // target items per warp: < 32 carried over + <= 32 pushed + <= 32 pushed back
-constexpr int kMaskQueueCap = 128; // mask items per warp: one per read of a tile row
+constexpr int kQueueCap = 64;      // target items per warp: < 32 carried over + <= 32 pushed (a round pops 32 before it pushes back)
+constexpr int kMaskQueueCap = 64;  // mask items per warp; drained early when the next 32 pushes may not fit
 constexpr int kQueueSegBits = 22;  // the host keeps the number of runs below 2^22
 constexpr int kCrowdedBit = 1 << 30;
 
+// A warp's queue in shared memory: one 16-byte record per item (a single LDS.128 / STS.128) plus a side word that
+// is only touched when somebody needs it (the draw index: hit records and pair thinning; mask items: always).
+template <typename C> struct QueueRef;
+template <> struct QueueRef<uint32_t> { // 20 bytes per item
+    uint4 *main;    // {st, L, a, sg}
+    uint32_t *side; // n
+    __device__ __forceinline__ QueueRef(void *base, int cap) : main((uint4 *)base), side((uint32_t *)((uint4 *)base + cap)) {}
+    __device__ __forceinline__ void put(int i, const WalkItem<uint32_t> &w, bool with_n) const
+    {
+        main[i] = make_uint4(w.st, w.L, (uint32_t)w.a, w.sg);
+        if (with_n) side[i] = w.n;
+    }
+    __device__ __forceinline__ WalkItem<uint32_t> get(int i, bool with_n) const
+    {
+        const uint4 v = main[i];
+        return WalkItem<uint32_t>{v.x, v.y, (int)v.z, v.w, with_n ? side[i] : 0u};
+    }
+};
+template <> struct QueueRef<uint64_t> { // 24 bytes per item
+    uint4 *main; // {st low, st high, L, a}
+    uint2 *side; // {sg, n}
+    __device__ __forceinline__ QueueRef(void *base, int cap) : main((uint4 *)base), side((uint2 *)((uint4 *)base + cap)) {}
+    __device__ __forceinline__ void put(int i, const WalkItem<uint64_t> &w, bool) const
+    {
+        main[i] = make_uint4((uint32_t)w.st, (uint32_t)(w.st >> 32), w.L, (uint32_t)w.a);
+        side[i] = make_uint2(w.sg, w.n);
+    }
+    __device__ __forceinline__ WalkItem<uint64_t> get(int i, bool) const
+    {
+        const uint4 v = main[i];
+        const uint2 t = side[i];
+        return WalkItem<uint64_t>{(uint64_t)v.x | (uint64_t)v.y << 32, v.z, (int)v.w, t.x, t.y};
+    }
+};
+
 // Called by all 32 lanes; n (the queue length) is warp-uniform.
 template <typename C>
-__device__ __forceinline__ void queue_push(WalkItem<C> *q, int &n, bool want, C st, uint32_t L, int a, uint32_t sg, uint32_t dn)
+__device__ __forceinline__ void queue_push(const QueueRef<C> &q, int &n, bool want, C st, uint32_t L, int a, uint32_t sg, uint32_t dn, bool with_n)
 {
     const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (want) {
-        WalkItem<C> w;
-        w.st = st; w.L = L; w.a = a; w.sg = sg; w.n = dn;
-        q[n + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = w;
-    }
+    if (want) q.put(n + __popc(m & ((1u << (threadIdx.x & 31)) - 1u)), WalkItem<C>{st, L, a, sg, dn}, with_n);
     n += __popc(m);
 }
 
 // One round: pop up to 32 items, one record visit per lane, push the walks that go on.
 template <typename C, typename Src>
 __device__ __forceinline__ void queue_round(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
-                                            int it, WalkItem<C> *q, int &n, uint32_t *s_hot)
+                                            int it, const QueueRef<C> &q, int &n, bool with_n, uint32_t *s_hot)
 {
     const int lane = threadIdx.x & 31;
     const int take = n < 32 ? n : 32;
     const bool on = lane < take;
-    WalkItem<C> w;
-    if (on) w = q[n - take + lane];
+    WalkItem<C> w{};
+    if (on) w = q.get(n - take + lane, with_n);
     __syncwarp();
     n -= take;
     bool more = false;
@@ -677,7 +713,7 @@ __device__ __forceinline__ void queue_round(const DevCtx<C> &cx, const Src &src,
         }
     }
     const unsigned m = __ballot_sync(0xffffffffu, more);
-    if (more) q[n + __popc(m & ((1u << lane) - 1u))] = w;
+    if (more) q.put(n + __popc(m & ((1u << lane) - 1u)), w, with_n);
     n += __popc(m);
     __syncwarp();
 }
@@ -714,9 +750,9 @@ __device__ __forceinline__ bool blocked_from(const DevCtx<C> &cx, const Src &src
 // Shared-memory layout of the bulk kernel, in 8-byte words, one definition for host (size) and device (offsets).
 // The arrays of compile-time size come first, so the hot ones sit at constant addresses.
 struct BulkSmem {
-    size_t queue, mqueue, mflags, hot, lut, sched, sgrid, desc, hist, cdf, total; // word offsets; total in BYTES
+    size_t queue, mqueue, mflags, hot, lut, sched, sgrid, desc, hist, cdf, mbits, total; // word offsets; total in BYTES
 };
-__host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool mask, bool shared, bool hot, int B, int sgrid_n)
+__host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool mask, bool shared, bool hot, int B, int sgrid_n, int mbits_words)
 {
     const size_t item = coord_bytes == 4 ? 20 : 24, warps = kBulkBlock / 32;
     BulkSmem o;
@@ -725,12 +761,13 @@ __host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool ma
     o.mqueue = w; w += mask ? (warps * kMaskQueueCap * item + 7) / 8 : 0;
     o.mflags = w; w += mask ? warps * kBulkIpt * 4 / 8 : 0;
     o.hot = w; w += hot ? kHotWords / 2 : 0;
-    o.lut = w; w += kCdfLut;
+    o.lut = w; w += B > 1 ? kCdfLut : 0; // (one barcode: no table)
     o.sched = w; w += 2;
     o.sgrid = w; w += ((size_t)(shared ? 2 * B * sgrid_n : 0) * coord_bytes + 15) / 16 * 2;
     o.desc = w; w += (size_t)(B <= kSmemDescs ? B : 0) * 2;
     o.hist = w; w += ((size_t)(B + 2) * 4 + 7) / 8;
     o.cdf = w; w += ((size_t)B * 4 + 7) / 8;
+    o.mbits = w; w += mask ? ((size_t)mbits_words * 4 + 7) / 8 : 0;
     o.total = w * 8;
     return o;
 }
@@ -761,10 +798,12 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
 {
     extern __shared__ u64 smem[];
     const int B = cx.n_barcodes;
-    const BulkSmem lay = bulk_smem_layout(sizeof(C), kMask, kShared, kHot, B, kShared ? cx.sgrid_n : 0);
+    const BulkSmem lay = bulk_smem_layout(sizeof(C), kMask, kShared, kHot, B, kShared ? cx.sgrid_n : 0, kMask ? cx.mbits_words : 0);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    WalkItem<C> *const queue = (WalkItem<C> *)(smem + lay.queue) + wid * kQueueCap;
-    WalkItem<C> *const mqueue = (WalkItem<C> *)(smem + lay.mqueue) + wid * kMaskQueueCap;
+    constexpr int kItemBytes = sizeof(C) == 4 ? 20 : 24;
+    const QueueRef<C> queue((char *)(smem + lay.queue) + wid * kQueueCap * kItemBytes, kQueueCap);
+    const QueueRef<C> mqueue((char *)(smem + lay.mqueue) + wid * kMaskQueueCap * kItemBytes, kMaskQueueCap);
+    const bool with_n = out.hits != nullptr || cx.thin; // the walks need the draw index only for hit records / thinning
     uint32_t *const mflags = (uint32_t *)(smem + lay.mflags) + wid * kBulkIpt; // bit l of word i: read i of lane l is blocked
     // private tallies of the hot targets + their rows (kHot: the host flagged some; otherwise the null pointer is a
     // compile-time constant and every hot-target branch below folds away)
@@ -776,6 +815,9 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     const int n_sdesc = B <= kSmemDescs ? B : 0;
     int *const s_hist = (int *)(smem + lay.hist);               // [B + 2] reads per label since the last flush
     uint32_t *const s_cdf = (uint32_t *)(smem + lay.cdf);       // [B]
+    uint32_t *const s_mbits = (uint32_t *)(smem + lay.mbits);   // [mbits_words] blocked-bucket bitmap
+    if (kMask)
+        for (int i = tid; i < cx.mbits_words; i += kBulkBlock) s_mbits[i] = cx.mbits[i];
     const int n_sgrid = kShared ? 2 * B * cx.sgrid_n : 0;
     for (int i = tid; i < n_sgrid; i += kBulkBlock) s_grid[i] = cx.sgrid[i];
     for (int i = tid; i < n_sdesc; i += kBulkBlock) s_desc[i] = __ldg(reinterpret_cast<const int4 *>(cx.seg + i));
@@ -843,37 +885,62 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                     if (n >= hi) { L[i] = 0; label[i] = kLabelInvalid; }
                 }
             }
-            u64 my = 0;
-            if (!Src::kHasLabel && kMask) {
-                // phase 2: blocked regions -- probe the barcode's tree (if any barcode has one) and the "ALL" tree for all
-                // reads, queue the reads with a candidate, let the warp test them with all lanes busy, read the verdicts
-                int mn = 0;
+            // target probes of the general path are issued here, ahead of the blocked-region phase: both only need the
+            // read's start, so their L2 round trips overlap instead of queueing up behind each other
+            Probe<C> pt[kShared ? 1 : kBulkIpt];
+            if (!kShared) {
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i) {
-                    const C re = (C)(st[i] + L[i]);
-                    int a_bc = -1, a_all = -1;
-                    if (cx.mask_mode & 1) {
-                        const int2 d = __ldg(reinterpret_cast<const int2 *>(cx.grp + (label[i] >= 0 ? label[i] : 0)) + 1);
-                        const GridEntry<C> e = load_entry(cx.mgrid + d.x + (int)((u64)st[i] >> (d.y & 0xff)));
-                        if (e.s < re) a_bc = e.j | ((d.y & 0x100) ? kCrowdedBit : 0);
-                    }
-                    if (cx.mask_mode & 2) {
-                        const int2 d = __ldg(reinterpret_cast<const int2 *>(cx.grp + B) + 1);
-                        const GridEntry<C> e = load_entry(cx.mgrid + d.x + (int)((u64)st[i] >> (d.y & 0xff)));
-                        if (e.s < re) a_all = e.j | ((d.y & 0x100) ? kCrowdedBit : 0);
-                    }
-                    queue_push(mqueue, mn, label[i] >= 0 && (a_bc >= 0 || a_all >= 0), st[i], L[i], a_bc, (uint32_t)a_all,
-                               (uint32_t)label[i] | (uint32_t)(i * 32 + lane) << 16);
+                    const bool ok = label[i] >= 0 && label[i] < B;
+                    const int b = ok ? label[i] : 0;
+                    const int4 dv = n_sdesc ? s_desc[b] : __ldg(reinterpret_cast<const int4 *>(cx.seg + b));
+                    ESL_CHK(dv.z + (int)((u64)st[i] >> (dv.w & 0xff)) + 1 < cx.n_tgrid, "target grid index");
+                    const GridEntry<C> e = load_entry(cx.tgrid + dv.z + (int)((u64)st[i] >> (dv.w & 0xff)));
+                    pt[kShared ? 0 : i] = Probe<C>{e.j | ((dv.w & 0x100) ? kCrowdedBit : 0), ok ? e.s : (C) ~(C)0};
                 }
+            }
+            u64 my = 0;
+            // the warp tests its queued reads against the blocked intervals, all lanes busy; verdicts go to mflags
+            auto drain_mask = [&](int &mn) {
                 __syncwarp();
                 for (int k = lane; k < mn; k += 32) {
-                    const WalkItem<C> w = mqueue[k];
+                    const WalkItem<C> w = mqueue.get(k, true);
                     const int slot = (int)(w.n >> 16);
                     const int owner = slot & 31; // the draw index follows from the slot: lane `owner`, read slot >> 5
                     const uint32_t nd = base + (uint32_t)((wid * 32 + owner) * kBulkIpt + (slot >> 5));
                     if (blocked_from(cx, src, it, (i64)nd, (int)(w.n & 0xffffu), w.st, (C)(w.st + w.L), w.a, (int)w.sg))
                         atomicOr(mflags + (slot >> 5), 1u << owner);
                 }
+                __syncwarp();
+                mn = 0;
+            };
+            if (!Src::kHasLabel && kMask) {
+                // phase 2: blocked regions -- a shared-memory bitmap clears most reads without a global load; the others
+                // probe the barcode's tree (if any barcode has one) and the "ALL" tree, all four reads of the thread in
+                // flight together; reads with a candidate are queued and the warp walks them with its lanes busy
+                int mn = 0;
+                const int2 d_all = __ldg(reinterpret_cast<const int2 *>(cx.grp + B) + 1);
+#pragma unroll
+                for (int i = 0; i < kBulkIpt; ++i) {
+                    const C re = (C)(st[i] + L[i]);
+                    const uint32_t b0 = (uint32_t)((u64)st[i] >> cx.mbits_shift), b1 = (uint32_t)((u64)(re - 1) >> cx.mbits_shift);
+                    const uint32_t b1c = b1 - b0 > 1u ? b0 : b1; // (keeps the second look-up in range whatever the length)
+                    const bool maybe = b1 - b0 > 1u || (((s_mbits[b0 >> 5] >> (b0 & 31)) | (s_mbits[b1c >> 5] >> (b1c & 31))) & 1u);
+                    int a_bc = -1, a_all = -1;
+                    if (maybe && (cx.mask_mode & 1)) {
+                        const int2 d = __ldg(reinterpret_cast<const int2 *>(cx.grp + (label[i] >= 0 ? label[i] : 0)) + 1);
+                        const GridEntry<C> e = load_entry(cx.mgrid + d.x + (int)((u64)st[i] >> (d.y & 0xff)));
+                        if (e.s < re) a_bc = e.j | ((d.y & 0x100) ? kCrowdedBit : 0);
+                    }
+                    if (maybe && (cx.mask_mode & 2)) {
+                        const GridEntry<C> e = load_entry(cx.mgrid + d_all.x + (int)((u64)st[i] >> (d_all.y & 0xff)));
+                        if (e.s < re) a_all = e.j | ((d_all.y & 0x100) ? kCrowdedBit : 0);
+                    }
+                    queue_push(mqueue, mn, label[i] >= 0 && (a_bc >= 0 || a_all >= 0), st[i], L[i], a_bc, (uint32_t)a_all,
+                               (uint32_t)label[i] | (uint32_t)(i * 32 + lane) << 16, true);
+                    if (mn > kMaskQueueCap - 32) drain_mask(mn);
+                }
+                drain_mask(mn);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i) {
@@ -929,21 +996,12 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                                                st[i], (C)(st[i] + L[i]), 1, s_hot);
                     }
                 }
-            } else { // phase 4: targets -- probe the layers for all reads, queue the "maybe"s, work the queue in full rounds
-                Probe<C> pt[kBulkIpt];
+            } else { // phase 4: targets -- queue the reads whose probe said "maybe", work the queue in full rounds
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i) {
-                    const bool ok = label[i] >= 0 && label[i] < B;
-                    const int b = ok ? label[i] : 0;
-                    const int4 dv = n_sdesc ? s_desc[b] : __ldg(reinterpret_cast<const int4 *>(cx.seg + b));
-                    ESL_CHK(dv.z + (int)((u64)st[i] >> (dv.w & 0xff)) + 1 < cx.n_tgrid, "target grid index");
-                    const GridEntry<C> e = load_entry(cx.tgrid + dv.z + (int)((u64)st[i] >> (dv.w & 0xff)));
-                    pt[i] = Probe<C>{e.j | ((dv.w & 0x100) ? kCrowdedBit : 0), ok ? e.s : (C) ~(C)0};
-                }
-#pragma unroll
-                for (int i = 0; i < kBulkIpt; ++i) {
-                    queue_push(queue, qn, pt[i].s < (C)(st[i] + L[i]), st[i], L[i], pt[i].a, (uint32_t)label[i], n0 + i);
-                    while (qn >= 32) queue_round(cx, src, out, tallies_it, it, queue, qn, s_hot);
+                    // (a read the blocked-region phase relabelled keeps its probe but is not tallied)
+                    queue_push(queue, qn, label[i] >= 0 && pt[i].s < (C)(st[i] + L[i]), st[i], L[i], pt[i].a, (uint32_t)label[i], n0 + i, with_n);
+                    while (qn >= 32) queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
                 }
                 if (cx.any_extra) { // nesting targets somewhere: layer k of every read's barcode, k ascending
                     int ne_max = 0;
@@ -967,8 +1025,8 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                                 const GridEntry<C> e = load_entry(cx.tgrid + d.x + (int)((u64)st[i] >> (d.y & 0xff)));
                                 pe = Probe<C>{e.j | ((d.y & 0x100) ? kCrowdedBit : 0), e.s};
                             }
-                            queue_push(queue, qn, pe.s < (C)(st[i] + L[i]), st[i], L[i], pe.a, (uint32_t)sg, n0 + i);
-                            while (qn >= 32) queue_round(cx, src, out, tallies_it, it, queue, qn, s_hot);
+                            queue_push(queue, qn, pe.s < (C)(st[i] + L[i]), st[i], L[i], pe.a, (uint32_t)sg, n0 + i, with_n);
+                            while (qn >= 32) queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
                         }
                     }
                 }
@@ -988,7 +1046,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
         if (!any) return false; // (block-uniform: nothing gathered, nothing to flush)
         // what the CTA gathered for this iteration: empty the walk queue, flush histogram / sums
         if (!kShared)
-            while (qn > 0) queue_round(cx, src, out, tallies_it, it, queue, qn, s_hot);
+            while (qn > 0) queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
         __syncthreads();
         if (s_hot) { flush_hot(s_hot, cx.n_hot, tallies_it); hot_tiles = 0; }
         for (int i = tid; i < B + 2; i += kBulkBlock)
