@@ -253,14 +253,15 @@ def measure(args, w, steps, warmup, batches, strong_total=None, e2e_mode="tallie
     B = w["n_barcodes"]
     params = dict(n_barcodes=B, barcode_weights=w["barcode_weights"], seed=w["seed"], scaling=w["scaling"],
                   combinations=[(w["mean_read_length"], w["coverage"])], sequenced_data_path=None, sigma=w["sigma"],
-                  min_read_length=w["min_read_length"], consuming=w["consuming"], min_overlap_for_detection=w["min_overlap"])
+                  min_read_length=w["min_read_length"], consuming=w["consuming"], min_overlap_for_detection=w["min_overlap"],
+                  length_sampler=args.sampler)
     masked_tree = build_mask_tree(w["mask"]) if w["mask"] else None
     # host inputs of the end-to-end leg live in pinned memory (the set-up calls copy straight from them)
     pool = torch.from_numpy(w["pool"].astype(np.uint32)).pin_memory().numpy()
     # large target sets are handed over as columns (arrays), small ones as the reference's dict
     targets = TargetColumns.from_dict(w["targets"], B) if len(w["targets"]) > 10000 else w["targets"]
     sess.invalidate()
-    sess.configure(w["genome_size"], targets, masked_tree, B, w["barcode_weights"])
+    sess.configure(w["genome_size"], targets, masked_tree, B, w["barcode_weights"], args.sampler)
     sess.set_pool(None, lambda: pool)
     T = eng.n_targets
     if strong_total is None:
@@ -477,7 +478,7 @@ def run_ours(args, w):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32" if w["genome_size"] <= 0xFFFFFFF0 else "u64", "data": "synthetic",
                 "config": config_dict(w, world, args.batches_per_step),
-                "run": {"path": args.path, "rng": "philox4x32-10", "iterations_per_step_per_gpu": main["iterations_per_step_per_gpu"],
+                "run": {"path": args.path, "rng": "philox4x32-10", "length_sampler": args.sampler, "iterations_per_step_per_gpu": main["iterations_per_step_per_gpu"],
                         "passes_per_step": main["passes_per_step"], "reads_per_iteration": main["reads_per_iteration"],
                         "timed_region_s": main["timed_region_s"]},
                 "roofline": main["roofline"], "collective_ms": main["collective_ms"], "cpu_baseline": cpu, "e2e": main["e2e"],
@@ -499,6 +500,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-north-star", dest="north_star", action="store_false",
                     help="skip the north_star_cfg3 block (config 3, 1000 iterations sharded over the GPUs)")
+    ap.add_argument("--sampler", default="quantile", choices=["pool", "quantile"],
+                    help="read-length sampler of the native stream: uniform pick from the length pool (the reference's exact "
+                         "distribution) or the shared-memory quantile table (esl_set_length_sampler)")
     ap.add_argument("--path", default="fused", choices=["fused", "staged"],
                     help="fused = the product kernels; staged = the north star's sort + sweep pipeline kept as a measured baseline")
     args = ap.parse_args()

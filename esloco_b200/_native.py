@@ -9,6 +9,7 @@ ESL_OK = 0
 ESL_ITER_CUT_IN_BULK = 1
 ESL_ITER_EXHAUSTED = 2
 ESL_MOMENT_COLS = 8
+ESL_SAMPLER_POOL, ESL_SAMPLER_QUANTILE = 0, 1
 LABEL_BLOCKED_CONSUMING = -1
 LABEL_BLOCKED_NOTCONSUMING = -2
 
@@ -23,6 +24,7 @@ SYMBOLS = {
     "esl_set_targets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_blocked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_length_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "esl_set_length_sampler": (C.c_int, [C.c_void_p, C.c_int32]),
     "esl_pool_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
     "esl_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esl_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_double, C.c_int64]),

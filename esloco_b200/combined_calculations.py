@@ -124,7 +124,8 @@ def run_simulation_batch(iteration_ids, param_dictionary, genome_size, target_re
         raise ValueError("overlap lists need the per-iteration results (results='tallies')")
     p = param_dictionary
     sess = get_session(device)
-    sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"])
+    sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"],
+                   p.get("length_sampler") or "quantile")
     eng = sess.engine
     T = eng.n_targets
     seed = int(p.get("seed", 0))
@@ -219,7 +220,8 @@ def format_iteration(res, i, keys, iteration_id, mean_read_length, coverage, n_b
 
 def process_combination(mean_read_length, coverage, genome_size, target_regions, iteration, sequenced_data_path, sigma,
                         min_read_length, n_barcodes, barcode_weights, consuming, masked_tree, output_path, scaling,
-                        min_overlap_for_detection, no_cov_plots, seed=0, combo=0, device=0, overlap_lists=False):
+                        min_overlap_for_detection, no_cov_plots, seed=0, combo=0, device=0, overlap_lists=False,
+                        length_sampler="quantile"):
     """process_combination with the reference's positional signature (combined_calculations.py:11-28) -> (detected,
     barcode_distribution) for ONE combination of ONE iteration.  `seed` and `combo` key the Philox stream (the
     reference takes its randomness from numpy's global state instead); output_path / no_cov_plots are accepted for
@@ -229,7 +231,7 @@ def process_combination(mean_read_length, coverage, genome_size, target_regions,
              sigma=sigma, min_read_length=min_read_length, consuming=consuming,
              min_overlap_for_detection=min_overlap_for_detection)
     sess = get_session(device)
-    sess.configure(genome_size, target_regions, masked_tree, n_barcodes, barcode_weights)
+    sess.configure(genome_size, target_regions, masked_tree, n_barcodes, barcode_weights, length_sampler)
     key, factory = _length_pool_key_and_factory(seed, combo, mean_read_length, sequenced_data_path, sigma, min_read_length)
     sess.set_pool(key, factory)
     sc = scaling if isinstance(scaling, (int, float)) else 1

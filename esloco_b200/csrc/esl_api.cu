@@ -86,6 +86,10 @@ struct esl_ctx {
     DevBuf d_sgrid;
     struct esl_host_scratch *host = nullptr; // persistent host-side scratch of esl_prepare (defined below)
     int sgrid_n = 0, sgrid_shift = 0; // shared-memory copy of the first-layer grids (0 = does not fit)
+    // quantile length sampler (esl_set_length_sampler): sorted pool + quantile table, built by esl_prepare
+    int sampler = ESL_SAMPLER_POOL;
+    bool qtab_dirty = true;
+    DevBuf d_pool_sorted, d_qtab, d_sort_keys, d_sort_vals_a, d_sort_vals_b, d_sort_hist;
     DevBuf d_mbits;
     int mbits_shift = 0, mbits_words = 0; // blocked-bucket bitmap (kernels.cuh DevCtx::mbits)
     u64 sgrid_lmax = 0;               // longest read its upper bounds were built for
@@ -601,7 +605,46 @@ int check_inputs(esl_ctx *ctx, bool need_pool)
 // The shared pre-filter's upper bounds assume no read is longer than sgrid_lmax: a longer pool needs a rebuild.
 bool index_stale(const esl_ctx *ctx)
 {
-    return ctx->index_dirty || (ctx->have_pool && ctx->sgrid_n && (u64)ctx->pool_max > ctx->sgrid_lmax);
+    return ctx->index_dirty || (ctx->have_pool && ctx->sgrid_n && (u64)ctx->pool_max > ctx->sgrid_lmax) ||
+           (ctx->have_pool && ctx->sampler == ESL_SAMPLER_QUANTILE && ctx->qtab_dirty);
+}
+
+// Quantile sampler set-up: LSD radix sort of the resident pool on the device (the staged baseline's sort kernels,
+// 8-bit digits, as many passes as the longest read needs) and the quantile table of the sorted pool.  Asynchronous.
+int build_quantile_table(esl_ctx *ctx, cudaStream_t st)
+{
+    const i64 n = ctx->n_pool;
+    const int sort_blocks = (int)((n + esl::kSortTile - 1) / esl::kSortTile);
+    CU(ctx->d_pool_sorted.reserve((size_t)n * 4));
+    CU(ctx->d_sort_keys.reserve((size_t)n * 4));
+    CU(ctx->d_sort_vals_a.reserve((size_t)n * 4));
+    CU(ctx->d_sort_vals_b.reserve((size_t)n * 4));
+    CU(ctx->d_sort_hist.reserve((size_t)sort_blocks * 256 * 4 + 256 * 4 + 16));
+    CU(ctx->d_qtab.reserve((size_t)(esl::kQuantBins + 1) * 4));
+    uint32_t *hist = ctx->d_sort_hist.as<uint32_t>(), *digit_tot = hist + (size_t)sort_blocks * 256;
+    int *n_dev = (int *)(digit_tot + 256);
+    const int n_host = (int)n;
+    CU(cudaMemcpyAsync(n_dev, &n_host, sizeof(int), cudaMemcpyHostToDevice, st));
+    int passes = 1;
+    while (passes < 4 && (ctx->pool_max >> (8 * passes)) != 0) ++passes;
+    // ping-pong so that the LAST pass lands in d_pool_sorted
+    uint32_t *bufs[2] = {ctx->d_sort_keys.as<uint32_t>(), ctx->d_pool_sorted.as<uint32_t>()};
+    uint32_t *vals[2] = {ctx->d_sort_vals_a.as<uint32_t>(), ctx->d_sort_vals_b.as<uint32_t>()};
+    const uint32_t *kin = ctx->d_pool.as<uint32_t>(), *vin = nullptr;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int o = (passes - 1 - pass) & 1 ? 0 : 1; // output buffer: index 1 on the last pass
+        esl::k_rs_hist<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, n_dev, pass * 8, sort_blocks, hist);
+        esl::k_rs_scan_rows<<<256, 1024, 0, st>>>(hist, sort_blocks, digit_tot);
+        esl::k_rs_scan_digits<<<1, 1024, 0, st>>>(digit_tot);
+        esl::k_rs_scatter<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, vin, bufs[o], vals[o], n_dev, pass * 8, sort_blocks, hist, digit_tot, pass == 0);
+        kin = bufs[o]; vin = vals[o];
+        ctx->launches += 4;
+    }
+    esl::k_quantile_table<<<(esl::kQuantBins + 256) / 256, 256, 0, st>>>(ctx->d_pool_sorted.as<uint32_t>(), n, ctx->d_qtab.as<uint32_t>());
+    CU(cudaGetLastError());
+    ctx->launches++;
+    ctx->qtab_dirty = false;
+    return ESL_OK;
 }
 
 // Run calls neither allocate nor block: they require the index esl_prepare built for the current inputs.
@@ -631,6 +674,11 @@ esl::DevCtx<C> make_devctx(const esl_ctx *ctx, double coverage, int consuming, i
     d.mbits_words = ctx->mbits_words;
     d.n_pool = ctx->n_pool;
     d.pool = ctx->d_pool.as<uint32_t>();
+    const bool quant = ctx->sampler == ESL_SAMPLER_QUANTILE && ctx->have_pool;
+    d.qtab = quant ? ctx->d_qtab.as<uint32_t>() : nullptr;
+    d.pool_sorted = ctx->d_pool_sorted.as<uint32_t>();
+    d.q_top_lo = (uint32_t)(((u64)(esl::kQuantBins - 1) * (u64)ctx->n_pool) / esl::kQuantBins);
+    d.q_top_n = ctx->n_pool - d.q_top_lo;
     d.cdf = ctx->d_cdf.as<double>();
     d.cdf_u32 = ctx->d_cdf_u32.as<uint32_t>();
     d.cdf_lut = ctx->d_cdf_lut.as<uint2>();
@@ -673,9 +721,9 @@ i64 bulk_reads(const esl_ctx *ctx, double coverage)
     return n < 2 * esl::kBulkTile ? 0 : n;
 }
 
-size_t bulk_smem(const esl_ctx *ctx)
+size_t bulk_smem(const esl_ctx *ctx, bool quant)
 {
-    return esl::bulk_smem_layout(ctx->wide ? 8 : 4, ctx->n_mask > 0, ctx->sgrid_n > 0, ctx->n_hot > 0, ctx->B, ctx->sgrid_n, ctx->mbits_words).total;
+    return esl::bulk_smem_layout(ctx->wide ? 8 : 4, ctx->n_mask > 0, ctx->sgrid_n > 0, ctx->n_hot > 0, ctx->B, ctx->sgrid_n, ctx->mbits_words, quant).total;
 }
 size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 8 + 24; }
 
@@ -723,11 +771,11 @@ int launch_bulk(esl_ctx *ctx, const esl::DevCtx<C> &dc, const Src &src, const es
         esl::k_place_tally_bulk<C, Src, true, true, false>,   esl::k_place_tally_bulk<C, Src, true, true, true>};
     const Kern kern = table[(dc.has_mask ? 4 : 0) | (dc.sgrid ? 2 : 0) | (dc.n_hot ? 1 : 0)];
     int occ = 0;
-    if (bulk_smem(ctx) > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem(ctx)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx)));
+    if (bulk_smem(ctx, dc.qtab != nullptr && Src::kPoolLengths) > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem(ctx, dc.qtab != nullptr && Src::kPoolLengths)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, esl::kBulkBlock, bulk_smem(ctx, dc.qtab != nullptr && Src::kPoolLengths)));
     if (occ < 1) occ = 1;
     const i64 grid = std::min<i64>((total_tiles + esl::kBulkClaim - 1) / esl::kBulkClaim, (i64)ctx->sm_count * occ);
-    kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx), st>>>(dc, src, out, r.lo_arr, r.lo_const, r.hi_arr, r.hi_const,
+    kern<<<(unsigned)grid, esl::kBulkBlock, bulk_smem(ctx, dc.qtab != nullptr && Src::kPoolLengths), st>>>(dc, src, out, r.lo_arr, r.lo_const, r.hi_arr, r.hi_const,
                                                                       (int)r.tile0, (int)r.tiles, n_iter, d_sched);
     CU(cudaGetLastError());
     ctx->launches++;
@@ -938,6 +986,16 @@ int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n, void 
     ctx->pool_mean = (double)mean;
     ctx->pool_sd = var > 0 ? (double)sqrtl(var) : 0.0;
     ctx->have_pool = true;
+    ctx->qtab_dirty = true;
+    return ESL_OK;
+}
+
+int esl_set_length_sampler(esl_ctx *ctx, int32_t mode)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (mode != ESL_SAMPLER_POOL && mode != ESL_SAMPLER_QUANTILE) return ctx->fail(ESL_ERR_INVALID, "unknown length sampler %d", mode);
+    if (mode != ctx->sampler) ctx->qtab_dirty = true;
+    ctx->sampler = mode;
     return ESL_OK;
 }
 
@@ -950,10 +1008,13 @@ int esl_prepare(esl_ctx *ctx, void *stream)
         if (b >= ctx->B) return ctx->fail(ESL_ERR_INVALID, "blocked interval names barcode %d but n_barcodes is %d", b, ctx->B);
     if (!index_stale(ctx)) return ESL_OK;
     CU(cudaSetDevice(ctx->device));
-    ctx->wide = ctx->G > 0xFFFFFFF0ull;
-    rc = ctx->wide ? upload_index<uint64_t>(ctx, (cudaStream_t)stream) : upload_index<uint32_t>(ctx, (cudaStream_t)stream);
-    if (rc) return rc;
-    ctx->index_dirty = false;
+    if (ctx->have_pool && ctx->sampler == ESL_SAMPLER_QUANTILE && ctx->qtab_dirty && (rc = build_quantile_table(ctx, (cudaStream_t)stream))) return rc;
+    if (ctx->index_dirty || (ctx->have_pool && ctx->sgrid_n && (u64)ctx->pool_max > ctx->sgrid_lmax)) {
+        ctx->wide = ctx->G > 0xFFFFFFF0ull;
+        rc = ctx->wide ? upload_index<uint64_t>(ctx, (cudaStream_t)stream) : upload_index<uint32_t>(ctx, (cudaStream_t)stream);
+        if (rc) return rc;
+        ctx->index_dirty = false;
+    }
     return ESL_OK;
 }
 

@@ -160,6 +160,11 @@ struct DevCtx {
     int mbits_shift, mbits_words;
     uint32_t n_pool;
     const uint32_t *__restrict__ pool;    // length table (K2)
+    // quantile sampler (esl_set_length_sampler): qtab[k] = sorted pool entry at rank k * n_pool / kQuantBins, k <= kQuantBins
+    // (null: lengths are uniform picks from `pool`); the top bin is picked exactly from pool_sorted[q_top_lo ..]
+    const uint32_t *__restrict__ qtab;
+    const uint32_t *__restrict__ pool_sorted;
+    uint32_t q_top_lo, q_top_n;
     const double *__restrict__ cdf;       // numpy-style cdf, replay path
     const uint32_t *__restrict__ cdf_u32; // ceil(cdf * 2^32) saturated, native path
     const uint2 *__restrict__ cdf_lut;    // [kCdfLut] per slice of 2^22 draws: {barcode k of the slice's lowest draw | (k < B-1) << 16, threshold cdf_u32[k]}
@@ -195,6 +200,15 @@ struct DevCtx {
     const GridEntry<C> *__restrict__ mgrid;
 };
 constexpr int kCdfLut = 1024;
+constexpr int kQuantBins = 2048; // bins of the quantile length sampler: 11 bits pick the bin, 13 bits the place inside it
+
+// Look-up tables a draw reads: barcode thresholds + start table (shared memory) and, with the quantile sampler, the
+// quantile table (shared memory in the bulk kernel, global elsewhere).
+struct DrawTabs {
+    const uint32_t *cdf;
+    const uint2 *lut;
+    const uint32_t *qtab;
+};
 constexpr int kSmemDescs = 1024; // first-layer descriptors are staged in shared memory up to this many barcodes
 
 struct DevOut {
@@ -236,71 +250,86 @@ struct PhiloxSrc {
         return philox4x32_10(c0, c1, iter_begin + (uint32_t)it, (combo << 4) | ESL_SLOT_PLACE, keys);
     }
     template <typename C>
-    static __device__ __forceinline__ int barcode_of(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint2 *s_lut, uint32_t w)
+    static __device__ __forceinline__ int barcode_of(const DevCtx<C> &cx, const DrawTabs &tb, uint32_t w)
     {
         // searchsorted(cdf, u, side='right') on integer thresholds: table start + short walk.  A slice of the start
         // table holds at most cx.cdf_walk thresholds: one branch-free step covers almost every CDF; the loop only
         // exists for more than ~1000 barcodes or pathological weights
-        const uint2 e = s_lut[w >> 22]; // one 8-byte load: start barcode, whether a step is possible, and its threshold
+        const uint2 e = tb.lut[w >> 22]; // one 8-byte load: start barcode, whether a step is possible, and its threshold
         int k = (int)(e.x & 0xffffu) + (int)((e.x >> 16) & (e.y <= w ? 1u : 0u));
         if (cx.cdf_walk > 1)
-            while (k < cx.n_barcodes - 1 && s_cdf[k] <= w) ++k;
+            while (k < cx.n_barcodes - 1 && tb.cdf[k] <= w) ++k;
         return k;
     }
-    static __device__ __forceinline__ void place32(const DevCtx<uint32_t> &cx, uint32_t a, uint32_t b, uint32_t &L, uint32_t &start)
+    // Read length from 24 uniform bits u.  Default: uniform pick from the pool, pool[floor(u * n_pool / 2^24)] (one random
+    // 4-byte gather from the L2-resident pool per read).  Quantile sampler: inverse-CDF look-up in the kQuantBins-bin
+    // quantile table -- 11 bits pick the bin, 13 bits interpolate between its two quantiles; the top bin, where a
+    // long-tailed distribution is anything but linear, is picked exactly from the sorted pool.
+    template <typename C>
+    static __device__ __forceinline__ uint32_t length_of(const DevCtx<C> &cx, const DrawTabs &tb, uint32_t u24)
     {
-        L = __ldg(cx.pool + __umulhi(b & 0xFFFFFF00u, cx.n_pool)); // index < n_pool by construction
+        if (tb.qtab) {
+            const uint32_t k = u24 >> 13, f = u24 & 0x1FFFu;
+            if (k == kQuantBins - 1) return __ldg(cx.pool_sorted + cx.q_top_lo + (uint32_t)(((u64)f * cx.q_top_n) >> 13));
+            const uint32_t q0 = tb.qtab[k], q1 = tb.qtab[k + 1];
+            return q0 + (uint32_t)(((u64)(q1 - q0) * f) >> 13);
+        }
+        return __ldg(cx.pool + __umulhi(u24 << 8, cx.n_pool)); // index < n_pool by construction
+    }
+    static __device__ __forceinline__ void place32(const DevCtx<uint32_t> &cx, const DrawTabs &tb, uint32_t a, uint32_t b, uint32_t &L, uint32_t &start)
+    {
+        L = length_of(cx, tb, b >> 8);
         ESL_CHK((u64)L < cx.G, "read not shorter than the genome");
         const uint32_t rg = (uint32_t)(cx.G - (u64)L); // two 32x32->64 products instead of a 64x64 high multiply
         start = (uint32_t)(((u64)a * rg + (((u64)(b << 24) * rg) >> 32)) >> 32);
     }
-    static __device__ __forceinline__ void place64(const DevCtx<uint64_t> &cx, const Philox4 &r, uint32_t &L, uint64_t &start)
+    static __device__ __forceinline__ void place64(const DevCtx<uint64_t> &cx, const DrawTabs &tb, const Philox4 &r, uint32_t &L, uint64_t &start)
     {
-        L = __ldg(cx.pool + __umulhi(r.z, cx.n_pool));
+        L = tb.qtab ? length_of(cx, tb, r.z >> 8) : __ldg(cx.pool + __umulhi(r.z, cx.n_pool));
         ESL_CHK((u64)L < cx.G, "read not shorter than the genome");
         start = __umul64hi(((u64)r.x << 32) | r.y, cx.G - (u64)L);
     }
 
     // One draw (cut-off kernel, partial tiles, materialisation).
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint2 *s_lut, int it, i64 n,
+    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const DrawTabs &tb, int it, i64 n,
                                          uint32_t &L, C &start, int &bc) const
     {
         bc = 0;
         if constexpr (sizeof(C) == 4) {
             const Philox4 r = block((uint32_t)n >> 1, 0u, it);
-            place32(cx, (n & 1) ? r.z : r.x, (n & 1) ? r.w : r.y, L, start);
+            place32(cx, tb, (n & 1) ? r.z : r.x, (n & 1) ? r.w : r.y, L, start);
             if (cx.n_barcodes > 1) {
                 const Philox4 q = block((uint32_t)n >> 2, 1u, it);
                 const uint32_t w = (n & 2) ? ((n & 1) ? q.w : q.z) : ((n & 1) ? q.y : q.x);
-                bc = barcode_of(cx, s_cdf, s_lut, w);
+                bc = barcode_of(cx, tb, w);
             }
         } else {
             const Philox4 r = block((uint32_t)n, 0u, it);
-            place64(cx, r, L, start);
-            if (cx.n_barcodes > 1) bc = barcode_of(cx, s_cdf, s_lut, r.w);
+            place64(cx, tb, r, L, start);
+            if (cx.n_barcodes > 1) bc = barcode_of(cx, tb, r.w);
         }
     }
     // Four consecutive draws n0 .. n0+3 (n0 a multiple of 4): the bulk kernel's full tiles.
     template <typename C>
-    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *s_cdf, const uint2 *s_lut, int it, uint32_t n0,
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const DrawTabs &tb, int it, uint32_t n0,
                                           uint32_t (&L)[4], C (&start)[4], int (&bc)[4]) const
     {
         if constexpr (sizeof(C) == 4) {
             const Philox4 r0 = block(n0 >> 1, 0u, it), r1 = block((n0 >> 1) + 1u, 0u, it);
-            place32(cx, r0.x, r0.y, L[0], start[0]);
-            place32(cx, r0.z, r0.w, L[1], start[1]);
-            place32(cx, r1.x, r1.y, L[2], start[2]);
-            place32(cx, r1.z, r1.w, L[3], start[3]);
+            place32(cx, tb, r0.x, r0.y, L[0], start[0]);
+            place32(cx, tb, r0.z, r0.w, L[1], start[1]);
+            place32(cx, tb, r1.x, r1.y, L[2], start[2]);
+            place32(cx, tb, r1.z, r1.w, L[3], start[3]);
             bc[0] = bc[1] = bc[2] = bc[3] = 0;
             if (cx.n_barcodes > 1) {
                 const Philox4 q = block(n0 >> 2, 1u, it);
-                bc[0] = barcode_of(cx, s_cdf, s_lut, q.x); bc[1] = barcode_of(cx, s_cdf, s_lut, q.y);
-                bc[2] = barcode_of(cx, s_cdf, s_lut, q.z); bc[3] = barcode_of(cx, s_cdf, s_lut, q.w);
+                bc[0] = barcode_of(cx, tb, q.x); bc[1] = barcode_of(cx, tb, q.y);
+                bc[2] = barcode_of(cx, tb, q.z); bc[3] = barcode_of(cx, tb, q.w);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) draw(cx, s_cdf, s_lut, it, (i64)(n0 + i), L[i], start[i], bc[i]);
+            for (int i = 0; i < 4; ++i) draw(cx, tb, it, (i64)(n0 + i), L[i], start[i], bc[i]);
         }
     }
     __device__ __forceinline__ double block_u(int it, i64 n, int j) const
@@ -331,7 +360,7 @@ struct DrawSrc {
     __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
 
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const uint32_t *, const uint2 *, int it, i64 n, uint32_t &L,
+    __device__ __forceinline__ void draw(const DevCtx<C> &cx, const DrawTabs &, int it, i64 n, uint32_t &L,
                                          C &st, int &bc) const
     {
         const i64 g = seg[it] + n;
@@ -343,11 +372,11 @@ struct DrawSrc {
         bc = k;
     }
     template <typename C>
-    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *c, const uint2 *l, int it, uint32_t n0,
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const DrawTabs &tb, int it, uint32_t n0,
                                           uint32_t (&L)[4], C (&st)[4], int (&bc)[4]) const
     {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) draw(cx, c, l, it, (i64)(n0 + i), L[i], st[i], bc[i]);
+        for (int i = 0; i < 4; ++i) draw(cx, tb, it, (i64)(n0 + i), L[i], st[i], bc[i]);
     }
     __device__ __forceinline__ double block_u(int it, i64 n, int j) const { return ublock[uoff[seg[it] + n] + j]; }
     __device__ __forceinline__ double scale_u(int, i64, int) const { return 0.0; }
@@ -365,7 +394,7 @@ struct ReadSrc {
     __device__ __forceinline__ i64 count(int it) const { return seg[it + 1] - seg[it]; }
 
     template <typename C>
-    __device__ __forceinline__ void draw(const DevCtx<C> &, const uint32_t *, const uint2 *, int it, i64 n, uint32_t &L,
+    __device__ __forceinline__ void draw(const DevCtx<C> &, const DrawTabs &, int it, i64 n, uint32_t &L,
                                          C &st, int &bc) const
     {
         const i64 g = seg[it] + n;
@@ -374,11 +403,11 @@ struct ReadSrc {
         bc = label[g];
     }
     template <typename C>
-    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const uint32_t *c, const uint2 *l, int it, uint32_t n0,
+    __device__ __forceinline__ void draw4(const DevCtx<C> &cx, const DrawTabs &tb, int it, uint32_t n0,
                                           uint32_t (&L)[4], C (&st)[4], int (&bc)[4]) const
     {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) draw(cx, c, l, it, (i64)(n0 + i), L[i], st[i], bc[i]);
+        for (int i = 0; i < 4; ++i) draw(cx, tb, it, (i64)(n0 + i), L[i], st[i], bc[i]);
     }
     __device__ __forceinline__ double block_u(int, i64, int) const { return 0.0; }
     __device__ __forceinline__ double scale_u(int, i64, int) const { return 0.0; }
@@ -750,9 +779,9 @@ __device__ __forceinline__ bool blocked_from(const DevCtx<C> &cx, const Src &src
 // Shared-memory layout of the bulk kernel, in 8-byte words, one definition for host (size) and device (offsets).
 // The arrays of compile-time size come first, so the hot ones sit at constant addresses.
 struct BulkSmem {
-    size_t queue, mqueue, mflags, hot, lut, sched, sgrid, desc, hist, cdf, mbits, total; // word offsets; total in BYTES
+    size_t queue, mqueue, mflags, hot, lut, sched, sgrid, desc, hist, cdf, mbits, qtab, total; // word offsets; total in BYTES
 };
-__host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool mask, bool shared, bool hot, int B, int sgrid_n, int mbits_words)
+__host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool mask, bool shared, bool hot, int B, int sgrid_n, int mbits_words, bool quant)
 {
     const size_t item = coord_bytes == 4 ? 20 : 24, warps = kBulkBlock / 32;
     BulkSmem o;
@@ -768,6 +797,7 @@ __host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool ma
     o.hist = w; w += ((size_t)(B + 2) * 4 + 7) / 8;
     o.cdf = w; w += ((size_t)B * 4 + 7) / 8;
     o.mbits = w; w += mask ? ((size_t)mbits_words * 4 + 7) / 8 : 0;
+    o.qtab = w; w += quant ? ((size_t)(kQuantBins + 1) * 4 + 7) / 8 : 0;
     o.total = w * 8;
     return o;
 }
@@ -798,7 +828,8 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
 {
     extern __shared__ u64 smem[];
     const int B = cx.n_barcodes;
-    const BulkSmem lay = bulk_smem_layout(sizeof(C), kMask, kShared, kHot, B, kShared ? cx.sgrid_n : 0, kMask ? cx.mbits_words : 0);
+    const bool quant = !Src::kHasLabel && Src::kPoolLengths && cx.qtab != nullptr; // native stream with the quantile sampler
+    const BulkSmem lay = bulk_smem_layout(sizeof(C), kMask, kShared, kHot, B, kShared ? cx.sgrid_n : 0, kMask ? cx.mbits_words : 0, quant);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int kItemBytes = sizeof(C) == 4 ? 20 : 24;
     const QueueRef<C> queue((char *)(smem + lay.queue) + wid * kQueueCap * kItemBytes, kQueueCap);
@@ -816,6 +847,10 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     int *const s_hist = (int *)(smem + lay.hist);               // [B + 2] reads per label since the last flush
     uint32_t *const s_cdf = (uint32_t *)(smem + lay.cdf);       // [B]
     uint32_t *const s_mbits = (uint32_t *)(smem + lay.mbits);   // [mbits_words] blocked-bucket bitmap
+    uint32_t *const s_qtab = (uint32_t *)(smem + lay.qtab);     // [kQuantBins + 1] quantile table of the read lengths
+    if (quant)
+        for (int i = tid; i <= kQuantBins; i += kBulkBlock) s_qtab[i] = cx.qtab[i];
+    const DrawTabs tabs{s_cdf, s_lut, quant ? s_qtab : nullptr};
     if (kMask)
         for (int i = tid; i < cx.mbits_words; i += kBulkBlock) s_mbits[i] = cx.mbits[i];
     const int n_sgrid = kShared ? 2 * B * cx.sgrid_n : 0;
@@ -836,8 +871,19 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     u64 acc_bases = 0, acc_reads = 0; // lane 0 of each warp / thread 0
     int qn = 0, hot_tiles = 0, parity = 0;
 
-    // Claim and process tiles of iteration `it` until its counter runs out; returns whether this CTA got any (all threads).
-    auto run_iteration = [&](const int it) -> bool {
+    // The CTA's schedule (one loop body, so that it is compiled in line): first the iterations of its own group in
+    // ascending order, then what is left of the other groups' -- their iterations are consumed in order, so walking a
+    // group's list backwards until an iteration yields nothing visits everything that can still hold unclaimed tiles.
+    const int n_slots = n_iter < kIterSlots ? n_iter : kIterSlots;
+    const int slot = (int)(blockIdx.x % (unsigned)n_slots);
+    int helping = 0; // 0: own group; k > 0: the group k places after it
+    for (int it = slot;;) {
+        if (helping == 0 && it >= n_iter) {
+            if (++helping >= n_slots) break;
+            const int other = (slot + helping) % n_slots;
+            it = other + (n_iter - 1 - other) / n_slots * n_slots;
+        }
+        // claim and process tiles of iteration `it` until its counter runs out
         i64 l = lo_arr ? lo_arr[it] : lo_const, h = hi_arr ? hi_arr[it] : hi_const;
         if (Src::kBounded) { const i64 c = src.count(it); h = h < c ? h : c; }
         const uint32_t lo = (uint32_t)l, hi = (uint32_t)(h > l ? h : l);
@@ -874,14 +920,14 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             int label[kBulkIpt];
             // phase 1: draws (Philox, pool gather, start, barcode)
             if (hi - base >= (uint32_t)kBulkTile) { // full tile (block-uniform; all but the last tile of a range)
-                src.draw4(cx, s_cdf, s_lut, it, n0, L, st, label);
+                src.draw4(cx, tabs, it, n0, L, st, label);
             } else {
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i) {
                     // branch-free tail handling: a thread past the end of the range redraws the range's last draw and is
                     // masked out afterwards (label = invalid, length 0)
                     const uint32_t n = n0 + i;
-                    src.draw(cx, s_cdf, s_lut, it, (i64)(n < hi ? n : hi - 1), L[i], st[i], label[i]);
+                    src.draw(cx, tabs, it, (i64)(n < hi ? n : hi - 1), L[i], st[i], label[i]);
                     if (n >= hi) { L[i] = 0; label[i] = kLabelInvalid; }
                 }
             }
@@ -1043,33 +1089,30 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             }
             } // tiles of the claim
         }
-        if (!any) return false; // (block-uniform: nothing gathered, nothing to flush)
-        // what the CTA gathered for this iteration: empty the walk queue, flush histogram / sums
-        if (!kShared)
-            while (qn > 0) queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
-        __syncthreads();
-        if (s_hot) { flush_hot(s_hot, cx.n_hot, tallies_it); hot_tiles = 0; }
-        for (int i = tid; i < B + 2; i += kBulkBlock)
-            if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
-        if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
-        if (tid == 0 && acc_reads) {
-            atomicAdd(out.n_reads + it, acc_reads);
-            if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
+        if (any) { // (block-uniform) what the CTA gathered for this iteration: empty the walk queue, flush histogram / sums
+            if (!kShared)
+                while (qn > 0) queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
+            __syncthreads();
+            if (s_hot) { flush_hot(s_hot, cx.n_hot, tallies_it); hot_tiles = 0; }
+            for (int i = tid; i < B + 2; i += kBulkBlock)
+                if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
+            if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
+            if (tid == 0 && acc_reads) {
+                atomicAdd(out.n_reads + it, acc_reads);
+                if (plain_labels) atomicAdd(out.label_counts + (i64)it * (B + 2), acc_reads);
+            }
+            acc_bases = acc_reads = 0;
+            __syncthreads();
         }
-        acc_bases = acc_reads = 0;
-        __syncthreads();
-        return true;
-    };
-
-    const int n_slots = n_iter < kIterSlots ? n_iter : kIterSlots;
-    const int slot = (int)(blockIdx.x % (unsigned)n_slots);
-    for (int it = slot; it < n_iter; it += n_slots) run_iteration(it);
-    // leftovers of the other groups: their iterations are consumed in order, so walking a group's list backwards until an
-    // iteration yields nothing visits everything that can still hold unclaimed tiles
-    for (int s2 = 1; s2 < n_slots; ++s2) {
-        const int other = (slot + s2) % n_slots;
-        for (int it = other + (n_iter - 1 - other) / n_slots * n_slots; it >= 0; it -= n_slots)
-            if (!run_iteration(it)) break;
+        if (helping == 0) {
+            it += n_slots;
+        } else if (any && it >= n_slots) {
+            it -= n_slots;
+        } else { // this group has nothing left: on to the next one
+            if (++helping >= n_slots) break;
+            const int other = (slot + helping) % n_slots;
+            it = other + (n_iter - 1 - other) / n_slots * n_slots;
+        }
     }
 }
 
@@ -1131,6 +1174,7 @@ k_cutoff_tail(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src 
     int *s_hist = (int *)(smem + 40);           // [B + 2] signed deltas to the label counts
     uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2);
     uint2 *s_lut = (uint2 *)(((uintptr_t)(s_cdf + cx.n_barcodes) + 7) & ~(uintptr_t)7);
+    const DrawTabs tabs{s_cdf, s_lut, cx.qtab}; // (the quantile table is read from global memory here: 0.4 % of the draws)
     __shared__ i64 s_cut_tile;
     __shared__ u64 s_cut_prefix;
     const int tid = threadIdx.x;
@@ -1198,7 +1242,7 @@ k_cutoff_tail(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src 
             valid[i] = idx < n_end;
             L[i] = 0; st[i] = 0; bc[i] = 0; label[i] = 0; counted[i] = 0;
             if (valid[i]) {
-                src.draw(cx, s_cdf, s_lut, it, idx, L[i], st[i], bc[i]);
+                src.draw(cx, tabs, it, idx, L[i], st[i], bc[i]);
                 resolve_read(cx, src, it, idx, L[i], st[i], bc[i], label[i], counted[i]);
                 mine += counted[i];
             }
@@ -1254,10 +1298,11 @@ k_materialize(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Phil
     uint2 *s_lut = (uint2 *)(((uintptr_t)(s_cdf + cx.n_barcodes) + 7) & ~(uintptr_t)7);
     for (int i = threadIdx.x; i < cx.n_barcodes; i += blockDim.x) s_cdf[i] = cx.cdf_u32[i];
     for (int i = threadIdx.x; i < kCdfLut; i += blockDim.x) s_lut[i] = cx.cdf_lut[i];
+    const DrawTabs tabs{s_cdf, s_lut, cx.qtab};
     __syncthreads();
     for (i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x; n < n_reads; n += (i64)gridDim.x * blockDim.x) {
         uint32_t L, counted; C st; int bc, label;
-        src.draw(cx, s_cdf, s_lut, 0, n, L, st, bc);
+        src.draw(cx, tabs, 0, n, L, st, bc);
         resolve_read(cx, src, 0, n, L, st, bc, label, counted);
         o_start[n] = (i64)st;
         o_length[n] = (i64)L;
@@ -1330,6 +1375,15 @@ k_pool_moments(const uint32_t *__restrict__ pool, const i64 n, u64 *__restrict__
         atomicMax(out_max, mx);
         atomicMin(out_min, mn);
     }
+}
+
+// Quantile table of the sorted length pool: q[k] = sorted[floor(k * n / kQuantBins)], q[kQuantBins] = the longest read.
+__global__ void __launch_bounds__(256)
+k_quantile_table(const uint32_t *__restrict__ sorted, const i64 n, uint32_t *__restrict__ q)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < kQuantBins) q[k] = sorted[(i64)(((u64)k * (u64)n) / kQuantBins)];
+    else if (k == kQuantBins) q[k] = sorted[n - 1];
 }
 
 // Per-target moment accumulators over the iterations of a batch (operand of the multi-GPU sum-reduce).

@@ -36,7 +36,7 @@ k_stage_generate(const __grid_constant__ DevCtx<uint32_t> cx, const __grid_const
     u64 counted = 0;
     if (n < n_cap) {
         uint32_t L, c; uint32_t st; int bc, lab;
-        src.draw(cx, s_cdf, s_lut, 0, (i64)n, L, st, bc);
+        src.draw(cx, DrawTabs{s_cdf, s_lut, cx.qtab}, 0, (i64)n, L, st, bc);
         resolve_read(cx, src, 0, (i64)n, L, st, bc, lab, c);
         start[n] = st; len[n] = L; label[n] = lab;
         counted = c;

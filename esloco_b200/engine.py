@@ -115,6 +115,12 @@ class Engine:
         a = _np(a, np.uint32)
         self._check(self.lib.esl_set_length_table(self.ctx, a.ctypes.data, a.size, self._stream()))
 
+    def set_length_sampler(self, mode):
+        """"pool" (uniform pick from the length table, the reference's exact distribution) or "quantile" (inverse CDF
+        through a 2048-bin quantile table in shared memory); native mode only, takes effect with the next run."""
+        code = {"pool": _native.ESL_SAMPLER_POOL, "quantile": _native.ESL_SAMPLER_QUANTILE}[mode]
+        self._check(self.lib.esl_set_length_sampler(self.ctx, code))
+
     def pool_stats(self):
         """(mean, sd, longest) of the resident length table, reduced on the device when it was uploaded."""
         m, sd, mx = C.c_double(), C.c_double(), C.c_uint32()

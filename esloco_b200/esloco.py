@@ -97,7 +97,8 @@ def run(param_dictionary):
     sess = get_session(local)
     dev = torch.device("cuda", local)
     n_targets = len(target_regions)
-    sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"])
+    sess.configure(genome_size, target_regions, masked_tree, p["n_barcodes"], p["barcode_weights"],
+                   p.get("length_sampler") or "quantile")
     keys = sess.keys
     moments = [torch.zeros((n_targets, 8), dtype=torch.int64, device=dev) for _ in combos]
     labels = [[torch.zeros((0, p["n_barcodes"] + 2), dtype=torch.int64, device=dev)] for _ in combos]

@@ -81,9 +81,10 @@ def generate_reads_based_on_coverage(genome_size, coverage, read_length_distribu
     from .session import get_session
     sess = get_session(device)
     sess.invalidate()
-    sess.configure(genome_size, {}, masked_tree, n_barcodes, barcode_weights)
+    # the caller hands over the very lengths to pick from (read_operations.py:102): exact uniform picks, not the quantile table
+    sess.configure(genome_size, {}, masked_tree, n_barcodes, barcode_weights, length_sampler="pool")
     lengths = np.asarray(read_length_distribution)
-    sess.set_pool(("explicit", id(read_length_distribution)), lambda: lengths)
+    sess.set_pool(None, lambda: lengths)
     eng = sess.engine
     res = eng.run_batch(seed, combo, iteration, 1, coverage, consuming).cpu()
     if int(res.status[0]) & 2:

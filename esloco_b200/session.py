@@ -24,6 +24,7 @@ class Session:
         self.engine = Engine(device)
         self.pinned = {}  # page-locked staging tensors for device -> host result copies (BatchResult.cpu)
         self.outputs = {}  # device output buffers reused between chunks of iterations (run_simulation_batch)
+        self._sampler = None
         self.invalidate()
 
     def invalidate(self):
@@ -36,10 +37,17 @@ class Session:
         self.pool_mean = None
         self.keys = None
 
-    def configure(self, genome_size, target_regions, masked_tree, n_barcodes, barcode_weights):
+    def configure(self, genome_size, target_regions, masked_tree, n_barcodes, barcode_weights, length_sampler="quantile"):
         """Upload whatever differs from what the engine holds.  target_regions: the reference's dict or
-        utils.TargetColumns."""
+        utils.TargetColumns.  length_sampler: how native runs turn uniform bits into read lengths -- "quantile" (inverse
+        CDF of the length table through a 2048-bin quantile table in shared memory; default, the faster one) or "pool"
+        (uniform pick from the table itself: exactly the reference's distribution, read_operations.py:102)."""
         eng = self.engine
+        if length_sampler not in ("quantile", "pool"):
+            raise ValueError("length_sampler must be 'quantile' or 'pool'")
+        if length_sampler != self._sampler:
+            eng.set_length_sampler(length_sampler)
+            self._sampler = length_sampler
         if eng.genome_size != genome_size:
             eng.set_genome(genome_size)
             self._pool_key = None  # the pool is filtered against the genome size

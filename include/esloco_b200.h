@@ -104,6 +104,19 @@ int esl_set_blocked(esl_ctx *ctx, const int64_t *start, const int64_t *end, cons
  * from mean / sd / max). */
 int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n, void *stream);
 
+/* How native-mode runs turn 24 uniform bits into a read length (the north star's "inverse-CDF look-up into a
+ * shared-memory-staged table"; replay modes are fed their lengths and ignore this).
+ *   ESL_SAMPLER_POOL      uniform pick from the length table -- exactly the reference's distribution
+ *                         (read_operations.py:102 on combined_calculations.py:57); one random 4-byte gather per read.
+ *   ESL_SAMPLER_QUANTILE  inverse CDF of the table through a 2048-bin quantile table staged in shared memory:
+ *                         11 bits pick the bin, 13 bits interpolate linearly between its two quantiles; the top bin
+ *                         is picked exactly from the sorted table.  The sampled CDF is within 1/2048 of the table's
+ *                         everywhere (tests: KS distance and mean), and no read is longer than the table's longest.
+ * Takes effect with the next esl_prepare (which sorts the resident table on the device and builds the quantiles). */
+#define ESL_SAMPLER_POOL 0
+#define ESL_SAMPLER_QUANTILE 1
+int esl_set_length_sampler(esl_ctx *ctx, int32_t mode);
+
 /* Statistics of the resident length table as the device reduced them (any pointer may be NULL). */
 int esl_pool_stats(const esl_ctx *ctx, double *mean, double *sd, uint32_t *longest);
 

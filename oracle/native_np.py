@@ -49,7 +49,37 @@ def cdf_thresholds(cdf):
     return np.where(v >= 4294967295.0, 0xFFFFFFFF, v).astype(np.uint64)
 
 
-def native_draws(seed, combo, iteration, n, genome_size, pool, cdf):
+QUANT_BINS = 2048
+
+
+def quantile_table(pool):
+    """(sorted pool, quantile table q[0..QUANT_BINS]) as esl_prepare builds them for ESL_SAMPLER_QUANTILE:
+    q[k] = sorted[k * n // QUANT_BINS], q[QUANT_BINS] = the longest read."""
+    sp = np.sort(np.asarray(pool, np.uint64))
+    n = sp.size
+    q = np.empty(QUANT_BINS + 1, np.uint64)
+    q[:QUANT_BINS] = sp[(np.arange(QUANT_BINS, dtype=np.uint64) * np.uint64(n)) // np.uint64(QUANT_BINS)]
+    q[QUANT_BINS] = sp[-1]
+    return sp, q
+
+
+def lengths_from_bits(u24, pool, sampler):
+    """Read lengths from 24 uniform bits (kernels.cuh PhiloxSrc::length_of)."""
+    u24 = np.asarray(u24, np.uint64)
+    pool = np.asarray(pool, np.uint64)
+    if sampler == "pool":
+        return pool[((u24 * np.uint64(pool.size)) >> np.uint64(24)).astype(np.int64)]
+    sp, q = quantile_table(pool)
+    n = sp.size
+    k, f = (u24 >> np.uint64(13)).astype(np.int64), u24 & np.uint64(0x1FFF)
+    top_lo = (QUANT_BINS - 1) * n // QUANT_BINS
+    top = sp[np.minimum(top_lo + ((f * np.uint64(n - top_lo)) >> np.uint64(13)).astype(np.int64), n - 1)]
+    kk = np.minimum(k, QUANT_BINS - 1)
+    inner = q[kk] + (((q[kk + 1] - q[kk]) * f) >> np.uint64(13))
+    return np.where(k == QUANT_BINS - 1, top, inner)
+
+
+def native_draws(seed, combo, iteration, n, genome_size, pool, cdf, sampler="pool"):
     """Draws 0..n-1 of one iteration: (length, start, barcode) as int64 arrays (kernels.cuh PhiloxSrc).
     32-bit coordinates (genome_size <= 2^32 - 16): draw n takes the 64 bits (a, b) = words (x, y) / (z, w) of block
     (n >> 1, 0) for even / odd n -- length = pool[(b >> 8) * n_pool >> 24], start = floor((a * 2^32 + (b & 0xff) * 2^24)
@@ -63,13 +93,14 @@ def native_draws(seed, combo, iteration, n, genome_size, pool, cdf):
         x, y, z, w = philox4x32_10(idx >> np.uint64(1), 0, iteration, slot, k0, k1)
         odd = (idx & np.uint64(1)).astype(bool)
         a, b = np.where(odd, z, x), np.where(odd, w, y)
-        L = pool[(((b & np.uint64(0xFFFFFF00)) * np.uint64(pool.size)) >> np.uint64(32)).astype(np.int64)]
+        L = lengths_from_bits(b >> np.uint64(8), pool, sampler)
         start = mulhi64((a << np.uint64(32)) | ((b & np.uint64(0xFF)) << np.uint64(24)), np.uint64(genome_size) - L)
         q = philox4x32_10(idx >> np.uint64(2), 1, iteration, slot, k0, k1)
         u = np.choose((idx & np.uint64(3)).astype(np.int64), q)
     else:
         x, y, z, u = philox4x32_10(idx, 0, iteration, slot, k0, k1)
-        L = pool[((z * np.uint64(pool.size)) >> np.uint64(32)).astype(np.int64)]
+        L = (pool[((z * np.uint64(pool.size)) >> np.uint64(32)).astype(np.int64)] if sampler == "pool"
+             else lengths_from_bits(z >> np.uint64(8), pool, sampler))
         start = mulhi64((x << np.uint64(32)) | y, np.uint64(genome_size) - L)
     thr = cdf_thresholds(cdf)
     B = thr.size
@@ -89,14 +120,15 @@ def scale_u(seed, combo, iteration, n, row):
     return float(u53(x, y))
 
 
-def native_iteration(seed, combo, iteration, genome_size, coverage, pool, cdf, consuming=False, mask=None, n_draws=None):
+def native_iteration(seed, combo, iteration, genome_size, coverage, pool, cdf, consuming=False, mask=None, n_draws=None,
+                     sampler="pool"):
     """Reads of one native iteration after blocked test and coverage cut-off (reference rules on native draws).
     mask = (start, end, weight, barcode) arrays, barcode -1 = ALL.  Returns dict(start, length, label, covered)."""
     pool = np.asarray(pool, np.int64)
     thr = int(np.ceil(coverage * float(genome_size)))
     if n_draws is None:
         n_draws = int(coverage * genome_size / max(1.0, pool.mean()) * 1.5) + 20000
-    L, start, bc = native_draws(seed, combo, iteration, n_draws, genome_size, pool, cdf)
+    L, start, bc = native_draws(seed, combo, iteration, n_draws, genome_size, pool, cdf, sampler)
     label = bc.copy()
     counted = L.copy()
     if mask is not None and len(mask[0]):

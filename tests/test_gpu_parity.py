@@ -783,3 +783,47 @@ def test_full_size_config3_consistency(eng):
         for b in (0, 1, 7, 23):
             d = depth[tb == b]
             assert abs(d.mean() - cov * p[b]) < 5 * d.std(ddof=1) / np.sqrt(d.size), (b, d.mean(), cov * p[b])
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_quantile_length_sampler_exact_and_close_to_the_pool(eng, wide):
+    """ESL_SAMPLER_QUANTILE (the north star's inverse-CDF look-up in a shared-memory-staged table): the sorted pool and
+    its 2048-bin quantile table are built on the device; 11 bits pick the bin, 13 bits interpolate, the top bin is an
+    exact pick.  (1) Exact: reads, labels, cut-off and tallies equal the numpy restatement of the same rule, for 32-
+    and 64-bit coordinates.  (2) Close to the reference's distribution (a uniform pick from the pool): Kolmogorov
+    distance between the sampled lengths and the pool below 1/2048 + sampling noise, mean within 0.2 %, no read longer
+    than the pool's longest.  (3) Switching back restores the pool pick bit for bit."""
+    G = 6_000_000_000 if wide else 80_000_000
+    rng = np.random.RandomState(12)
+    T = 90
+    ts = np.sort(rng.randint(0, G - 200_000, T).astype(np.int64) if not wide else (rng.rand(T) * (G - 200_000)).astype(np.int64))
+    te = ts + rng.randint(500, 150_000, T)
+    tb = (np.arange(T) % 3).astype(np.int32)
+    cdf = np.array([0.5, 0.8, 1.0])
+    pool = O.lognormal_pool(O.Rng(77), 9000, 1, 20, n=300000)
+    cov = 0.4 if wide else 12.0
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
+    eng.set_length_table(pool)
+    base = eng.run_batch(5, 1, 3, 1, cov).cpu()
+    try:
+        eng.set_length_sampler("quantile")
+        res = eng.run_batch(5, 1, 3, 2, cov).cpu()
+        it = NN.native_iteration(5, 1, 4, G, cov, pool, cdf, sampler="quantile")
+        assert int(res.n_reads[1]) == it["n_placed"] and int(res.n_bases[1]) == it["covered"]
+        exp = O.count_matches_indexed(ts, te, tb, 3, it["start"], it["start"] + it["length"], it["label"], 1)
+        t = res.tallies[1].numpy()
+        assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+        assert t[:, 2].sum() > 0
+        s, ln, lab = eng.materialize_reads(5, 1, 4, False, int(res.n_reads[1]))
+        lh = ln.cpu().numpy()
+        assert np.array_equal(lh, it["length"]) and np.array_equal(s.cpu().numpy(), it["start"])
+        # distribution of the sampled lengths against the pool
+        assert lh.max() <= pool.max() and lh.min() >= pool.min()
+        sp = np.sort(pool)
+        ks = np.abs(np.searchsorted(sp, np.sort(lh), side="right") / sp.size - np.arange(1, lh.size + 1) / lh.size).max()
+        assert ks < 1 / 2048 + 1.63 / np.sqrt(lh.size), ks  # table resolution + the 1 % point of the KS statistic
+        assert abs(lh.mean() / pool.mean() - 1) < 0.002 + 4 * pool.std() / pool.mean() / np.sqrt(lh.size)
+    finally:
+        eng.set_length_sampler("pool")
+    again = eng.run_batch(5, 1, 3, 1, cov).cpu()
+    assert np.array_equal(again.tallies.numpy(), base.tallies.numpy()) and int(again.n_reads[0]) == int(base.n_reads[0])

@@ -95,8 +95,9 @@ def test_oracle_port_matches_reference_sample(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sampler", ["quantile", "pool"])
 @pytest.mark.parametrize("name", CASES)
-def test_native_stream_matches_reference_sample(name):
+def test_native_stream_matches_reference_sample(name, sampler):
     from esloco_b200.engine import Engine
     from esloco_b200.read_operations import barcode_cdf, barcode_probabilities
     s = Sample(name)
@@ -107,6 +108,7 @@ def test_native_stream_matches_reference_sample(name):
         eng.set_barcode_cdf(barcode_cdf(barcode_probabilities(s.B, p["barcode_weights"])))
         eng.set_targets(s.ts, s.te, s.tb)
         eng.set_blocked(*(s.mask or ()))
+        eng.set_length_sampler(sampler)  # both length samplers must reproduce the reference's distribution
         eng.set_length_table(O.lognormal_pool(O.Rng(4242), s.mrl, p["sigma"], p["min_read_length"]))
         res = eng.run_batch(20261020, 0, 0, s.n_iter, s.cov, p["consuming"], p["min_overlap_for_detection"], p["scaling"]).cpu()
     finally:
