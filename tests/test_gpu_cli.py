@@ -178,7 +178,7 @@ def test_generate_reads_and_process_combination_mirrors():
     from esloco_b200.session import get_session
     sess = get_session(0)
     sess.invalidate()
-    sess.configure(G, targets, tree, 2, {"0": 3})
+    sess.configure(G, targets, tree, 2, {"0": 3}, length_sampler="pool")  # the sampler generate_reads_based_on_coverage uses
     sess.set_pool(("explicit-test",), lambda: pool)
     res = sess.engine.run_batch(5, 1, 2, 1, 4, False, 10, 1.0).cpu()
     assert [int(x) for x in res.tallies[0, :, 2]] == [d["on_target_bases"] for d in by_reads]
