@@ -142,13 +142,41 @@ struct Rec { i64 s, e; int32_t row; };
 // (binary search), so pathological nesting stays O(n log n).
 constexpr int kDeadScan = 16;
 constexpr size_t kRelaxedLayers = 64;
-void build_layers(Rec *first_rec, Rec *last_rec, std::vector<std::vector<Rec>> &layers, u64 G)
+// Sort targets by (start, end, row).  Large sets: stable LSD radix sort on the start (11-bit digits), then the rare runs
+// of equal starts are ordered by (end, row) -- 10 k targets take ~0.1 ms instead of 0.7 ms with a comparison sort, and
+// the index of a 240 k-target set is rebuilt on every esl_prepare.
+void sort_recs(Rec *first_rec, Rec *last_rec)
 {
-    std::sort(first_rec, last_rec, [](const Rec &a, const Rec &b) {
+    auto less = [](const Rec &a, const Rec &b) {
         if (a.s != b.s) return a.s < b.s;
         if (a.e != b.e) return a.e < b.e;
         return a.row < b.row;
-    });
+    };
+    const size_t n = (size_t)(last_rec - first_rec);
+    if (n < 512) { std::sort(first_rec, last_rec, less); return; }
+    i64 mx = 0;
+    for (const Rec *r = first_rec; r != last_rec; ++r) mx = std::max(mx, r->s);
+    std::vector<Rec> tmp(n);
+    Rec *src = first_rec, *dst = tmp.data();
+    for (int shift = 0; shift < 63 && (mx >> shift) != 0; shift += 11) {
+        size_t cnt[2049] = {0};
+        for (size_t i = 0; i < n; ++i) ++cnt[((u64)src[i].s >> shift & 2047u) + 1];
+        for (int d = 0; d < 2048; ++d) cnt[d + 1] += cnt[d];
+        for (size_t i = 0; i < n; ++i) dst[cnt[(u64)src[i].s >> shift & 2047u]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != first_rec) std::copy(src, src + n, first_rec);
+    for (size_t i = 0; i < n;) { // equal starts: order by (end, row)
+        size_t j = i + 1;
+        while (j < n && first_rec[j].s == first_rec[i].s) ++j;
+        if (j - i > 1) std::sort(first_rec + i, first_rec + j, less);
+        i = j;
+    }
+}
+
+void build_layers(Rec *first_rec, Rec *last_rec, std::vector<std::vector<Rec>> &layers, u64 G)
+{
+    sort_recs(first_rec, last_rec);
     struct Relaxed {
         std::vector<i64> pm_end;    // the records that raised the running max of ends: their ends (ascending) ...
         std::vector<size_t> pm_idx; // ... and their positions in the layer
@@ -330,7 +358,10 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
     // independently on a few host threads (config 3: 24 barcodes x 10 k targets); (3) the layout of the final arrays
     // follows from the layer sizes; (4) the threads write records and grids straight to their final places.
     const size_t n_all = ctx->t_start.size();
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    // host threads of the build: at most 8, and a fair share of the cores when several ranks of one launch (torchrun's
+    // LOCAL_WORLD_SIZE) rebuild their indexes at the same time
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char *lws = getenv("LOCAL_WORLD_SIZE")) hw = std::max(1u, hw / (unsigned)std::max(1, atoi(lws)));
     const int n_thr = (int)std::min<size_t>({(size_t)hw, (size_t)8, n_all / 4096 + 1});
     std::vector<size_t> off(B + 1, 0);
     {
