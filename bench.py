@@ -6,10 +6,10 @@
 Metric (BASELINE.json): simulated reads placed per second (and iterations per second), hg38-size genome, 30x.
 
 Headline line (N GPUs, WEAK scaling): BASELINE.json configs[1] -- I mode, synthetic hg38-size reference (3.1 Gb, 24
-contigs), 1 barcode, 30x, 100 random insertions of 5 kb, 100 iterations.  One STEP = `--batches-per-step` (16) passes of
+contigs), 1 barcode, 30x, 100 random insertions of 5 kb, 100 iterations.  One STEP = `--batches-per-step` (24) passes of
 the hot path, each one esl_run_batch call over the config's 100 iterations with fresh iteration ids, every pass followed
-by the per-target moment kernel; a step is 16 passes rather than one so that the timed region lasts about a second
-(20 steps x 16 x 3.2 ms) instead of 64 ms.  Every rank runs its own iterations; for N > 1 the per-target moment
+by the per-target moment kernel; a step is 24 passes rather than one so that the timed region lasts about a second
+(20 steps x 24 x 2.1 ms) instead of 40 ms.  Every rank runs its own iterations; for N > 1 the per-target moment
 accumulators are combined by ONE NCCL sum-reduce at the end of the step (`collective_ms`).
 
 `north_star_cfg3` block (same JSON line, STRONG scaling): BASELINE.json configs[2] -- 24 weighted barcodes, 10 k
@@ -459,7 +459,7 @@ def run_ours(args, w):
         w3 = make_workload("cfg3")
         w3["desc"] = ("I mode, hg38-size, 24 barcodes (weights 0:10, 1:5), 30x, 10k insertions per barcode (240k targets), "
                       "1000 iterations in total sharded over the GPUs")
-        ns = measure(args, w3, max(3, min(args.steps, 10)), 3, 1, strong_total=1000, e2e_mode="moments")
+        ns = measure(args, w3, max(10, args.steps), 3, 1, strong_total=1000, e2e_mode="moments")
         if rank == 0:
             ns.pop("_sampler").stop()
             ns.update(metric=METRIC, unit="reads/s", scaling="strong", n_gpus=world,
@@ -495,8 +495,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
-    ap.add_argument("--batches-per-step", type=int, default=16,
-                    help="passes of the config's iterations per timed step (16 x 100 iterations ~ 51 ms per step)")
+    ap.add_argument("--batches-per-step", type=int, default=24,
+                    help="passes of the config's iterations per timed step (24 x 100 iterations ~ 50 ms per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-north-star", dest="north_star", action="store_false",
                     help="skip the north_star_cfg3 block (config 3, 1000 iterations sharded over the GPUs)")

@@ -235,7 +235,8 @@ template <typename C> C clampc(i64 v, u64 G) { return (C)((u64)v > G + 1 ? G + 1
 // rarely a false alarm even for sparse runs, yet at most 2^21 entries (16 MB) per run.
 inline int grid_shift(u64 n_intervals, u64 G)
 {
-    const u64 want = std::min<u64>(std::max<u64>(std::max<u64>(64, 8ull * n_intervals), (G >> 16) + 1), 1ull << 21);
+    static const u64 per_interval = getenv("ESL_GRID_FACTOR") ? (u64)atoi(getenv("ESL_GRID_FACTOR")) : 8; // (tuning knob)
+    const u64 want = std::min<u64>(std::max<u64>(std::max<u64>(64, per_interval * n_intervals), (G >> 16) + 1), 1ull << 21);
     int shift = 0;
     while (((G + 1) >> shift) + 2 > want) ++shift;
     return shift;

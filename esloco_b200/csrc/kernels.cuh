@@ -38,7 +38,10 @@ constexpr int kBulkBlock = ESL_BULK_BLOCK; // threads per CTA of the bulk kernel
 // on its four reads instead of 4.
 constexpr int kBulkIpt = 4;
 constexpr int kBulkTile = kBulkBlock * kBulkIpt;
-constexpr int kBulkClaim = 8; // tiles a CTA claims from the launch's tile counter at a time
+#ifndef ESL_BULK_CLAIM
+#define ESL_BULK_CLAIM 8
+#endif
+constexpr int kBulkClaim = ESL_BULK_CLAIM; // tiles a CTA claims from an iteration's tile counter at a time
 #ifndef ESL_BULK_MIN_BLOCKS
 #define ESL_BULK_MIN_BLOCKS 4
 #endif
