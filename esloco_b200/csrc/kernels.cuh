@@ -39,7 +39,7 @@ constexpr int kBulkBlock = ESL_BULK_BLOCK; // threads per CTA of the bulk kernel
 constexpr int kBulkIpt = 4;
 constexpr int kBulkTile = kBulkBlock * kBulkIpt;
 #ifndef ESL_BULK_CLAIM
-#define ESL_BULK_CLAIM 8
+#define ESL_BULK_CLAIM 16
 #endif
 constexpr int kBulkClaim = ESL_BULK_CLAIM; // tiles a CTA claims from an iteration's tile counter at a time
 #ifndef ESL_BULK_MIN_BLOCKS
@@ -712,10 +712,11 @@ __device__ __forceinline__ void queue_push(const QueueRef<C> &q, int &n, bool wa
     n += __popc(m);
 }
 
-// One round: pop up to 32 items, one record visit per lane, push the walks that go on.
+// One round: pop up to 32 items, one record visit per lane, push the walks that go on; returns the new queue length.
+// (Compiled in line at every call site: as a real call it spills 300 bytes and config 4 loses a third.)
 template <typename C, typename Src>
-__device__ __forceinline__ void queue_round(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
-                                            int it, const QueueRef<C> &q, int &n, bool with_n, uint32_t *s_hot)
+__device__ __forceinline__ int queue_round(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it,
+                                            int it, const QueueRef<C> q, int n, bool with_n, uint32_t *s_hot)
 {
     const int lane = threadIdx.x & 31;
     const int take = n < 32 ? n : 32;
@@ -748,6 +749,7 @@ __device__ __forceinline__ void queue_round(const DevCtx<C> &cx, const Src &src,
     if (more) q.put(n + __popc(m & ((1u << lane) - 1u)), w, with_n);
     n += __popc(m);
     __syncwarp();
+    return n;
 }
 
 // Blocked test of a queued read, starting from the first candidates its probes found (a < 0: that tree has none).
@@ -1050,7 +1052,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 for (int i = 0; i < kBulkIpt; ++i) {
                     // (a read the blocked-region phase relabelled keeps its probe but is not tallied)
                     queue_push(queue, qn, label[i] >= 0 && pt[i].s < (C)(st[i] + L[i]), st[i], L[i], pt[i].a, (uint32_t)label[i], n0 + i, with_n);
-                    while (qn >= 32) queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
+                    while (qn >= 32) qn = queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
                 }
                 if (cx.any_extra) { // nesting targets somewhere: layer k of every read's barcode, k ascending
                     int ne_max = 0;
@@ -1075,7 +1077,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                                 pe = Probe<C>{e.j | ((d.y & 0x100) ? kCrowdedBit : 0), e.s};
                             }
                             queue_push(queue, qn, pe.s < (C)(st[i] + L[i]), st[i], L[i], pe.a, (uint32_t)sg, n0 + i, with_n);
-                            while (qn >= 32) queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
+                            while (qn >= 32) qn = queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
                         }
                     }
                 }
@@ -1094,7 +1096,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
         }
         if (any) { // (block-uniform) what the CTA gathered for this iteration: empty the walk queue, flush histogram / sums
             if (!kShared)
-                while (qn > 0) queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
+                while (qn > 0) qn = queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
             __syncthreads();
             if (s_hot) { flush_hot(s_hot, cx.n_hot, tallies_it); hot_tiles = 0; }
             for (int i = tid; i < B + 2; i += kBulkBlock)
