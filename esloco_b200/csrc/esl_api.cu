@@ -759,7 +759,7 @@ size_t bulk_smem(const esl_ctx *ctx, bool quant)
 {
     return esl::bulk_smem_layout(ctx->wide ? 8 : 4, ctx->n_mask > 0, ctx->sgrid_n > 0, ctx->n_hot > 0, ctx->B, ctx->sgrid_n, ctx->mbits_words, quant).total;
 }
-size_t tail_smem(int B) { return (size_t)40 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 8 + 24; }
+size_t tail_smem(int B) { return (size_t)112 * 8 + (size_t)(2 * B + 2) * 4 + (size_t)esl::kCdfLut * 8 + 24; }
 
 // Upper bound on the draws per iteration any bulk pass may cover.  Without a mask (or with consuming = True)
 // every draw counts and the first-pass bound n1 is already tight.  With a mask a blocked draw may count nothing,
@@ -1361,7 +1361,9 @@ int esl_moments(esl_ctx *ctx, const int64_t *d_tallies, int32_t n_iter, int64_t 
     const i64 T = (i64)ctx->t_start.size();
     if (T == 0) return ESL_OK;
     CU(cudaSetDevice(ctx->device));
-    esl::k_moments<<<(unsigned)((T + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_tallies, n_iter, T, d_moments);
+    // enough threads to fill the GPU: iterations are split over grid.y when there are few targets
+    const int n_slices = (int)std::max<i64>(1, std::min<i64>({(i64)n_iter, (i64)65536 / std::max<i64>(T, 1), (i64)65535}));
+    esl::k_moments<<<dim3((unsigned)((T + 255) / 256), (unsigned)n_slices), 256, 0, (cudaStream_t)stream>>>(d_tallies, n_iter, T, n_slices, d_moments);
     CU(cudaGetLastError());
     ctx->launches++;
     return ESL_OK;

@@ -56,7 +56,7 @@ constexpr int kBulkMinBlocksGeneral = ESL_BULK_MIN_BLOCKS_GENERAL;
 template <typename C, bool kShared>
 constexpr int bulk_min_blocks() { return (kShared ? kBulkMinBlocks : kBulkMinBlocksGeneral) - (sizeof(C) == 8 ? 1 : 0); }
 constexpr int kTailBlock = 1024;
-constexpr int kTailIpt = 2;
+constexpr int kTailIpt = 4; // consecutive draws per thread: one scan orders a chunk of 4096 draws, and draw4 serves them
 constexpr int kTailChunk = kTailBlock * kTailIpt;
 constexpr int kMaxBarcodes = 4096;
 
@@ -1169,14 +1169,31 @@ __device__ __forceinline__ u64 block_excl_scan(u64 v, u64 *s_warp, u64 *total)
     return ex;
 }
 
+// Block-wide sums of two values at once (two barriers): every thread gets both totals.
+__device__ __forceinline__ void block_sum2(u64 a, u64 b, u64 *s_pair, u64 &tot_a, u64 &tot_b)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { s_pair[2 * wid] = a; s_pair[2 * wid + 1] = b; }
+    __syncthreads();
+    if (wid == 0) {
+        a = warp_sum(s_pair[2 * lane]); b = warp_sum(s_pair[2 * lane + 1]); // kTailBlock / 32 == 32 warps
+        if (lane == 0) { s_pair[64] = a; s_pair[65] = b; }
+    }
+    __syncthreads();
+    tot_a = s_pair[64]; tot_b = s_pair[65];
+    __syncthreads();
+}
+
 template <typename C, typename Src>
 __global__ void __launch_bounds__(kTailBlock)
 k_cutoff_tail(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src src, const DevOut out, const i64 *__restrict__ n_bulk_arr,
               const i64 n_bulk_const)
 {
     extern __shared__ u64 smem[];
-    u64 *s_warp = smem;                         // [33]
-    int *s_hist = (int *)(smem + 40);           // [B + 2] signed deltas to the label counts
+    u64 *s_warp = smem;                         // [33] scans
+    u64 *s_pair = smem + 40;                    // [66] pair sums
+    int *s_hist = (int *)(smem + 112);          // [B + 2] signed deltas to the label counts
     uint32_t *s_cdf = (uint32_t *)(s_hist + cx.n_barcodes + 2);
     uint2 *s_lut = (uint2 *)(((uintptr_t)(s_cdf + cx.n_barcodes) + 7) & ~(uintptr_t)7);
     const DrawTabs tabs{s_cdf, s_lut, cx.qtab}; // (the quantile table is read from global memory here: 0.4 % of the draws)
@@ -1241,15 +1258,26 @@ k_cutoff_tail(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src 
         uint32_t counted[kTailIpt];
         bool valid[kTailIpt];
         u64 mine = 0;
+        const i64 idx0 = n + (i64)tid * kTailIpt; // thread-contiguous draw order so one scan orders the chunk
+        if (idx0 + kTailIpt <= n_end) { // (n and the bulk range are multiples of 4: idx0 is aligned)
+            src.draw4(cx, tabs, it, (uint32_t)idx0, L, st, bc);
 #pragma unroll
-        for (int i = 0; i < kTailIpt; ++i) { // thread-contiguous draw order so one scan orders the chunk
-            const i64 idx = n + (i64)tid * kTailIpt + i;
-            valid[i] = idx < n_end;
-            L[i] = 0; st[i] = 0; bc[i] = 0; label[i] = 0; counted[i] = 0;
-            if (valid[i]) {
-                src.draw(cx, tabs, it, idx, L[i], st[i], bc[i]);
-                resolve_read(cx, src, it, idx, L[i], st[i], bc[i], label[i], counted[i]);
+            for (int i = 0; i < kTailIpt; ++i) {
+                valid[i] = true;
+                resolve_read(cx, src, it, idx0 + i, L[i], st[i], bc[i], label[i], counted[i]);
                 mine += counted[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kTailIpt; ++i) {
+                const i64 idx = idx0 + i;
+                valid[i] = idx < n_end;
+                L[i] = 0; st[i] = 0; bc[i] = 0; label[i] = 0; counted[i] = 0;
+                if (valid[i]) {
+                    src.draw(cx, tabs, it, idx, L[i], st[i], bc[i]);
+                    resolve_read(cx, src, it, idx, L[i], st[i], bc[i], label[i], counted[i]);
+                    mine += counted[i];
+                }
             }
         }
         u64 chunk_total;
@@ -1270,10 +1298,9 @@ k_cutoff_tail(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src 
             if (label[i] >= 0 && label[i] < B)
                 tally_read(cx, src, out, tallies_it, it, n + (i64)tid * kTailIpt + i, st[i], (C)(st[i] + L[i]), label[i], sign);
         }
-        u64 tot_b, tot_r, tot_x;
-        block_excl_scan(inc_bases, s_warp, &tot_b);
-        block_excl_scan((u64)inc_reads, s_warp, &tot_r);
-        block_excl_scan((u64)excluded, s_warp, &tot_x);
+        u64 tot_b, tot_rx; // one pass for the three totals: bases; reads and excluded draws packed (<= 4096 each)
+        block_sum2(inc_bases, (u64)inc_reads | (u64)excluded << 32, s_pair, tot_b, tot_rx);
+        const u64 tot_r = tot_rx & 0xffffffffull, tot_x = tot_rx >> 32;
         if (take_back) { d_bases -= (i64)tot_b; d_reads -= (i64)tot_r; }
         else { d_bases += (i64)tot_b; d_reads += (i64)tot_r; }
         covered += chunk_total;
@@ -1391,24 +1418,31 @@ k_quantile_table(const uint32_t *__restrict__ sorted, const i64 n, uint32_t *__r
     else if (k == kQuantBins) q[k] = sorted[n - 1];
 }
 
-// Per-target moment accumulators over the iterations of a batch (operand of the multi-GPU sum-reduce).
+// Per-target moment accumulators over the iterations of a batch (operand of the multi-GPU sum-reduce).  Thread
+// (target t, slice s) folds iterations s, s + n_slices, ... and adds its partial sums with atomics: small target sets
+// get their parallelism from the iterations (100 targets x 100 iterations: one thread per pair), large ones from the
+// targets (n_slices = 1, coalesced 24-byte rows).  The square sum of the bases is carried as hi * 2^32 + lo; partial
+// sums may leave lo above 2^32, which every consumer folds back (hi << 32) + lo.
 __global__ void __launch_bounds__(256)
-k_moments(const i64 *__restrict__ tallies, const int n_iter, const i64 n_targets, i64 *__restrict__ mom)
+k_moments(const i64 *__restrict__ tallies, const int n_iter, const i64 n_targets, const int n_slices, i64 *__restrict__ mom)
 {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
     if (t >= n_targets) return;
     i64 sf = 0, sf2 = 0, sp = 0, sp2 = 0, sb = 0;
     unsigned __int128 sb2 = 0;
-    for (int it = 0; it < n_iter; ++it) {
+    for (int it = s; it < n_iter; it += n_slices) {
         const i64 *r = tallies + ((i64)it * n_targets + t) * 3;
         const i64 f = r[0], p = r[1], b = r[2];
         sf += f; sf2 += f * f; sp += p; sp2 += p * p; sb += b;
         sb2 += (unsigned __int128)(u64)b * (u64)b;
     }
-    i64 *m = mom + t * 8;
-    m[0] += n_iter; m[1] += sf; m[2] += sf2; m[3] += sp; m[4] += sp2; m[5] += sb;
-    m[6] += (i64)(u64)(sb2 & 0xffffffffull);
-    m[7] += (i64)(u64)(sb2 >> 32);
+    u64 *m = (u64 *)(mom + t * 8);
+    if (s == 0) atomicAdd(m, (u64)n_iter);
+    atomicAdd(m + 1, (u64)sf); atomicAdd(m + 2, (u64)sf2); atomicAdd(m + 3, (u64)sp); atomicAdd(m + 4, (u64)sp2);
+    atomicAdd(m + 5, (u64)sb);
+    atomicAdd(m + 6, (u64)(sb2 & 0xffffffffull));
+    atomicAdd(m + 7, (u64)(sb2 >> 32));
 }
 
 } // namespace esl
