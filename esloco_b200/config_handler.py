@@ -99,7 +99,8 @@ _COMMON = (
     ("no_cov_plots", "bool", False), ("parallel_jobs", "int", 1), ("seed", "int", "<random>"),
     ("coverages", "json_list", "[1]"), ("mean_read_lengths", "json_list", "[10000]"),
     ("overlap_lists", "bool", False),  # extension: fill the per-read `overlap` column
-    ("length_sampler", None, "quantile"),  # extension: "quantile" (shared-memory inverse-CDF table) | "pool" (exact uniform pick)
+    ("length_sampler", None, "quantile"),
+    ("label_columns", None, "barcode"),  # extension: "reference" = the reference's first-appearance columns and total_Reads rule  # extension: "quantile" (shared-memory inverse-CDF table) | "pool" (exact uniform pick)
     ("blocked_regions_bedpath", None, None), ("consuming", "bool", False),
 )
 _MODE = {

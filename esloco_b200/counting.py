@@ -64,3 +64,21 @@ def label_counts_to_dict(counts, n_barcodes):
         if counts[n_barcodes + j]:
             out[name] = int(counts[n_barcodes + j])
     return out
+
+
+def label_first_appearance(engine, seed, combo, iteration, consuming, n_reads):
+    """Labels of one native iteration in the order they first appear among its reads -- the key order of the
+    reference's count_barcode_occurrences (counting.py:63-71).  The reads are regenerated on the device (counter-based
+    stream) and reduced there; only B + 2 positions come back."""
+    import torch
+    n_reads = int(n_reads)
+    B = engine.n_barcodes
+    names = [str(k) for k in range(B)] + list(LABELS_BLOCKED)
+    if n_reads == 0:
+        return []
+    _s, _l, lab = engine.materialize_reads(seed, combo, iteration, consuming, n_reads)
+    slot = torch.where(lab >= 0, lab, B - 1 - lab).long()  # -1 -> B (Blocked/Consuming), -2 -> B + 1
+    first = torch.full((B + 2,), n_reads, dtype=torch.int64, device=lab.device)
+    first.scatter_reduce_(0, slot, torch.arange(n_reads, device=lab.device), reduce="amin")
+    first = first.cpu().tolist()
+    return [names[k] for k in sorted(range(B + 2), key=lambda k: first[k]) if first[k] < n_reads]

@@ -175,8 +175,22 @@ def run(param_dictionary):
     out = None
     if rank == 0:
         its = list(range(p["iterations"]))
-        dist_df = barcode_distribution_table(p["n_barcodes"], combos, its, [x.cpu().numpy() for x in labels],
-                                             [x.cpu().numpy() for x in nbases])
+        labels_host = [x.cpu().numpy() for x in labels]
+
+        def first_appearance(_row, iteration_id, c):
+            # the reference's label order needs the reads of that iteration: regenerate them (any rank can, the stream
+            # is keyed by the iteration id) with the combination's length table resident
+            from .combined_calculations import _length_pool_key_and_factory
+            from .counting import label_first_appearance
+            mrl, _cov = combos[c]
+            key, factory = _length_pool_key_and_factory(int(p.get("seed", 0)), c, mrl, p.get("sequenced_data_path"),
+                                                        p["sigma"], p["min_read_length"])
+            sess.set_pool(key, factory)
+            return label_first_appearance(sess.engine, int(p.get("seed", 0)), c, iteration_id, p["consuming"],
+                                          int(labels_host[c][iteration_id].sum()))
+
+        dist_df = barcode_distribution_table(p["n_barcodes"], combos, its, labels_host, [x.cpu().numpy() for x in nbases],
+                                             label_columns=p.get("label_columns") or "barcode", first_appearance=first_appearance)
         summary = summary_table(keys, mode, combos, [m.cpu().numpy() for m in moments])
         try:
             if ws > 1:

@@ -142,13 +142,45 @@ class MatchesWriter:
                     shutil.copyfileobj(fh, out, 16 << 20)
 
 
-def barcode_distribution_table(n_barcodes, combos, iteration_ids, label_counts_per_combo, n_bases_per_combo):
+def barcode_distribution_table(n_barcodes, combos, iteration_ids, label_counts_per_combo, n_bases_per_combo,
+                               label_columns="barcode", first_appearance=None):
     """DataFrame of `{exp}_barcode_distribution_table.csv` (esloco.py:161-180): one row per (iteration,
-    combination); label columns, coverage, mean_read_length, iteration, N_bases, total_Reads.  All barcode columns
-    are always present (the reference drops barcodes without reads, which shifts its total_Reads sum onto other
-    columns); blocked columns appear only when such reads exist."""
+    combination); label columns, coverage, mean_read_length, iteration, N_bases, total_Reads.
+
+    label_columns="barcode" (default): all barcode columns, in barcode order, are always present and total_Reads is the
+    number of unblocked reads; blocked columns appear only when such reads exist.
+    label_columns="reference": the reference's layout, quirks included.  Every row is a dict
+    whose label keys come in the order the labels first appear among that iteration's reads (counting.py:63-71) with
+    labels that have no read left out; pandas then orders the columns by first appearance across the rows, so a label
+    first seen in a later row lands behind the bookkeeping columns, and total_Reads is the sum of the FIRST n_barcodes
+    COLUMNS (esloco.py:168,180) whatever they hold.  `first_appearance(row_index, iteration_id, combination)` must
+    return that iteration's labels in first-appearance order; it is only asked for rows that bring a label no earlier
+    row had (the first row always does) -- for the others the order of the keys cannot influence the columns."""
+    names = [str(k) for k in range(n_barcodes)] + list(LABELS_BLOCKED)
     rows = []
     lc = [np.asarray(x) for x in label_counts_per_combo]
+    if label_columns == "reference":
+        if first_appearance is None:
+            raise ValueError("the reference layout needs the first-appearance order of the labels")
+        known = []
+        for i, it in enumerate(iteration_ids):
+            for c, (mrl, cov) in enumerate(combos):
+                present = [names[k] for k in range(n_barcodes + 2) if lc[c][i, k]]
+                if any(nm not in known for nm in present):
+                    order = [nm for nm in first_appearance(len(rows), it, c) if nm in present]
+                    if sorted(order) != sorted(present):
+                        raise ValueError("first-appearance order does not cover the labels of its iteration")
+                    known += [nm for nm in order if nm not in known]
+                else:
+                    order = [nm for nm in known if nm in present]
+                row = {nm: int(lc[c][i, names.index(nm)]) for nm in order}
+                row.update(coverage=cov, mean_read_length=mrl, iteration=it, N_bases=int(np.asarray(n_bases_per_combo[c])[i]))
+                rows.append(row)
+        df = pd.DataFrame(rows)
+        df["total_Reads"] = df.iloc[:, :n_barcodes].sum(axis=1)  # esloco.py:168,180
+        return df
+    if label_columns != "barcode":
+        raise ValueError("label_columns must be 'barcode' or 'reference'")
     any_blocked = [any(x[:, n_barcodes + j].any() for x in lc) for j in range(2)]
     for i, it in enumerate(iteration_ids):
         for c, (mrl, cov) in enumerate(combos):

@@ -242,3 +242,38 @@ def test_cli_streaming_chunks_are_invisible(tmp_path, monkeypatch):
     assert len(m) == 5 * 2 * 6
     import ast
     assert all(sum(ast.literal_eval(o)) == b for o, b in zip(m["overlap"], m["on_target_bases"]))
+
+
+def test_cli_reference_label_columns(tmp_path):
+    """`label_columns = reference`: the barcode-distribution table gets the reference's layout (esloco.py:161-180,
+    counting.py:63-71) -- label columns in the order the labels first appear among the reads of the first row's
+    iteration, total_Reads = the sum of the first n_barcodes columns.  The expected order comes from an independent
+    route: the reads of that iteration as a reference-shaped dict, counted by the reference-style
+    count_barcode_occurrences."""
+    from esloco_b200.config_handler import parse_config
+    from esloco_b200.counting import count_barcode_occurrences
+    from esloco_b200.esloco import run
+    from esloco_b200.read_operations import generate_reads_based_on_coverage
+    from esloco_b200.session import lognormal_pool
+    from esloco_b200.utils import build_mask_tree
+    tmp = str(tmp_path)
+    ini, fmt = make_config(tmp, "ROI")
+    text = open(ini).read().replace("[ROI]", "label_columns = reference\nlength_sampler = pool\n\n[ROI]")
+    open(ini, "w").write(text)
+    p = parse_config(ini)
+    dist_df, _summary = run(p)
+    d = pd.read_csv(os.path.join(tmp, "out_ROI", "expROI_barcode_distribution_table.csv"), sep="\t")
+    assert list(d.columns) == list(dist_df.columns)
+    labels = list(d.columns[:list(d.columns).index("coverage")])
+    assert set(labels) == {"0", "1", "Blocked/NotConsuming"} == set(fmt["barcode_distribution_table.csv"]["columns"][:3])
+    assert list(d.columns)[3:] == fmt["barcode_distribution_table.csv"]["columns"][3:]
+    # first row = iteration 0 of combination 0 (mean read length 3000, coverage 2): its reads, counted the reference's way
+    G = 600_000
+    tree = build_mask_tree({"b1": {"start": 300_000 + 1000, "end": 300_000 + 90_000, "weight": 1, "barcode": []}})
+    pool = lognormal_pool(p["seed"], 0, 3000, p["sigma"], p["min_read_length"])
+    reads, covered = generate_reads_based_on_coverage(G, 2, pool, 2, p["barcode_weights"], False, tree, seed=p["seed"], iteration=0, combo=0)
+    hist = count_barcode_occurrences(reads)
+    assert labels == list(hist)  # first-appearance order
+    row0 = d.iloc[0]
+    assert [int(row0[k]) for k in labels] == [hist[k] for k in labels] and int(row0["N_bases"]) == covered
+    assert (d["total_Reads"] == d[labels[0]] + d[labels[1]]).all()  # the reference's rule: the first n_barcodes COLUMNS

@@ -149,7 +149,7 @@ def test_fasta_byte_scanner_chunk_boundaries(tmp_path):
 
 def test_parse_config_matches_reference(tmp_path):
     """parse_config returns the reference's parameter dictionary (keys, types, defaults, derived values) for the INI
-    files recorded from the unmodified reference in tests/golden/config_golden.json (+ the `overlap_lists` and `length_sampler` extensions)."""
+    files recorded from the unmodified reference in tests/golden/config_golden.json (+ the `overlap_lists`, `length_sampler` and `label_columns` extensions)."""
     import json
     from esloco_b200.config_handler import parse_config
     tmp = str(tmp_path)
@@ -164,6 +164,7 @@ def test_parse_config_matches_reference(tmp_path):
         got = parse_config(ini)
         assert got.pop("overlap_lists") is False
         assert got.pop("length_sampler") == "quantile"
+        assert got.pop("label_columns") == "barcode"
         got = json.loads(json.dumps(got, default=str).replace(tmp, "{tmp}"))
         assert got == case["params"], k
     bad = os.path.join(tmp, "bad.ini")

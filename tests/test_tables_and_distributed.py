@@ -76,6 +76,37 @@ def test_barcode_distribution_table():
     assert df["total_Reads"].tolist() == [12, 15] and df["N_bases"].tolist() == [111, 222]
 
 
+def test_barcode_distribution_table_reference_layout():
+    """label_columns="reference": what pandas makes of the reference's per-row dicts (esloco.py:161-180) -- label keys in
+    first-appearance order, labels without reads absent, a label first seen in a later row behind the bookkeeping
+    columns, total_Reads = sum of the first n_barcodes COLUMNS (Appendix C.5).  Expected frame written out by hand."""
+    from esloco_b200.tables import barcode_distribution_table
+    lc = np.array([[5, 7, 0, 0, 2], [6, 1, 8, 0, 0]])  # B = 3: barcode 2 has no read in iteration 0, nothing blocked in iteration 1
+    orders = {0: ["1", "Blocked/NotConsuming", "0"], 1: ["2", "0", "1"]}
+    asked = []
+
+    def first_appearance(row, it, c):
+        asked.append((row, it, c))
+        return orders[it]
+
+    df = barcode_distribution_table(3, [(1000, 2)], [0, 1], [lc], [np.array([111, 222])], label_columns="reference",
+                                    first_appearance=first_appearance)
+    exp = pd.DataFrame([
+        {"1": 7, "Blocked/NotConsuming": 2, "0": 5, "coverage": 2, "mean_read_length": 1000, "iteration": 0, "N_bases": 111},
+        {"2": 8, "0": 6, "1": 1, "coverage": 2, "mean_read_length": 1000, "iteration": 1, "N_bases": 222}])
+    exp["total_Reads"] = exp.iloc[:, :3].sum(axis=1)
+    assert list(df.columns) == ["1", "Blocked/NotConsuming", "0", "coverage", "mean_read_length", "iteration", "N_bases", "2", "total_Reads"]
+    pd.testing.assert_frame_equal(df, exp)
+    assert df["total_Reads"].tolist() == [14.0, 7.0]  # the quirk: 1 + Blocked + 0, barcode 2 left out
+    assert asked == [(0, 0, 0), (1, 1, 0)]
+    # a row that brings nothing new is not asked for its order
+    asked.clear()
+    lc2 = np.array([[5, 7, 1, 0, 0], [6, 1, 8, 0, 0]])
+    barcode_distribution_table(3, [(1000, 2)], [0, 1], [lc2], [np.array([1, 2])], label_columns="reference",
+                               first_appearance=lambda r, it, c: asked.append(r) or ["2", "0", "1"])
+    assert asked == [0]
+
+
 def test_shard_iterations_partition():
     from esloco_b200.distributed import shard_iterations
     for n in (0, 1, 7, 8, 1000):
