@@ -479,10 +479,31 @@ static_assert(kHotWords % 4 == 0, "the hot-target block must keep 16-byte alignm
 constexpr int kHotFlushTiles = 32;          // 32 tiles x 1024 reads x 0xffff < 2^32: the 32-bit shared sums cannot overflow
 static_assert((unsigned long long)kHotFlushTiles * kBulkTile * 0xffffull < (1ull << 32), "hot-target sums must fit 32 bits between flushes");
 
+// Rare paths of tally_hit, kept out of line: they would otherwise be compiled into every one of its call sites (the
+// bulk kernel of a masked run with many targets was 100 KB of code, and 14 % of its stall samples waited for
+// instructions).
+template <typename Src>
+__device__ __noinline__ bool thin_keeps(const Src &src, int it, i64 n, int row, double scaling)
+{
+    return src.scale_u(it, n, row) <= scaling; // counting.py:46,51
+}
+__device__ __noinline__ void record_hit(i64 *hits, u64 *hit_count, i64 hit_cap, int it, int row, i64 n, i64 ov, int kind)
+{
+    const u64 slot_h = atomicAdd(hit_count, 1ull);
+    if ((i64)slot_h < hit_cap) {
+        i64 *h = hits + slot_h * 4;
+        h[0] = it; h[1] = row; h[2] = n;
+        h[3] = ov | (kind == 0 ? (i64)0x8000000000000000ULL : 0); // sign bit = full match
+    }
+}
+
 // K6 + K7 for ONE target record a read [rs, re) was found to overlap (r.s < re and r.e > rs): add (sign = +1) or take
 // back (sign = -1) the read's contribution (counting.py:40-57).  s_hot = the CTA's private tallies of the hot targets
 // (bulk kernel) or null (cut-off kernel: plain atomics, it sees 0.4 % of the reads).
-template <typename C, typename Src>
+// kCompact: the rare paths (pair thinning, hit records) are calls instead of inline code -- for the queue rounds, whose
+// code is compiled into several places of the largest kernel; the walk-in-place callers keep them inline (as calls they
+// cost the small-target-set kernel 8 registers and 5 % of its throughput).
+template <typename C, typename Src, bool kCompact = false>
 __device__ __forceinline__ void tally_hit(const DevCtx<C> &cx, const Src &src, const DevOut &out, u64 *__restrict__ tallies_it, int it, i64 n,
                                           const TargetRec<C> &r, C rs, C re, i64 sign, uint32_t *s_hot)
 {
@@ -493,7 +514,8 @@ __device__ __forceinline__ void tally_hit(const DevCtx<C> &cx, const Src &src, c
     const int slot = row;
     if (r.row < 0) row = s_hot ? (int)s_hot[kHotSlots * 4 + slot] : __ldg(cx.hot_row + slot);
     ESL_CHK(row < cx.n_targets, "target row");
-    if ((u64)ov >= (u64)cx.min_ov32 && !(cx.thin && !(src.scale_u(it, n, row) <= cx.scaling))) {
+    if ((u64)ov >= (u64)cx.min_ov32 &&
+        !(cx.thin && !(kCompact ? thin_keeps(src, it, n, row, cx.scaling) : src.scale_u(it, n, row) <= cx.scaling))) {
         const int kind = (rs <= r.s && r.e <= re) ? 0 : 1;
         if (r.row < 0 && s_hot) {
             // bulk kernel: hits go to the CTA's private 32-bit sums in shared memory (flushed to the global
@@ -509,11 +531,15 @@ __device__ __forceinline__ void tally_hit(const DevCtx<C> &cx, const Src &src, c
             atomicAdd(t + 2, (u64)(sign * (i64)ov));
         }
         if (out.hits && sign > 0) { // draws beyond the cut-off are dropped on the host by their index
-            const u64 slot_h = atomicAdd(out.hit_count, 1ull);
-            if ((i64)slot_h < out.hit_cap) {
-                i64 *h = out.hits + slot_h * 4;
-                h[0] = it; h[1] = row; h[2] = n;
-                h[3] = (i64)ov | (kind == 0 ? (i64)0x8000000000000000ULL : 0); // sign bit = full match
+            if (kCompact) {
+                record_hit(out.hits, out.hit_count, out.hit_cap, it, row, n, (i64)ov, kind);
+            } else {
+                const u64 slot_h = atomicAdd(out.hit_count, 1ull);
+                if ((i64)slot_h < out.hit_cap) {
+                    i64 *h = out.hits + slot_h * 4;
+                    h[0] = it; h[1] = row; h[2] = n;
+                    h[3] = (i64)ov | (kind == 0 ? (i64)0x8000000000000000ULL : 0); // sign bit = full match
+                }
             }
         }
     }
@@ -663,7 +689,7 @@ struct WalkItem {
     uint32_t sg;  // run (layer) index            | mask items: first candidate in the "ALL" tree (or -1)
     uint32_t n;   // draw index in the iteration  | mask items: barcode | slot in the warp's tile row << 16
 };
-constexpr int kQueueCap = 64;      // target items per warp: < 32 carried over + <= 32 pushed (a round pops 32 before it pushes back)
+constexpr int kQueueCap = 96;      // target items per warp: < 32 carried over + <= 64 pushed (a round pops 32 before it pushes back)
 constexpr int kMaskQueueCap = 64;  // mask items per warp; drained early when the next 32 pushes may not fit
 constexpr int kQueueSegBits = 22;  // the host keeps the number of runs below 2^22
 constexpr int kCrowdedBit = 1 << 30;
@@ -739,7 +765,7 @@ __device__ __forceinline__ int queue_round(const DevCtx<C> &cx, const Src &src, 
             ESL_CHK(j >= 0 && j < cx.n_trec, "target record index");
             const TargetRec<C> r = load_rec(cx.trec + j);
             if (r.s < re) { // else: starts ascend, nothing further overlaps
-                if (r.e > rs) tally_hit(cx, src, out, tallies_it, it, (i64)w.n, r, rs, re, 1, s_hot);
+                if (r.e > rs) tally_hit<C, Src, true>(cx, src, out, tallies_it, it, (i64)w.n, r, rs, re, 1, s_hot);
                 more = r.s_next < re; // known without touching the next record (all ones behind a run's last record)
             }
             w.a = j + 1;
@@ -1052,7 +1078,8 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 for (int i = 0; i < kBulkIpt; ++i) {
                     // (a read the blocked-region phase relabelled keeps its probe but is not tallied)
                     queue_push(queue, qn, label[i] >= 0 && pt[i].s < (C)(st[i] + L[i]), st[i], L[i], pt[i].a, (uint32_t)label[i], n0 + i, with_n);
-                    while (qn >= 32) qn = queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
+                    if (i & 1) // two reads per batch of rounds: half the copies of the round's code
+                        while (qn >= 32) qn = queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
                 }
                 if (cx.any_extra) { // nesting targets somewhere: layer k of every read's barcode, k ascending
                     int ne_max = 0;
@@ -1077,7 +1104,8 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                                 pe = Probe<C>{e.j | ((d.y & 0x100) ? kCrowdedBit : 0), e.s};
                             }
                             queue_push(queue, qn, pe.s < (C)(st[i] + L[i]), st[i], L[i], pe.a, (uint32_t)sg, n0 + i, with_n);
-                            while (qn >= 32) qn = queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
+                            if (i & 1)
+                                while (qn >= 32) qn = queue_round(cx, src, out, tallies_it, it, queue, qn, with_n, s_hot);
                         }
                     }
                 }
