@@ -24,6 +24,8 @@ SYMBOLS = {
     "esl_set_targets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_blocked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_length_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "esl_set_index_builder": (C.c_int, [C.c_void_p, C.c_int32]),
+    "esl_index_built_on_device": (C.c_int32, [C.c_void_p]),
     "esl_set_length_sampler": (C.c_int, [C.c_void_p, C.c_int32]),
     "esl_pool_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
     "esl_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),

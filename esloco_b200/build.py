@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libesloco_b200.so")
 SOURCES = ["esl_api.cu", "seqscan.cpp", "tablewriter.cpp"]
-DEPS = ["esl_api.cu", "seqscan.cpp", "tablewriter.cpp", "kernels.cuh", "philox.cuh", "staged.cuh", os.path.join("..", "..", "include", "esloco_b200.h")]
+DEPS = ["esl_api.cu", "seqscan.cpp", "tablewriter.cpp", "kernels.cuh", "philox.cuh", "staged.cuh", "index_build.cuh", os.path.join("..", "..", "include", "esloco_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

@@ -14,6 +14,7 @@
 #include "../../include/esloco_b200.h"
 #include "kernels.cuh"
 #include "staged.cuh"
+#include "index_build.cuh"
 
 using esl::i64;
 using esl::u64;
@@ -52,6 +53,33 @@ struct DevBuf {
     template <typename T> T *as() const { return (T *)p; }
 };
 
+// Host array in page-locked memory (the targets: set-up uploads them straight from here).  Just enough of std::vector.
+template <typename T>
+struct PinnedVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    ~PinnedVec() { if (p) cudaFreeHost(p); }
+    bool assign(const T *first, const T *last)
+    {
+        const size_t m = (size_t)(last - first);
+        if (m > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            if (cudaMallocHost((void **)&p, (m + m / 4 + 64) * sizeof(T)) != cudaSuccess) { p = nullptr; n = 0; return false; }
+            cap = m + m / 4 + 64;
+        }
+        if (m) memcpy(p, first, m * sizeof(T));
+        n = m;
+        return true;
+    }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    const T *data() const { return p; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
+
+struct SortScratch { DevBuf keys[2], vals[2], hist; };
+
 } // namespace
 
 struct esl_ctx {
@@ -63,8 +91,10 @@ struct esl_ctx {
     u64 G = 0;
     int B = 0;
     std::vector<double> cdf;
-    std::vector<i64> t_start, t_end;
-    std::vector<int32_t> t_bc;
+    PinnedVec<i64> t_start, t_end;
+    PinnedVec<int32_t> t_bc;
+    int index_builder = ESL_INDEX_AUTO; // esl_set_index_builder
+    bool index_on_device = false;       // how the current target index was built
     std::vector<i64> m_start, m_end;
     std::vector<double> m_w;
     std::vector<int32_t> m_bc;
@@ -89,7 +119,9 @@ struct esl_ctx {
     // quantile length sampler (esl_set_length_sampler): sorted pool + quantile table, built by esl_prepare
     int sampler = ESL_SAMPLER_POOL;
     bool qtab_dirty = true;
-    DevBuf d_pool_sorted, d_qtab, d_sort_keys, d_sort_vals_a, d_sort_vals_b, d_sort_hist;
+    DevBuf d_pool_sorted, d_qtab;
+    SortScratch sort;
+    DevBuf d_idx_key_s, d_idx_key_b, d_idx_res; // device index builder
     DevBuf d_mbits;
     int mbits_shift = 0, mbits_words = 0; // blocked-bucket bitmap (kernels.cuh DevCtx::mbits)
     u64 sgrid_lmax = 0;               // longest read its upper bounds were built for
@@ -347,12 +379,12 @@ void parallel_for(int n, int n_thr, F f)
 
 struct LayerPlan { int barcode, lo, hi, grid_off, shift; u64 nb; const std::vector<Rec> *recs; };
 
+// The target index built on the host: any geometry (nesting layers, hot targets, the shared pre-filter of small sets).
 template <typename C>
-int upload_index(esl_ctx *ctx, cudaStream_t st)
+int build_targets_host(esl_ctx *ctx, cudaStream_t st, PhaseTimer &tm)
 {
     const int B = ctx->B;
     const u64 G = ctx->G;
-    PhaseTimer tm;
     esl_host_scratch &hs = *ctx->host;
     if (!hs.uploaded) CU(cudaEventCreateWithFlags(&hs.uploaded, cudaEventDisableTiming));
     CU(cudaEventSynchronize(hs.uploaded)); // an earlier prepare may still be copying out of the pinned buffers
@@ -551,6 +583,127 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
     CU(ctx->d_seg.upload(seg.data(), seg.size() * sizeof(esl::SegDesc), st));
     CU(ctx->d_extra_off.upload(extra_off.data(), extra_off.size() * sizeof(int32_t), st));
     tm.mark("target uploads");
+    ctx->index_on_device = false;
+    return ESL_OK;
+}
+
+// LSD radix sort of n 32-bit keys (+ 32-bit payload; vals_in == NULL: the payload is the element's index) on the
+// device with the staged baseline's sort kernels, 8-bit digits, as many passes as max_key needs.  Asynchronous;
+// *keys_out / *vals_out point into the scratch buffers.
+int device_radix_sort(esl_ctx *ctx, SortScratch &sc, const uint32_t *keys_in, const uint32_t *vals_in, i64 n, uint32_t max_key,
+                      const uint32_t **keys_out, const uint32_t **vals_out, cudaStream_t st)
+{
+    const int sort_blocks = (int)((n + esl::kSortTile - 1) / esl::kSortTile);
+    for (int i = 0; i < 2; ++i) {
+        CU(sc.keys[i].reserve((size_t)n * 4));
+        CU(sc.vals[i].reserve((size_t)n * 4));
+    }
+    CU(sc.hist.reserve((size_t)sort_blocks * 256 * 4 + 256 * 4 + 16));
+    uint32_t *hist = sc.hist.as<uint32_t>(), *digit_tot = hist + (size_t)sort_blocks * 256;
+    int *n_dev = (int *)(digit_tot + 256);
+    const int n_host = (int)n;
+    CU(cudaMemcpyAsync(n_dev, &n_host, sizeof(int), cudaMemcpyHostToDevice, st));
+    int passes = 1;
+    while (passes < 4 && (max_key >> (8 * passes)) != 0) ++passes;
+    const uint32_t *kin = keys_in, *vin = vals_in;
+    for (int pass = 0; pass < passes; ++pass) {
+        uint32_t *ko = sc.keys[pass & 1].as<uint32_t>(), *vo = sc.vals[pass & 1].as<uint32_t>();
+        esl::k_rs_hist<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, n_dev, pass * 8, sort_blocks, hist);
+        esl::k_rs_scan_rows<<<256, 1024, 0, st>>>(hist, sort_blocks, digit_tot);
+        esl::k_rs_scan_digits<<<1, 1024, 0, st>>>(digit_tot);
+        esl::k_rs_scatter<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, vin, ko, vo, n_dev, pass * 8, sort_blocks, hist, digit_tot,
+                                                                  pass == 0 && vals_in == nullptr);
+        kin = ko; vin = vo;
+        ctx->launches += 4;
+    }
+    CU(cudaGetLastError());
+    *keys_out = kin;
+    if (vals_out) *vals_out = vin;
+    return ESL_OK;
+}
+
+// The target index built on the device (index_build.cuh): large target sets with 32-bit coordinates whose ends ascend
+// with their starts inside every barcode and that hold no hot target.  *built = false: the geometry needs the host builder.
+int build_targets_device(esl_ctx *ctx, cudaStream_t st, PhaseTimer &tm, bool *built)
+{
+    *built = false;
+    const int B = ctx->B;
+    const u64 G = ctx->G;
+    const int n = (int)ctx->t_start.size();
+    // raw targets in caller order, straight from the page-locked copies esl_set_targets made
+    CU(ctx->d_raw_ts.reserve((size_t)n * 8)); CU(ctx->d_raw_te.reserve((size_t)n * 8)); CU(ctx->d_raw_tb.reserve((size_t)n * 4));
+    CU(cudaMemcpyAsync(ctx->d_raw_ts.p, ctx->t_start.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_raw_te.p, ctx->t_end.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_raw_tb.p, ctx->t_bc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    ctx->raw_dirty = false;
+    CU(ctx->d_idx_key_s.reserve((size_t)n * 4)); CU(ctx->d_idx_key_b.reserve((size_t)n * 4));
+    CU(ctx->d_idx_res.reserve(sizeof(esl::IdxResult)));
+    CU(ctx->d_trec.reserve((size_t)n * sizeof(esl::TargetRec<uint32_t>)));
+    CU(ctx->d_te.reserve((size_t)n * 4));
+    CU(ctx->d_seg.reserve((size_t)B * sizeof(esl::SegDesc)));
+    CU(ctx->d_extra_off.reserve((size_t)B * 4));
+    const size_t grid_cap = (size_t)kBucketsPerInterval * (size_t)n + (size_t)B * (size_t)((G >> 16) + 67);
+    CU(ctx->d_tgrid.reserve(grid_cap * sizeof(esl::GridEntry<uint32_t>)));
+    CU(ctx->d_hot_row.reserve(esl::kHotSlots * sizeof(int32_t)));
+    CU(cudaMemsetAsync(ctx->d_idx_res.p, 0, sizeof(esl::IdxResult), st));
+    const i64 *ts = ctx->d_raw_ts.as<i64>(), *te = ctx->d_raw_te.as<i64>();
+    uint32_t *key_s = ctx->d_idx_key_s.as<uint32_t>(), *key_b = ctx->d_idx_key_b.as<uint32_t>();
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    esl::k_idx_keys<<<blocks, 256, 0, st>>>(ts, te, ctx->d_raw_tb.as<int32_t>(), n, B, G, key_s, key_b);
+    const uint32_t *sorted = nullptr, *perm = nullptr;
+    int rc = device_radix_sort(ctx, ctx->sort, key_s, nullptr, n, 0xFFFFFFFFu, &sorted, &perm, st); // by start; payload = row
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(key_s, perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, st)); // the rows in start order, out of the sort's way
+    uint32_t *bc_by_start = ctx->d_te.as<uint32_t>();                              // (scratch until k_idx_records fills it)
+    esl::k_idx_gather<<<blocks, 256, 0, st>>>(key_b, key_s, n, bc_by_start);
+    const uint32_t *kb = nullptr;
+    rc = device_radix_sort(ctx, ctx->sort, bc_by_start, key_s, n, (uint32_t)B, &kb, &perm, st); // stable: by barcode, starts stay ordered
+    if (rc) return rc;
+    esl::IdxResult *res = ctx->d_idx_res.as<esl::IdxResult>();
+    esl::k_idx_bounds<<<1, 1024, 0, st>>>(kb, n, B, G, kBucketsPerInterval, ctx->d_seg.as<esl::SegDesc>(), ctx->d_extra_off.as<int32_t>(), res);
+    const double hot_len = (double)G / 512.0 - ctx->pool_mean;
+    esl::k_idx_records<<<blocks, 256, 0, st>>>(ts, te, perm, kb, ctx->d_seg.as<esl::SegDesc>(), n, B, G, hot_len,
+                                                ctx->d_trec.as<esl::TargetRec<uint32_t>>(), ctx->d_te.as<uint32_t>(), res);
+    esl::k_idx_grid<<<(unsigned)((grid_cap + 255) / 256), 256, 0, st>>>(ctx->d_seg.as<esl::SegDesc>(), B, ctx->d_trec.as<esl::TargetRec<uint32_t>>(),
+                                                                        ctx->d_te.as<uint32_t>(), res, ctx->d_tgrid.as<esl::GridEntry<uint32_t>>());
+    CU(cudaGetLastError());
+    ctx->launches += 5;
+    esl::IdxResult h;
+    CU(cudaMemcpyAsync(&h, res, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st)); // one small read-back decides whether the geometry was simple enough
+    tm.mark("device target index");
+    if (h.flags) return ESL_OK; // nested or hot targets: the host builder takes over
+    ctx->n_layers = ctx->n_first_layers = h.n_nonempty;
+    ctx->n_indexed = h.n_valid;
+    ctx->n_hot = 0;
+    ctx->sgrid_n = 0;
+    ctx->sgrid_lmax = 1;
+    while (ctx->sgrid_lmax < (u64)ctx->pool_max) ctx->sgrid_lmax <<= 1;
+    ctx->n_seg = B; ctx->n_tgrid = h.n_grid; ctx->n_trec = h.n_valid;
+    ctx->index_on_device = true;
+    *built = true;
+    return ESL_OK;
+}
+
+template <typename C>
+int upload_index(esl_ctx *ctx, cudaStream_t st)
+{
+    const int B = ctx->B;
+    const u64 G = ctx->G;
+    PhaseTimer tm;
+    // who builds the target index: the device for large sets with 32-bit coordinates (it hands back to the host when it
+    // meets nesting or hot targets), the host otherwise; esl_set_index_builder overrides the size rule
+    bool on_device = false;
+    const bool try_device = sizeof(C) == 4 && ctx->index_builder != ESL_INDEX_HOST && ctx->t_start.size() > 0 &&
+                            (ctx->index_builder == ESL_INDEX_DEVICE || ctx->t_start.size() >= 16384);
+    if (try_device) {
+        int rc = build_targets_device(ctx, st, tm, &on_device);
+        if (rc) return rc;
+    }
+    if (!on_device) {
+        int rc = build_targets_host<C>(ctx, st, tm);
+        if (rc) return rc;
+    }
     // blocked intervals: group g < B = barcode g, group B = "ALL"; (start, end) order, running max of ends
     std::vector<C> ms, me, mp;
     std::vector<double> mw;
@@ -643,37 +796,16 @@ bool index_stale(const esl_ctx *ctx)
            (ctx->have_pool && ctx->sampler == ESL_SAMPLER_QUANTILE && ctx->qtab_dirty);
 }
 
-// Quantile sampler set-up: LSD radix sort of the resident pool on the device (the staged baseline's sort kernels,
-// 8-bit digits, as many passes as the longest read needs) and the quantile table of the sorted pool.  Asynchronous.
+// Quantile sampler set-up: the resident pool sorted on the device, and its quantile table.  Asynchronous.
 int build_quantile_table(esl_ctx *ctx, cudaStream_t st)
 {
     const i64 n = ctx->n_pool;
-    const int sort_blocks = (int)((n + esl::kSortTile - 1) / esl::kSortTile);
     CU(ctx->d_pool_sorted.reserve((size_t)n * 4));
-    CU(ctx->d_sort_keys.reserve((size_t)n * 4));
-    CU(ctx->d_sort_vals_a.reserve((size_t)n * 4));
-    CU(ctx->d_sort_vals_b.reserve((size_t)n * 4));
-    CU(ctx->d_sort_hist.reserve((size_t)sort_blocks * 256 * 4 + 256 * 4 + 16));
     CU(ctx->d_qtab.reserve((size_t)(esl::kQuantBins + 1) * 4));
-    uint32_t *hist = ctx->d_sort_hist.as<uint32_t>(), *digit_tot = hist + (size_t)sort_blocks * 256;
-    int *n_dev = (int *)(digit_tot + 256);
-    const int n_host = (int)n;
-    CU(cudaMemcpyAsync(n_dev, &n_host, sizeof(int), cudaMemcpyHostToDevice, st));
-    int passes = 1;
-    while (passes < 4 && (ctx->pool_max >> (8 * passes)) != 0) ++passes;
-    // ping-pong so that the LAST pass lands in d_pool_sorted
-    uint32_t *bufs[2] = {ctx->d_sort_keys.as<uint32_t>(), ctx->d_pool_sorted.as<uint32_t>()};
-    uint32_t *vals[2] = {ctx->d_sort_vals_a.as<uint32_t>(), ctx->d_sort_vals_b.as<uint32_t>()};
-    const uint32_t *kin = ctx->d_pool.as<uint32_t>(), *vin = nullptr;
-    for (int pass = 0; pass < passes; ++pass) {
-        const int o = (passes - 1 - pass) & 1 ? 0 : 1; // output buffer: index 1 on the last pass
-        esl::k_rs_hist<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, n_dev, pass * 8, sort_blocks, hist);
-        esl::k_rs_scan_rows<<<256, 1024, 0, st>>>(hist, sort_blocks, digit_tot);
-        esl::k_rs_scan_digits<<<1, 1024, 0, st>>>(digit_tot);
-        esl::k_rs_scatter<<<sort_blocks, esl::kStageBlock, 0, st>>>(kin, vin, bufs[o], vals[o], n_dev, pass * 8, sort_blocks, hist, digit_tot, pass == 0);
-        kin = bufs[o]; vin = vals[o];
-        ctx->launches += 4;
-    }
+    const uint32_t *sorted = nullptr;
+    int rc = device_radix_sort(ctx, ctx->sort, ctx->d_pool.as<uint32_t>(), nullptr, n, ctx->pool_max, &sorted, nullptr, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->d_pool_sorted.p, sorted, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     esl::k_quantile_table<<<(esl::kQuantBins + 256) / 256, 256, 0, st>>>(ctx->d_pool_sorted.as<uint32_t>(), n, ctx->d_qtab.as<uint32_t>());
     CU(cudaGetLastError());
     ctx->launches++;
@@ -969,9 +1101,9 @@ int esl_set_targets(esl_ctx *ctx, const int64_t *start, const int64_t *end, cons
     if (n < 0 || n > 0x7fffffff / 3 || (n && (!start || !end || !barcode))) return ctx->fail(ESL_ERR_INVALID, "bad target arrays");
     for (int64_t i = 0; i < n; ++i)
         if (start[i] < 0 || end[i] < 0) return ctx->fail(ESL_ERR_INVALID, "target %lld has a negative coordinate", (long long)i);
-    ctx->t_start.assign(start, start + n);
-    ctx->t_end.assign(end, end + n);
-    ctx->t_bc.assign(barcode, barcode + n);
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->t_start.assign(start, start + n) || !ctx->t_end.assign(end, end + n) || !ctx->t_bc.assign(barcode, barcode + n))
+        return ctx->fail(ESL_ERR_CUDA, "cannot allocate page-locked memory for %lld targets", (long long)n);
     ctx->have_targets = true;
     ctx->index_dirty = true;
     return ESL_OK;
@@ -1023,6 +1155,17 @@ int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n, void 
     ctx->qtab_dirty = true;
     return ESL_OK;
 }
+
+int esl_set_index_builder(esl_ctx *ctx, int32_t mode)
+{
+    if (!ctx) return ESL_ERR_INVALID;
+    if (mode != ESL_INDEX_AUTO && mode != ESL_INDEX_HOST && mode != ESL_INDEX_DEVICE) return ctx->fail(ESL_ERR_INVALID, "unknown index builder %d", mode);
+    if (mode != ctx->index_builder) ctx->index_dirty = true;
+    ctx->index_builder = mode;
+    return ESL_OK;
+}
+
+int32_t esl_index_built_on_device(const esl_ctx *ctx) { return ctx && ctx->index_on_device ? 1 : 0; }
 
 int esl_set_length_sampler(esl_ctx *ctx, int32_t mode)
 {

@@ -121,6 +121,14 @@ class Engine:
         code = {"pool": _native.ESL_SAMPLER_POOL, "quantile": _native.ESL_SAMPLER_QUANTILE}[mode]
         self._check(self.lib.esl_set_length_sampler(self.ctx, code))
 
+    def set_index_builder(self, mode):
+        """"auto" (device for >= 16384 targets with 32-bit coordinates, host otherwise), "host" or "device"."""
+        self._check(self.lib.esl_set_index_builder(self.ctx, {"auto": 0, "host": 1, "device": 2}[mode]))
+
+    def index_built_on_device(self):
+        self.prepare()
+        return bool(self.lib.esl_index_built_on_device(self.ctx))
+
     def pool_stats(self):
         """(mean, sd, longest) of the resident length table, reduced on the device when it was uploaded."""
         m, sd, mx = C.c_double(), C.c_double(), C.c_uint32()

@@ -117,6 +117,19 @@ int esl_set_length_table(esl_ctx *ctx, const uint32_t *lengths, int64_t n, void 
 #define ESL_SAMPLER_QUANTILE 1
 int esl_set_length_sampler(esl_ctx *ctx, int32_t mode);
 
+/* Who builds the target index in esl_prepare.  ESL_INDEX_AUTO (default): the device for sets of >= 16384 targets with
+ * 32-bit coordinates -- a radix sort by (barcode, start) and two parallel passes write the records and bucket grids,
+ * no host work beyond the upload of the raw targets -- the host otherwise.  The device builder handles one layer per
+ * barcode; when it meets nesting (an end below its predecessor's) or hot targets it hands the set to the host
+ * builder, which handles every geometry.  ESL_INDEX_HOST / ESL_INDEX_DEVICE force one (the latter still falls back).
+ * Both builders produce indexes that give identical tallies. */
+#define ESL_INDEX_AUTO 0
+#define ESL_INDEX_HOST 1
+#define ESL_INDEX_DEVICE 2
+int esl_set_index_builder(esl_ctx *ctx, int32_t mode);
+/* 1 when the current target index came from the device builder (after esl_prepare). */
+int32_t esl_index_built_on_device(const esl_ctx *ctx);
+
 /* Statistics of the resident length table as the device reduced them (any pointer may be NULL). */
 int esl_pool_stats(const esl_ctx *ctx, double *mean, double *sd, uint32_t *longest);
 
