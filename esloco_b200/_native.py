@@ -22,6 +22,7 @@ SYMBOLS = {
     "esl_set_genome": (C.c_int, [C.c_void_p, C.c_uint64]),
     "esl_set_barcode_cdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "esl_set_targets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "esl_targets_equal": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_blocked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "esl_set_length_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "esl_set_index_builder": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -1109,6 +1109,15 @@ int esl_set_targets(esl_ctx *ctx, const int64_t *start, const int64_t *end, cons
     return ESL_OK;
 }
 
+int32_t esl_targets_equal(const esl_ctx *ctx, const int64_t *start, const int64_t *end, const int32_t *barcode, int64_t n)
+{
+    if (!ctx || !ctx->have_targets || n < 0 || (size_t)n != ctx->t_start.size()) return 0;
+    if (n == 0) return 1;
+    if (!start || !end || !barcode) return 0;
+    return memcmp(start, ctx->t_start.data(), (size_t)n * 8) == 0 && memcmp(end, ctx->t_end.data(), (size_t)n * 8) == 0 &&
+           memcmp(barcode, ctx->t_bc.data(), (size_t)n * 4) == 0;
+}
+
 int esl_set_blocked(esl_ctx *ctx, const int64_t *start, const int64_t *end, const double *weight,
                     const int32_t *barcode, int64_t n)
 {

@@ -101,6 +101,13 @@ class Engine:
         self._check(self.lib.esl_set_targets(self.ctx, s.ctypes.data, e.ctypes.data, b.ctypes.data, s.size))
         self.n_targets = int(s.size)
 
+    def targets_equal(self, start, end, barcode):
+        """True when the arrays equal the targets the context already holds (compared inside the library)."""
+        s, e, b = _np(start, np.int64), _np(end, np.int64), _np(barcode, np.int32)
+        if not (s.size == e.size == b.size):
+            return False
+        return bool(self.lib.esl_targets_equal(self.ctx, s.ctypes.data, e.ctypes.data, b.ctypes.data, s.size))
+
     def set_blocked(self, start=(), end=(), weight=(), barcode=()):
         s, e, w, b = _np(start, np.int64), _np(end, np.int64), _np(weight, np.float64), _np(barcode, np.int32)
         if not (s.size == e.size == w.size == b.size):

@@ -30,6 +30,7 @@ class Session:
     def invalidate(self):
         """Forget what is uploaded: the next configure / set_pool sends everything again."""
         self._targets = None
+        self._targets_valid = False
         self._mask = None
         self._bc_key = None
         self._pool_key = None
@@ -55,12 +56,15 @@ class Session:
         if bc_key != self._bc_key:
             eng.set_barcode_cdf(barcode_cdf(barcode_probabilities(n_barcodes, barcode_weights)))
             self._bc_key = bc_key
-            self._targets = self._mask = None
+            self._targets_valid = False
+            self._mask = None
         keys, ts, te, tb = targets_to_arrays(target_regions, n_barcodes)
         self.keys = keys
-        if not _same(self._targets, (ts, te, tb)):
+        # (the library keeps its own copy of the targets and compares against it: no second copy on this side)
+        if not (self._targets_valid and eng.targets_equal(ts, te, tb)):
             eng.set_targets(ts, te, tb)
-            self._targets = (ts.copy(), te.copy(), tb.copy())
+            self._targets_valid = True
+        self._targets = (ts, te, tb)  # this call's arrays, for expected_pairs_per_iteration
         mask = mask_tree_to_arrays(masked_tree, n_barcodes)
         if not _same(self._mask, mask):
             eng.set_blocked(*mask)

@@ -89,6 +89,10 @@ int esl_set_barcode_cdf(esl_ctx *ctx, const double *cdf, int32_t n_barcodes);
 int esl_set_targets(esl_ctx *ctx, const int64_t *start, const int64_t *end, const int32_t *barcode,
                     int64_t n_targets);
 
+/* 1 when the arrays equal the targets the context holds (a caller that is handed the same target set again, as the
+ * reference's per-iteration call pattern does, can skip esl_set_targets and the index rebuild it triggers). */
+int32_t esl_targets_equal(const esl_ctx *ctx, const int64_t *start, const int64_t *end, const int32_t *barcode, int64_t n_targets);
+
 /* Blocked intervals of build_mask_tree (utils.py:89-101): barcode >= 0 for that barcode's tree, -1 for "ALL".
  * A read [s, s+L) hits interval k iff start[k] < s+L and end[k] > s (read_operations.py:63); each visited hit
  * draws u and blocks when u < weight[k] (:65).  n = 0 clears the mask. */
