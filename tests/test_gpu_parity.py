@@ -830,9 +830,11 @@ def test_quantile_length_sampler_exact_and_close_to_the_pool(eng, wide):
     assert np.array_equal(again.tallies.numpy(), base.tallies.numpy()) and int(again.n_reads[0]) == int(base.n_reads[0])
 
 
-def test_device_index_builder_equals_host_builder(eng):
+@pytest.mark.parametrize("B", [6, 1300])
+def test_device_index_builder_equals_host_builder(eng, B):
     """esl_prepare builds the target index of large, non-nesting sets on the device (radix sort by (barcode, start) +
-    two parallel passes).  20 k targets over 6 barcodes (one of them without targets), with targets that match no
+    two parallel passes).  20 k targets over B barcodes (the last one without targets; 1300 barcodes take the bounds
+    kernel through two chunks and the bulk kernel through descriptors in global memory), with targets that match no
     barcode, empty ones, ones starting beyond the genome end, exact duplicates, and a cluster of 300 short targets
     inside one grid bucket (the crowded-bucket bisect): device-built and host-built indexes give the same integers as
     the CPU restatement; a nested pair sends the device builder back to the host."""
@@ -841,7 +843,7 @@ def test_device_index_builder_equals_host_builder(eng):
     n = 20_000
     ts = np.sort(rng.randint(0, G - 3000, n)).astype(np.int64)
     te = ts + 2500
-    tb = rng.randint(0, 5, n).astype(np.int32)  # barcode 5 gets nothing
+    tb = rng.randint(0, B - 1, n).astype(np.int32)  # the last barcode gets nothing
     tb[::97] = -1                               # matches no barcode
     te[5::211] = ts[5::211]                     # empty
     ts[-3:] = G + np.array([0, 10, 5000]); te[-3:] = ts[-3:] + 2500  # start at / beyond the genome end
@@ -849,13 +851,13 @@ def test_device_index_builder_equals_host_builder(eng):
     c0 = 123_456_789
     ts[2000:2300] = c0 + np.arange(300) * 30; te[2000:2300] = ts[2000:2300] + 50; tb[2000:2300] = 2  # 300 targets in 9 kb
     order = np.argsort(ts, kind="stable"); ts, te, tb = ts[order], te[order], tb[order]
-    cdf = np.array([0.3, 0.5, 0.6, 0.8, 0.9, 1.0])
+    cdf = np.cumsum(rng.rand(B) + 0.2); cdf /= cdf[-1]; cdf[2] = max(cdf[2], 0.2); cdf = np.maximum.accumulate(cdf); cdf[-1] = 1.0
     pool = O.lognormal_pool(O.Rng(9), 6000, 1, 50, n=200000)
     cov = 3.0
     eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
     eng.set_length_table(pool)
     it = NN.native_iteration(31, 2, 5, G, cov, pool, cdf)
-    exp = O.count_matches_indexed(ts, te, tb, 6, it["start"], it["start"] + it["length"], it["label"], 1)
+    exp = O.count_matches_indexed(ts, te, tb, B, it["start"], it["start"] + it["length"], it["label"], 1)
     try:
         got = {}
         for mode in ("device", "host"):
@@ -866,7 +868,7 @@ def test_device_index_builder_equals_host_builder(eng):
             assert int(res.n_reads[0]) == it["n_placed"]
             assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"]), mode
             got[mode] = t
-        assert got["device"][:, 2].sum() > 0 and got["device"][2000:2300, 2].sum() > 0
+        assert got["device"][:, 2].sum() > 0 and got["device"][tb == 2, 2].sum() > 0
         # one nested target (it ends before its predecessor in the same barcode does): the device builder declines, the
         # result stays exact
         k = next(i for i in range(5000, n) if tb[i - 1] >= 0 and te[i - 1] > ts[i - 1] + 100 and ts[i] > ts[i - 1])
@@ -876,7 +878,7 @@ def test_device_index_builder_equals_host_builder(eng):
         eng.set_targets(ts2, te2, tb2)
         res = eng.run_batch(31, 2, 5, 1, cov).cpu()
         assert not eng.index_built_on_device()
-        exp2 = O.count_matches_indexed(ts2, te2, tb2, 6, it["start"], it["start"] + it["length"], it["label"], 1)
+        exp2 = O.count_matches_indexed(ts2, te2, tb2, B, it["start"], it["start"] + it["length"], it["label"], 1)
         assert np.array_equal(res.tallies[0, :, 2].numpy(), exp2["otb"])
     finally:
         eng.set_index_builder("auto")
