@@ -66,6 +66,44 @@ insertion_numbers = 100
                    log_tail=[ln for ln in open(os.path.join(out, "cfg2_log.log")).read().splitlines() if "seconds" in ln][-3:])
     else:
         res["stderr"] = r.stderr[-1500:]
+    # the same CLI at the config-3 shape: 24 weighted barcodes, 10 k insertions per barcode (240 k targets), 40 iterations
+    # = 9.6 M rows of matches_table.csv through the pipelined native row writer
+    ini3 = os.path.join(work, "cfg3.ini")
+    open(ini3, "w").write(f"""[COMMON]
+mode = I
+reference_genome_path = {fasta}
+output_path = {work}/out3/
+experiment_name = cfg3
+n_barcodes = 24
+barcode_weights = {{"0": 10, "1": 5}}
+iterations = 40
+coverages = [30]
+mean_read_lengths = [15000]
+no_cov_plots = True
+seed = 20261019
+label_columns = reference
+
+[I]
+insertion_length = 5000
+insertion_numbers = 10000
+""")
+    t0 = time.time()
+    r3 = subprocess.run([sys.executable, "-m", "esloco_b200", "--config", ini3], cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT),
+                        capture_output=True, text=True)
+    res["cfg3"] = {"cli_wall_s": round(time.time() - t0, 1), "cli_rc": r3.returncode}
+    if r3.returncode == 0:
+        out3 = os.path.join(work, "out3")
+        mt = os.path.join(out3, "cfg3_matches_table.csv")
+        d3 = pd.read_csv(os.path.join(out3, "cfg3_barcode_distribution_table.csv"), sep="\t")
+        s3 = pd.read_csv(os.path.join(out3, "cfg3_summary.csv"), sep="\t")
+        with open(mt, "rb") as fh:
+            rows = sum(chunk.count(b"\n") for chunk in iter(lambda: fh.read(64 << 20), b"")) - 1
+        res["cfg3"].update(matches_rows=rows, matches_bytes=os.path.getsize(mt), summary_rows=len(s3),
+                           label_columns=list(d3.columns[:list(d3.columns).index("coverage")])[:6],
+                           mean_depth_barcode0=float(s3[s3["target"].str.startswith("Barcode_0_")]["mean_bases_on_target"].mean() / 5000),
+                           log_tail=[ln for ln in open(os.path.join(out3, "cfg3_log.log")).read().splitlines() if "seconds" in ln][-3:])
+    else:
+        res["cfg3"]["stderr"] = r3.stderr[-1500:]
     print(json.dumps(res, indent=1))
 
 
