@@ -451,10 +451,12 @@ int build_targets_host(esl_ctx *ctx, cudaStream_t st, PhaseTimer &tm)
             plan.push_back(LayerPlan{b, (int)n_rec, (int)(n_rec + n), (int)n_grid, shift, nb, &layers[b][l]});
             n_rec += n; n_grid += nb;
         }
-        if (layers[b].empty()) n_grid += 2; // two entries that reject every read (placed below)
         ctx->n_layers += (int)layers[b].size();
         ctx->n_first_layers += layers[b].empty() ? 0 : 1;
     }
+    // barcodes without targets: two entries each that reject every read, placed BEHIND all real grids (below) -- so they
+    // are added only now, after every real grid has its offset
+    n_grid += 2 * (size_t)(B - ctx->n_first_layers);
     if (n_rec > 0x7fffffffull || n_grid > 0x7fffffffull) return ctx->fail(ESL_ERR_UNSUPPORTED, "target index too large");
     if ((size_t)B + n_extra >= ((size_t)1 << esl::kQueueSegBits)) return ctx->fail(ESL_ERR_UNSUPPORTED, "too many target layers (barcodes + nesting levels must stay below 2^22)");
     CU(hs.trec.reserve(std::max<size_t>(n_rec, 1) * sizeof(esl::TargetRec<C>)));

@@ -882,3 +882,123 @@ def test_device_index_builder_equals_host_builder(eng, B):
         assert np.array_equal(res.tallies[0, :, 2].numpy(), exp2["otb"])
     finally:
         eng.set_index_builder("auto")
+
+
+def random_geometry(seed):
+    """A seeded random workload that mixes everything the index and the kernels special-case: clustered, nested,
+    duplicate, empty, inverted and out-of-genome targets, unknown barcodes, hot (very long) targets, weighted barcodes,
+    blocked intervals with weights 1 / fractional / 0 for one barcode or all, either coordinate width."""
+    rng = np.random.RandomState(7000 + seed)
+    wide = seed % 8 == 7
+    G = 5_000_000_000 if wide else int(rng.choice([300_000, 2_000_000, 40_000_000]))
+    B = int(rng.choice([1, 2, 5, 40]))
+    weights = {str(int(k)): int(rng.randint(2, 30)) for k in rng.choice(B, size=rng.randint(0, min(B, 4) + 1), replace=False)} or None
+    mean_len = int(rng.choice([300, 2000, 12000]))
+    mean_len = min(mean_len, G // 200)
+    pool = O.lognormal_pool(O.Rng(900 + seed), mean_len, 1, 10, n=50000)
+    pool = pool[pool < G // 8]
+    n_reads = int(rng.choice([30_000, 60_000, 110_000]))
+    cov = n_reads * float(pool.mean()) / G
+    T = int(rng.choice([0, 1, 40, 400, 2500]))
+    ts = np.zeros(T, np.int64); ln = np.zeros(T, np.int64)
+    if T:
+        centres = rng.randint(0, G, 6, dtype=np.int64)
+        clustered = rng.rand(T) < 0.4
+        ts = np.where(clustered, centres[rng.randint(0, 6, T)] + (rng.randn(T) * 20 * mean_len).astype(np.int64),
+                      (rng.rand(T) * G).astype(np.int64))
+        kind = rng.choice(4, T, p=[0.25, 0.55, 0.15, 0.05])
+        ln = np.select([kind == 0, kind == 1, kind == 2], [rng.randint(1, 50, T), rng.randint(mean_len // 4 + 1, 4 * mean_len + 2, T),
+                                                          rng.randint(10 * mean_len, 60 * mean_len, T)], 0).astype(np.int64)
+        n_hot = min(T, int(rng.choice([0, 0, 2, 5])))
+        ln[:n_hot] = rng.randint(G // 400, G // 6, n_hot)  # long enough to be "hot" (>= G/512 - mean read length)
+        for k in range(1, T, 7):  # nest a target inside its predecessor, duplicate another
+            ts[k] = ts[k - 1] + ln[k - 1] // 4; ln[k] = max(1, ln[k - 1] // 3)
+        for k in range(3, T, 11):
+            ts[k] = ts[k - 2]; ln[k] = ln[k - 2]
+        ts = np.clip(ts, 0, None)
+        if T > 10:
+            ln[5] = 0; ln[6] = -500  # empty / inverted
+            ts[7] = G - 10; ts[8] = G + 1000  # sticking out of / beyond the genome
+    te = ts + ln
+    tb = rng.randint(0, B, T).astype(np.int32)
+    if T > 10:
+        tb[9] = -1  # a key whose second token is no barcode number
+    K = int(rng.choice([0, 2, 12, 40]))
+    mask = None
+    if K:
+        ms = (rng.rand(K) * G).astype(np.int64)
+        me = ms + (rng.rand(K) * G / rng.choice([30, 200, 2000])).astype(np.int64) + 1
+        mw = rng.choice([1.0, 0.35, 0.0], K, p=[0.6, 0.3, 0.1])
+        mb = np.where(rng.rand(K) < 0.5, -1, rng.randint(0, B, K)).astype(np.int32)
+        mask = (ms, me, mw, mb)
+    return dict(G=G, B=B, weights=weights, pool=pool, cov=cov, ts=ts, te=te, tb=tb, mask=mask, consuming=bool(rng.rand() < 0.5),
+                min_overlap=int(rng.choice([1, 25, max(1, mean_len // 2)])), sampler=str(rng.choice(["pool", "quantile"])),
+                scaling=float(rng.choice([1.0, 1.0, 0.6])) if T <= 400 else 1.0, seed=int(rng.randint(1, 2**31)),
+                combo=int(rng.randint(0, 5)), it0=int(rng.randint(0, 1000)))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_native_random_geometries_exact(eng, seed):
+    """Seeded random workloads (random_geometry) through the native path, two iterations each: reads placed, N_bases,
+    label counts and every tally bit-exact against the numpy restatement of the draws + the oracle's faithful tally,
+    including pair thinning (scaling < 1) recomputed from the same counter-based uniforms."""
+    w = random_geometry(seed)
+    G, B, ts, te, tb = w["G"], w["B"], w["ts"], w["te"], w["tb"]
+    cdf = O.barcode_cdf(O.barcode_probabilities(B, w["weights"]))
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb)
+    eng.set_blocked(*(w["mask"] or ()))
+    eng.set_length_table(w["pool"])
+    try:
+        eng.set_length_sampler(w["sampler"])
+        res = eng.run_batch(w["seed"], w["combo"], w["it0"], 2, w["cov"], w["consuming"], w["min_overlap"], w["scaling"]).cpu()
+    finally:
+        eng.set_length_sampler("pool")
+    assert not (res.status.numpy() & 2).any()
+    n_draws = int(w["cov"] * G / w["pool"].mean() * 4) + 20000
+    for i in range(2):
+        it = NN.native_iteration(w["seed"], w["combo"], w["it0"] + i, G, w["cov"], w["pool"], cdf, consuming=w["consuming"],
+                                 mask=w["mask"], n_draws=n_draws, sampler=w["sampler"])
+        rs, re_, lab = it["start"], it["start"] + it["length"], it["label"]
+        counts, _ = O.label_hist(lab, B)
+        assert int(res.n_reads[i]) == it["n_placed"] and int(res.n_bases[i]) == it["covered"], seed
+        assert np.array_equal(res.label_counts[i].numpy(), counts), seed
+        t = res.tallies[i].numpy()
+        if w["scaling"] >= 1.0:
+            exp = O.count_matches(None, ts, te, tb, rs, re_, lab, 1.0, w["min_overlap"])
+            exp = np.stack([exp["full"], exp["partial"], exp["otb"]], 1)
+        else:  # the kept pairs from the same per-pair uniforms (Philox block (draw, target row), slot SCALE)
+            exp = np.zeros((ts.size, 3), np.int64)
+            k0, k1 = w["seed"] & 0xFFFFFFFF, (w["seed"] >> 32) & 0xFFFFFFFF
+            for row in range(ts.size):
+                s, e = int(ts[row]), int(te[row])
+                ov = np.minimum(e, re_) - np.maximum(s, rs)
+                n = np.nonzero((lab == tb[row]) & (np.maximum(s, rs) < np.minimum(e, re_)) & (ov >= w["min_overlap"]))[0]
+                if n.size == 0:
+                    continue
+                x, y, _, _ = NN.philox4x32_10(n.astype(np.uint64), np.uint64(row), w["it0"] + i, (w["combo"] << 4) | NN.SLOT_SCALE, k0, k1)
+                n = n[NN.u53(x, y) <= w["scaling"]]
+                full = (rs[n] <= s) & (e <= re_[n])
+                exp[row] = [int(full.sum()), int((~full).sum()), int(ov[n].sum())]
+        assert np.array_equal(t, exp), (seed, np.nonzero((t != exp).any(1))[0][:10])
+
+
+@pytest.mark.parametrize("B,owner", [(40, 20), (16, 15), (5, 3)])
+def test_barcodes_without_targets_before_one_with(eng, B, owner):
+    """Regression: barcodes without targets get two reject-all grid entries behind the real grids; their space must not
+    shift the real grids' offsets (it once did, and the reject-all entries then overwrote the top buckets of the last
+    real grid: a lone target of barcode 20 of 40 was never hit).  Native and replay paths, host index builder."""
+    G = 2_000_000
+    ts, te, tb = np.array([1_582_638, 40_000]), np.array([1_792_432, 47_000]), np.array([owner, owner], np.int32)
+    cdf = O.barcode_cdf(O.barcode_probabilities(B, None))
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
+    pool = O.lognormal_pool(O.Rng(3), 2000, 1, 10, n=50000)
+    eng.set_length_table(pool)
+    res = eng.run_batch(11, 0, 0, 1, 100.0).cpu()
+    it = NN.native_iteration(11, 0, 0, G, 100.0, pool, cdf)
+    exp = O.count_matches(None, ts, te, tb, it["start"], it["start"] + it["length"], it["label"], 1.0, 1)
+    t = res.tallies[0].numpy()
+    assert int(res.n_reads[0]) == it["n_placed"]
+    assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"])
+    assert t[0, 2] > 0 and t[1, 2] > 0
+    rep = eng.replay_reads(it["start"], it["length"], it["label"], [0, it["n_placed"]]).cpu()
+    assert np.array_equal(rep.tallies[0].numpy(), t)
