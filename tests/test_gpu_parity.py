@@ -1002,3 +1002,70 @@ def test_barcodes_without_targets_before_one_with(eng, B, owner):
     assert t[0, 2] > 0 and t[1, 2] > 0
     rep = eng.replay_reads(it["start"], it["length"], it["label"], [0, it["n_placed"]]).cpu()
     assert np.array_equal(rep.tallies[0].numpy(), t)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_replay_random_geometries_exact(eng, seed):
+    """The same random workloads through the REFERENCE stream: the oracle (MT19937 port, pinned by the goldens) runs
+    process_combination on them and records its raw draws; the device does CDF look-up, blocked test with the recorded
+    uniforms, cut-off and tally from those draws (level-2 replay) with the bulk / cut-off split in three places.
+    Everything the reference reports must come out bit-exact."""
+    w = random_geometry(seed)
+    G, B, ts, te, tb = w["G"], w["B"], w["ts"], w["te"], w["tb"]
+    mrl = max(20, int(w["pool"].mean()))
+    rng = O.Rng(3000 + seed)
+    out = O.process_combination(rng, mrl, w["cov"], G, ts, te, tb, B, w["weights"], w["consuming"], w["mask"], 1, 10, 1.0,
+                                w["min_overlap"], n_extra=4000, record_draws=True)
+    pl = out["placement"]
+    n_placed, n_total = pl["n_placed"], pl["start"].size
+    eng.set_genome(G); eng.set_barcode_cdf(O.barcode_cdf(O.barcode_probabilities(B, w["weights"]))); eng.set_targets(ts, te, tb)
+    eng.set_blocked(*(w["mask"] or ()))
+    for bulk in (0, n_placed // 2, n_total):
+        res = eng.replay_draws(pl["u_barcode"], pl["length"], pl["start"], [0, n_total], w["cov"], consuming=w["consuming"],
+                               min_overlap=w["min_overlap"], ublock_off=pl["ublock_off"] if w["mask"] is not None else None,
+                               ublock=pl["ublock"] if w["mask"] is not None else None, bulk_draws=bulk).cpu()
+        assert not int(res.status[0]) & 2
+        assert int(res.n_reads[0]) == n_placed and int(res.n_bases[0]) == pl["covered_length"], (seed, bulk)
+        assert np.array_equal(res.label_counts[0].numpy(), out["label_counts"]), (seed, bulk)
+        t = res.tallies[0].numpy()
+        assert np.array_equal(t[:, 0], out["full"]) and np.array_equal(t[:, 1], out["partial"]) and np.array_equal(t[:, 2], out["otb"]), (seed, bulk)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_device_index_builder_random_flat_sets(eng, seed):
+    """Random non-nesting target sets (one target length per case, so ends ascend with starts) forced through the
+    device index builder and through the host builder: 1-300 barcodes of which a random subset owns all targets (empty
+    barcodes in front of, between and behind the used ones), overlapping and duplicate targets, unknown barcodes,
+    targets at / beyond the genome end, 1-40 k targets.  Both indexes give the CPU restatement's integers."""
+    rng = np.random.RandomState((900 if seed < 5 else 1300) + seed)
+    G = int(rng.choice([3_000_000, 80_000_000, 900_000_000]))
+    B = int(rng.choice([1, 7, 64, 300]))
+    used = rng.choice(B, size=max(1, int(B * rng.choice([0.1, 0.5, 1.0]))), replace=False)
+    n = int(rng.choice([1, 50, 3000, 40_000]))
+    tlen = int(rng.choice([40, 3000, 30_000]))
+    ts = (rng.rand(n) * G).astype(np.int64)
+    if n > 20:
+        ts[3] = ts[2]; ts[10] = G - 5; ts[11] = G; ts[12] = G + 999
+    te = ts + tlen
+    tb = used[rng.randint(0, used.size, n)].astype(np.int32)
+    if n > 20:
+        tb[3] = tb[2]; tb[15] = -1
+    cdf = np.cumsum(rng.rand(B) + 0.05); cdf /= cdf[-1]; cdf[-1] = 1.0
+    mean_len = int(min(rng.choice([500, 8000]), G // 300))
+    pool = O.lognormal_pool(O.Rng(seed), mean_len, 1, 10, n=50000)
+    cov = 80_000 * float(pool.mean()) / G
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb); eng.set_blocked()
+    eng.set_length_table(pool)
+    it = NN.native_iteration(77, 1, seed, G, cov, pool, cdf)
+    exp = O.count_matches_indexed(ts, te, tb, B, it["start"], it["start"] + it["length"], it["label"], 1)
+    hot = tlen >= G / 512 - pool.mean()  # hot targets are the host builder's business
+    try:
+        for mode in ("device", "host"):
+            eng.set_index_builder(mode)
+            res = eng.run_batch(77, 1, seed, 1, cov).cpu()
+            assert eng.index_built_on_device() == (mode == "device" and not hot), (seed, mode)
+            t = res.tallies[0].numpy()
+            assert int(res.n_reads[0]) == it["n_placed"]
+            assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"]), (seed, mode)
+    finally:
+        eng.set_index_builder("auto")
