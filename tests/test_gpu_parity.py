@@ -939,7 +939,7 @@ def random_geometry(seed):
 
 @pytest.mark.parametrize("seed", range(24))
 def test_native_random_geometries_exact(eng, seed):
-    """Seeded random workloads (random_geometry) through the native path, two iterations each: reads placed, N_bases,
+    """Seeded random workloads (random_geometry) through the native path, six iterations each: reads placed, N_bases,
     label counts and every tally bit-exact against the numpy restatement of the draws + the oracle's faithful tally,
     including pair thinning (scaling < 1) recomputed from the same counter-based uniforms."""
     w = random_geometry(seed)
@@ -950,12 +950,27 @@ def test_native_random_geometries_exact(eng, seed):
     eng.set_length_table(w["pool"])
     try:
         eng.set_length_sampler(w["sampler"])
-        res = eng.run_batch(w["seed"], w["combo"], w["it0"], 2, w["cov"], w["consuming"], w["min_overlap"], w["scaling"]).cpu()
+        n_iter = 6  # more iterations than CTA groups: the first and the last against the CPU, the others against solo runs
+        res_dev = eng.run_batch(w["seed"], w["combo"], w["it0"], n_iter, w["cov"], w["consuming"], w["min_overlap"], w["scaling"])
+        res = res_dev.cpu()
+        if ts.size:  # the moment kernel (operand of the multi-GPU reduce) on the same tallies, hot targets' big squares included
+            acc = eng.moments(res_dev.tallies).cpu().numpy()
+            tt = res_dev.tallies.cpu().numpy().astype(object)
+            assert (acc[:, 0] == n_iter).all()
+            for col, k in ((1, 0), (3, 1), (5, 2)):
+                assert np.array_equal(acc[:, col], tt[:, :, k].sum(0)), (seed, col)
+            assert np.array_equal(acc[:, 2], (tt[:, :, 0] ** 2).sum(0)) and np.array_equal(acc[:, 4], (tt[:, :, 1] ** 2).sum(0))
+            assert [int(h) * 2**32 + int(l) for h, l in zip(acc[:, 7], acc[:, 6])] == [int(x) for x in (tt[:, :, 2] ** 2).sum(0)]
+        for i in range(1, n_iter - 1):
+            solo = eng.run_batch(w["seed"], w["combo"], w["it0"] + i, 1, w["cov"], w["consuming"], w["min_overlap"], w["scaling"]).cpu()
+            assert np.array_equal(solo.tallies[0].numpy(), res.tallies[i].numpy()), (seed, i)
+            assert np.array_equal(solo.label_counts[0].numpy(), res.label_counts[i].numpy()), (seed, i)
+            assert int(solo.n_reads[0]) == int(res.n_reads[i]) and int(solo.n_bases[0]) == int(res.n_bases[i]), (seed, i)
     finally:
         eng.set_length_sampler("pool")
     assert not (res.status.numpy() & 2).any()
     n_draws = int(w["cov"] * G / w["pool"].mean() * 4) + 20000
-    for i in range(2):
+    for i in (0, n_iter - 1):
         it = NN.native_iteration(w["seed"], w["combo"], w["it0"] + i, G, w["cov"], w["pool"], cdf, consuming=w["consuming"],
                                  mask=w["mask"], n_draws=n_draws, sampler=w["sampler"])
         rs, re_, lab = it["start"], it["start"] + it["length"], it["label"]
@@ -972,7 +987,8 @@ def test_native_random_geometries_exact(eng, seed):
             for row in range(ts.size):
                 s, e = int(ts[row]), int(te[row])
                 ov = np.minimum(e, re_) - np.maximum(s, rs)
-                n = np.nonzero((lab == tb[row]) & (np.maximum(s, rs) < np.minimum(e, re_)) & (ov >= w["min_overlap"]))[0]
+                # (tb = -1 is a key without a barcode number: it matches no read, least of all the blocked ones labelled -1)
+                n = np.nonzero((tb[row] >= 0) & (lab == tb[row]) & (np.maximum(s, rs) < np.minimum(e, re_)) & (ov >= w["min_overlap"]))[0]
                 if n.size == 0:
                     continue
                 x, y, _, _ = NN.philox4x32_10(n.astype(np.uint64), np.uint64(row), w["it0"] + i, (w["combo"] << 4) | NN.SLOT_SCALE, k0, k1)
