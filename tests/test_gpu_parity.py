@@ -931,6 +931,11 @@ def random_geometry(seed):
         mw = rng.choice([1.0, 0.35, 0.0], K, p=[0.6, 0.3, 0.1])
         mb = np.where(rng.rand(K) < 0.5, -1, rng.randint(0, B, K)).astype(np.int32)
         mask = (ms, me, mw, mb)
+    if T >= 400:  # twenty 60-base targets of one barcode 3 bases apart: a crowded grid bucket (the bisect inside a bucket)
+        ts[20:40] = G // 3 + 3 * np.arange(20); te[20:40] = ts[20:40] + 60; tb[20:40] = tb[20]
+    if K >= 12:   # twelve blocked intervals of mixed weights inside 100 bases: crowded bucket + several uniforms per read
+        ms[:12] = G // 2 + 8 * np.arange(12); me[:12] = ms[:12] + 5; mb[:12] = -1
+        mw[:12] = np.tile([0.35, 0.0, 0.35, 1.0], 3)
     return dict(G=G, B=B, weights=weights, pool=pool, cov=cov, ts=ts, te=te, tb=tb, mask=mask, consuming=bool(rng.rand() < 0.5),
                 min_overlap=int(rng.choice([1, 25, max(1, mean_len // 2)])), sampler=str(rng.choice(["pool", "quantile"])),
                 scaling=float(rng.choice([1.0, 1.0, 0.6])) if T <= 400 else 1.0, seed=int(rng.randint(1, 2**31)),
