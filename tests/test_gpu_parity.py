@@ -917,7 +917,7 @@ def random_geometry(seed):
             ts[k] = ts[k - 2]; ln[k] = ln[k - 2]
         ts = np.clip(ts, 0, None)
         if T > 10:
-            ln[5] = 0; ln[6] = -500  # empty / inverted
+            ln[5] = 0; ln[6] = -min(500, int(ts[6]))  # empty / inverted (coordinates stay >= 0: the engine rejects negative ones)
             ts[7] = G - 10; ts[8] = G + 1000  # sticking out of / beyond the genome
     te = ts + ln
     tb = rng.randint(0, B, T).astype(np.int32)
@@ -942,7 +942,14 @@ def random_geometry(seed):
                 combo=int(rng.randint(0, 5)), it0=int(rng.randint(0, 1000)))
 
 
-@pytest.mark.parametrize("seed", range(24))
+def fuzz_seeds(default):
+    """Seeds of the random-workload tests; ESL_FUZZ_SEEDS=lo:hi widens the sweep (e.g. 24:300 for a one-off hunt)."""
+    import os
+    lo, hi = (int(x) for x in os.environ.get("ESL_FUZZ_SEEDS", f"0:{default}").split(":"))
+    return range(lo, hi)
+
+
+@pytest.mark.parametrize("seed", fuzz_seeds(24))
 def test_native_random_geometries_exact(eng, seed):
     """Seeded random workloads (random_geometry) through the native path, six iterations each: reads placed, N_bases,
     label counts and every tally bit-exact against the numpy restatement of the draws + the oracle's faithful tally,
@@ -1025,7 +1032,7 @@ def test_barcodes_without_targets_before_one_with(eng, B, owner):
     assert np.array_equal(rep.tallies[0].numpy(), t)
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", fuzz_seeds(16))
 def test_replay_random_geometries_exact(eng, seed):
     """The same random workloads through the REFERENCE stream: the oracle (MT19937 port, pinned by the goldens) runs
     process_combination on them and records its raw draws; the device does CDF look-up, blocked test with the recorded
@@ -1035,8 +1042,11 @@ def test_replay_random_geometries_exact(eng, seed):
     G, B, ts, te, tb = w["G"], w["B"], w["ts"], w["te"], w["tb"]
     mrl = max(20, int(w["pool"].mean()))
     rng = O.Rng(3000 + seed)
-    out = O.process_combination(rng, mrl, w["cov"], G, ts, te, tb, B, w["weights"], w["consuming"], w["mask"], 1, 10, 1.0,
-                                w["min_overlap"], n_extra=4000, record_draws=True)
+    try:
+        out = O.process_combination(rng, mrl, w["cov"], G, ts, te, tb, B, w["weights"], w["consuming"], w["mask"], 1, 10, 1.0,
+                                    w["min_overlap"], n_extra=4000, record_draws=True)
+    except ValueError:  # (seen once in a 1000-seed sweep, at G = 300 kb)
+        pytest.skip("the 1 M-entry log-normal pool holds a length >= the genome size: the reference raises here too")
     pl = out["placement"]
     n_placed, n_total = pl["n_placed"], pl["start"].size
     eng.set_genome(G); eng.set_barcode_cdf(O.barcode_cdf(O.barcode_probabilities(B, w["weights"]))); eng.set_targets(ts, te, tb)
