@@ -51,6 +51,7 @@ SYMBOLS = {
     "esl_replay_thin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
     "esl_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "esl_scan_read_lengths": (C.c_int64, [C.c_char_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]),
+    "esl_scan_fasta_contigs": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "esl_shift_insertions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "esl_write_match_rows": (C.c_int64, [C.c_char_p, C.c_int32, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_char_p]),
     "esl_write_match_rows_batch": (C.c_int64, [C.c_char_p, C.c_int32, C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

@@ -4,10 +4,42 @@ joins all sequences into one string, fasta_operations.py:17-22)."""
 import gzip
 
 
-def fasta_contig_lengths(path_to_fasta, chunk_bytes=1 << 24):
+def _contigs_native(path_to_fasta):
+    """[(id, length)] through the native one-pass scanner (esl_scan_fasta_contigs); None when the library is not built."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _native
+    try:
+        lib = _native.load()
+    except _native.NativeLibraryError:  # library not built yet: the Python scan below does the same job, slower
+        return None
+    names_cap, max_records = 1 << 16, 1 << 12
+    while True:
+        names = C.create_string_buffer(names_cap)
+        lengths = np.zeros(max_records, np.int64)
+        need = C.c_int64()
+        n = lib.esl_scan_fasta_contigs(str(path_to_fasta).encode(), names, names_cap, lengths.ctypes.data, max_records, C.byref(need))
+        if n < 0:
+            raise OSError(f"cannot read {path_to_fasta}")
+        if n <= max_records and need.value <= names_cap:
+            ids = names.raw[:need.value].split(b"\0")[:n] if n else []
+            return [(i.decode(), int(l)) for i, l in zip(ids, lengths[:n])]
+        names_cap, max_records = max(names_cap, need.value + 64), max(max_records, n)  # assemblies with > 4096 scaffolds: once more, with room
+
+
+def fasta_contig_lengths(path_to_fasta, chunk_bytes=None):
     """Yield (record id, sequence length) in file order; id = first whitespace-delimited token of the header.
-    Byte-level scan in 16 MB chunks (find the next ">" / newline, count everything else that is not a line break),
-    so an hg38-sized FASTA is measured at disk speed instead of through tens of millions of Python line objects."""
+    Default: the native one-pass scanner (csrc/seqscan.cpp; an hg38-sized FASTA at the speed of the read).  With
+    chunk_bytes given, or without the built library: a byte-level scan in Python in chunks of that size (find the next
+    ">" / newline, count everything else that is not a line break)."""
+    if chunk_bytes is None:
+        native = _contigs_native(path_to_fasta)
+        if native is not None:
+            yield from native
+            return
+        chunk_bytes = 1 << 24
     open_func = gzip.open if str(path_to_fasta).endswith(".gz") else open
     with open_func(path_to_fasta, "rb") as fh:
         name, n, header = None, 0, None  # header: bytes of a header line that is still open (None = in sequence)

@@ -231,6 +231,15 @@ int esl_set_hit_buffer(esl_ctx *ctx, int64_t *d_hits, int64_t capacity, int64_t 
 int64_t esl_scan_read_lengths(const char *path, int32_t is_fastq, int64_t min_read_length, uint32_t *out,
                               int64_t capacity, double *mean_out);
 
+/* Host helper (no GPU): contig ids and lengths of a FASTA, plain or gzip, in one streaming pass -- all that
+ * pseudo_fasta_coordinates (fasta_operations.py:3-22) keeps of the sequences it loads.  A record starts at a line
+ * beginning with '>'; its id (first whitespace-delimited token) is written NUL-terminated behind the previous one into
+ * names[0..names_cap), its length (characters of the following lines without line breaks, blanks, tabs) to
+ * lengths[i], i < max_records.  Returns the number of records and *names_bytes = the bytes all ids need (either may
+ * exceed the capacities: call again with room), or a negative esl_status (ESL_ERR_INVALID: cannot open). */
+int64_t esl_scan_fasta_contigs(const char *path, char *names, int64_t names_cap, int64_t *lengths, int64_t max_records,
+                               int64_t *names_bytes);
+
 /* Host helper (no GPU): final start coordinates of n insertions placed one after the other, each pushing the earlier
  * insertions at or after its position right by insertion_length (create_insertion_genome.py:60-64,76-80). */
 int esl_shift_insertions(const int64_t *positions, int64_t n, int64_t insertion_length, int64_t *starts);

@@ -241,3 +241,34 @@ def test_targets_to_arrays_shapes_and_barcode_rule():
     keys, s, e, b = targets_to_arrays(np_vals, 2)
     assert s.tolist() == [4, 1] and e.tolist() == [9, 2]
     assert targets_to_arrays({}, 4)[1].size == 0
+
+
+def test_native_contig_scanner_matches_python_scan(tmp_path):
+    """esl_scan_fasta_contigs (C++, one pass, SSE2 block counting, gzip transparent) == the chunked Python scan: ids and
+    lengths for CRLF / blank lines / blanks inside sequence lines / '>' inside a description / a header at the end of
+    the file / text before the first header / an empty file / more records and id bytes than the first call's buffers
+    hold (the retry path), plain and gzip."""
+    import gzip
+    from esloco_b200 import fasta_operations as fo
+    rng = np.random.RandomState(3)
+    texts = {
+        "tricky": ">chr1 desc >weird\nACGT\nAC\r\n\n>chr2\n" + "G" * 205 + "\n" + "T" * 17 + "\n>empty\n>chr3 last",
+        "junk": "text before\n>  \n A C\tG \n>x\n",
+        "empty": "",
+        "noheader": "ACGT\nACGT\n",
+        "many": "".join(f">scaffold_{i}_{'n' * (i % 40)} d\n" + "\n".join("A" * w for w in rng.randint(1, 90, rng.randint(0, 5))) + "\n" for i in range(6000)),
+        "long": ">a\n" + ("ACGT" * 20 + "\n") * 200_000 + ">b x\n" + "N" * 3_000_001,
+    }
+    for name, text in texts.items():
+        p = tmp_path / f"{name}.fa"
+        p.write_bytes(text.encode())
+        want = list(fo.fasta_contig_lengths(str(p), 1 << 16))
+        assert fo._contigs_native(str(p)) == want, name
+        assert list(fo.fasta_contig_lengths(str(p))) == want, name
+        gz = tmp_path / f"{name}.fa.gz"
+        with gzip.open(gz, "wb") as fh:
+            fh.write(text.encode())
+        assert fo._contigs_native(str(gz)) == want, name
+    assert dict(fo.fasta_contig_lengths(str(tmp_path / "long.fa"))) == {"a": 16_000_000, "b": 3_000_001}
+    with pytest.raises(OSError):
+        fo._contigs_native(str(tmp_path / "missing.fa"))
