@@ -88,8 +88,14 @@ insertion_length = 5000
 insertion_numbers = 10000
 """)
     t0 = time.time()
-    r3 = subprocess.run([sys.executable, "-m", "esloco_b200", "--config", ini3], cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT),
-                        capture_output=True, text=True)
+    prof = os.path.join(work, "cfg3.prof")
+    cmd = [sys.executable] + (["-m", "cProfile", "-o", prof] if "--profile" in sys.argv else []) + ["-m", "esloco_b200", "--config", ini3]
+    r3 = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True)
+    if "--profile" in sys.argv and os.path.exists(prof):
+        import io, pstats
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
+        open(os.path.join(ROOT, "gpurun_out", "cli_cfg3_cprofile.txt"), "w").write(buf.getvalue())
     res["cfg3"] = {"cli_wall_s": round(time.time() - t0, 1), "cli_rc": r3.returncode}
     if r3.returncode == 0:
         out3 = os.path.join(work, "out3")
