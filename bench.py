@@ -218,7 +218,7 @@ def run_reference_arm(args, w):
             "reference_impl": "CPU port of the reference algorithm (oracle/esloco_oracle.c), numpy-legacy MT19937 stream, pinned by the reference's golden outputs",
             "cpu_baseline": {"value": val, "unit": "reads/s", "cores": n_thr, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -483,12 +483,33 @@ def run_ours(args, w):
                         "timed_region_s": main["timed_region_s"]},
                 "roofline": main["roofline"], "collective_ms": main["collective_ms"], "cpu_baseline": cpu, "e2e": main["e2e"],
                 "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "north_star_cfg3": ns}
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version on fd 1 when the
+    first communicator is made), so the real stdout is kept aside for the JSON line and fd 1 is pointed at stderr for
+    everything else, native code included."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
