@@ -1100,3 +1100,72 @@ def test_device_index_builder_random_flat_sets(eng, seed):
             assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"]), (seed, mode)
     finally:
         eng.set_index_builder("auto")
+
+
+def extreme_geometry(seed):
+    """Seeded workloads at the edges of the parameter space: genomes of 2 kb and right below / above the 32-bit
+    coordinate limit, a length pool with one entry or with reads nearly as long as the genome, a handful of reads per
+    iteration (cut-off kernel only), up to 1300 barcodes with weight ratios of 10^4, no targets / tens of thousands of
+    them (device index builder) in one barcode or spread, a blocked interval over the whole genome for one barcode."""
+    rng = np.random.RandomState(91000 + seed)
+    G = int(rng.choice([2_000, 50_000, 3_000_000, 4_294_967_000, 4_294_967_400, 9_000_000_000]))
+    B = int(rng.choice([1, 3, 257, 1300]))
+    heavy = rng.choice(B, size=min(B, int(rng.choice([0, 1, 3]))), replace=False)
+    weights = {str(int(k)): int(rng.choice([2, 100, 10_000])) for k in heavy} or None
+    kind = int(rng.choice(4))
+    if kind == 0:
+        pool = np.array([int(rng.choice([1, 7, max(2, G // 1000)]))], np.int64)          # one length
+    elif kind == 1:
+        pool = np.array([1, max(2, G // 3), max(3, G - 1)], np.int64)                    # 1 base ... the whole genome but one base
+        pool = np.minimum(pool, 0xFFFFFFFF)                                              # (lengths are 32-bit)
+    else:
+        pool = O.lognormal_pool(O.Rng(seed), max(30, G // int(rng.choice([100, 5000, 200_000]))), 1, 1, n=20000)
+        pool = pool[pool < min(G, 1 << 32)]  # (the reference raises for a read as long as the genome; lengths are 32-bit)
+    n_reads = int(rng.choice([4, 300, 40_000]))
+    cov = max(n_reads * float(pool.mean()) / G, 1e-9)
+    T = int(rng.choice([0, 3, 500, 20_000, 70_000]))
+    tlen = int(rng.choice([1, max(1, int(pool.mean())), max(2, G // 50)]))
+    ts = (rng.rand(T) * G).astype(np.int64)
+    te = ts + tlen                                                                       # one length: no nesting, ends may pass G
+    tb = (np.full(T, rng.randint(0, B)) if rng.rand() < 0.3 else rng.randint(0, B, T)).astype(np.int32)
+    mask = None
+    mk = int(rng.choice(3))
+    if mk == 1 and B > 1:   # every read of one barcode is blocked
+        mask = (np.array([0], np.int64), np.array([G], np.int64), np.array([1.0]), np.array([int(tb[0]) if T else 0], np.int32))
+    elif mk == 2:           # a third of the genome blocked for everybody with probability 1/2, plus one base
+        mask = (np.array([G // 3, G - 1], np.int64), np.array([2 * (G // 3), G], np.int64), np.array([0.5, 1.0]), np.array([-1, -1], np.int32))
+    consuming = bool(rng.rand() < 0.5)
+    if mk == 1 and B > 1 and weights and str(int(mask[3][0])) in weights:
+        consuming = True  # (nearly every read blocked AND not counted would need 10^4 times the draws)
+    return dict(G=G, B=B, weights=weights, pool=pool, cov=cov, ts=ts, te=te, tb=tb, mask=mask, consuming=consuming,
+                min_overlap=int(rng.choice([1, 2, max(1, tlen)])), sampler=str(rng.choice(["pool", "quantile"])),
+                seed=int(rng.randint(1, 2**31)) | (int(rng.randint(0, 2**31)) << 32), combo=int(rng.randint(0, 16)),
+                it0=int(rng.choice([0, 999_999, 2**31 - 10])))
+
+
+@pytest.mark.parametrize("seed", fuzz_seeds(16))
+def test_native_extreme_geometries_exact(eng, seed):
+    """extreme_geometry through the native path, three iterations per batch: everything the engine returns bit-exact
+    against the numpy restatement + the oracle's indexed tally."""
+    w = extreme_geometry(seed)
+    G, B, ts, te, tb = w["G"], w["B"], w["ts"], w["te"], w["tb"]
+    cdf = O.barcode_cdf(O.barcode_probabilities(B, w["weights"]))
+    eng.set_genome(G); eng.set_barcode_cdf(cdf); eng.set_targets(ts, te, tb)
+    eng.set_blocked(*(w["mask"] or ()))
+    eng.set_length_table(w["pool"])
+    try:
+        eng.set_length_sampler(w["sampler"])
+        res = eng.run_batch(w["seed"], w["combo"], w["it0"], 3, w["cov"], w["consuming"], w["min_overlap"], 1.0).cpu()
+    finally:
+        eng.set_length_sampler("pool")
+    assert not (res.status.numpy() & 2).any()
+    n_draws = int(w["cov"] * G / w["pool"].mean() * 6) + 20000
+    for i in (0, 2):
+        it = NN.native_iteration(w["seed"], w["combo"], w["it0"] + i, G, w["cov"], w["pool"], cdf, consuming=w["consuming"],
+                                 mask=w["mask"], n_draws=n_draws, sampler=w["sampler"])
+        counts, _ = O.label_hist(it["label"], B)
+        assert int(res.n_reads[i]) == it["n_placed"] and int(res.n_bases[i]) == it["covered"], seed
+        assert np.array_equal(res.label_counts[i].numpy(), counts), seed
+        exp = O.count_matches_indexed(ts, te, tb, B, it["start"], it["start"] + it["length"], it["label"], w["min_overlap"])
+        t = res.tallies[i].numpy()
+        assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"]), seed
