@@ -88,17 +88,20 @@ def _mean_sd(n, s, s2):
 def summary_from_moments(mom):
     """[T, 8] moments (possibly summed over ranks / rows of one group) -> dict of float arrays with the columns of
     summary.csv (esloco.py:183-195): mean / sd of full and partial matches, mean / sd / sem / 95 % CI of bases."""
-    mom = np.asarray(mom)
-    T = mom.shape[0]
-    cols = {k: np.empty(T) for k in ("mean_full_matches", "sd_full_matches", "mean_partial_matches", "sd_partial_matches",
-                                     "mean_bases_on_target", "sd_bases_on_target", "sem_bases_on_target")}
-    for i in range(T):
-        n, sf, sf2, sp, sp2, sb, lo, hi = (int(x) for x in mom[i])
-        cols["mean_full_matches"][i], cols["sd_full_matches"][i] = _mean_sd(n, sf, sf2)
-        cols["mean_partial_matches"][i], cols["sd_partial_matches"][i] = _mean_sd(n, sp, sp2)
-        m, sd = _mean_sd(n, sb, (hi << 32) + lo)
-        cols["mean_bases_on_target"][i], cols["sd_bases_on_target"][i] = m, sd
-        cols["sem_bases_on_target"][i] = sd / n ** 0.5
+    m = np.asarray(mom).astype(object)  # Python integers: exact products and differences, element by element inside numpy
+    n = m[:, 0]
+    nan = float("nan")
+
+    def mean_sd(s, s2):  # _mean_sd over the rows
+        num, den = n * s2 - s * s, n * (n - 1)
+        sd = np.array([nan if k < 2 else ((a / b) ** 0.5 if a > 0 else 0.0) for k, a, b in zip(n, num, den)], dtype=float)
+        return (s / n).astype(float), sd
+
+    cols = {}
+    cols["mean_full_matches"], cols["sd_full_matches"] = mean_sd(m[:, 1], m[:, 2])
+    cols["mean_partial_matches"], cols["sd_partial_matches"] = mean_sd(m[:, 3], m[:, 4])
+    cols["mean_bases_on_target"], cols["sd_bases_on_target"] = mean_sd(m[:, 5], m[:, 7] * (1 << 32) + m[:, 6])
+    cols["sem_bases_on_target"] = np.array([sd / k ** 0.5 for sd, k in zip(cols["sd_bases_on_target"].tolist(), n)], dtype=float)
     cols["ci_lower_bases_on_target"] = cols["mean_bases_on_target"] - 1.96 * cols["sem_bases_on_target"]
     cols["ci_upper_bases_on_target"] = cols["mean_bases_on_target"] + 1.96 * cols["sem_bases_on_target"]
     return cols

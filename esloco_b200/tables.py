@@ -12,22 +12,27 @@ from .counting import LABELS_BLOCKED
 from .distributed import summary_from_moments
 
 
+_SPLIT_CACHE = [None]  # (keys object, mode, columns) of the last call: the CLI splits the same 240 k keys twice
+
+
 def split_target_keys(keys, mode):
     """target / barcode / insertion columns from the target keys, exactly the rsplit logic of esloco.py:165-177
     applied to "<key>_<iteration>"."""
-    cols = {"target": [], "barcode": []}
-    if mode != "ROI":
-        cols["insertion"] = []
-    for k in keys:
-        if mode == "ROI":  # {ROI}_{barcode}[_{iteration}]
-            parts = k.rsplit("_", 1)
-            cols["target"].append(parts[0]); cols["barcode"].append(parts[1] if len(parts) > 1 else None)
-        else:  # Barcode_{b}_insertion_{i}[_{iteration}]: rsplit n=4 on key+iteration == rsplit n=3 on key
-            parts = k.rsplit("_", 3)
-            parts = [None] * (4 - len(parts)) + parts
-            cols["target"].append("_".join(str(p) for p in parts))
-            cols["barcode"].append(parts[1])
-            cols["insertion"].append(f"{parts[2]}_{parts[3]}")
+    hit = _SPLIT_CACHE[0]
+    if hit is not None and hit[0] is keys and hit[1] == mode and len(hit[2]["target"]) == len(keys):
+        return hit[2]
+    if mode == "ROI":  # {ROI}_{barcode}[_{iteration}]
+        parts = [k.rsplit("_", 1) for k in keys]
+        cols = {"target": [p[0] for p in parts], "barcode": [p[1] if len(p) > 1 else None for p in parts]}
+    else:  # Barcode_{b}_insertion_{i}[_{iteration}]: rsplit n=4 on key+iteration == rsplit n=3 on key
+        parts = [k.rsplit("_", 3) for k in keys]
+        if all(len(p) == 4 for p in parts):  # the generator's keys: joining the four parts gives the key back
+            cols = {"target": list(keys), "barcode": [p[1] for p in parts], "insertion": [p[2] + "_" + p[3] for p in parts]}
+        else:
+            parts = [[None] * (4 - len(p)) + p for p in parts]
+            cols = {"target": ["_".join(str(x) for x in p) for p in parts], "barcode": [p[1] for p in parts],
+                    "insertion": [f"{p[2]}_{p[3]}" for p in parts]}
+    _SPLIT_CACHE[0] = (keys, mode, cols)
     return cols
 
 
@@ -201,18 +206,21 @@ def summary_table(keys, mode, combos, moments_per_combo):
     target's rows of all barcodes fall into one group, so their accumulators are added."""
     names = split_target_keys(keys, mode)["target"]
     frames = []
+    index = {}
+    for nm in names:
+        if nm not in index:
+            index[nm] = len(index)
+    order = list(index)
     for (mrl, cov), mom in zip(combos, moments_per_combo):
         mom = np.asarray(mom).astype(object)
-        order, index = [], {}
-        for i, nm in enumerate(names):
-            if nm not in index:
-                index[nm] = len(order); order.append(nm)
-        grouped = np.zeros((len(order), 8), dtype=object)
-        for i, nm in enumerate(names):
-            grouped[index[nm]] += mom[i]
-        lo_hi = grouped[:, 7] * (1 << 32) + grouped[:, 6]  # re-normalise the split square sum after adding rows
-        grouped[:, 6] = [int(x) & 0xFFFFFFFF for x in lo_hi]
-        grouped[:, 7] = [int(x) >> 32 for x in lo_hi]
+        if len(order) == len(names):  # every target its own group (I mode): nothing to add up
+            grouped = mom
+        else:
+            grouped = np.zeros((len(order), 8), dtype=object)
+            np.add.at(grouped, np.fromiter((index[nm] for nm in names), np.int64, len(names)), mom)
+            lo_hi = grouped[:, 7] * (1 << 32) + grouped[:, 6]  # re-normalise the split square sum after adding rows
+            grouped[:, 6] = [int(x) & 0xFFFFFFFF for x in lo_hi]
+            grouped[:, 7] = [int(x) >> 32 for x in lo_hi]
         cols = summary_from_moments(grouped)
         df = pd.DataFrame({"target": order, "mean_read_length": mrl, "coverage": cov})
         for k in ("mean_full_matches", "sd_full_matches", "mean_partial_matches", "sd_partial_matches",
