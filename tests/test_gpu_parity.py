@@ -990,8 +990,10 @@ def test_native_random_geometries_exact(eng, seed):
         assert int(res.n_reads[i]) == it["n_placed"] and int(res.n_bases[i]) == it["covered"], seed
         assert np.array_equal(res.label_counts[i].numpy(), counts), seed
         t = res.tallies[i].numpy()
+        pairs = []  # expected hit records of this iteration: (target row, overlap), target-major, reads in draw order
         if w["scaling"] >= 1.0:
-            exp = O.count_matches(None, ts, te, tb, rs, re_, lab, 1.0, w["min_overlap"])
+            exp = O.count_matches(None, ts, te, tb, rs, re_, lab, 1.0, w["min_overlap"], want_overlaps=True)
+            pairs = np.stack([np.repeat(np.arange(ts.size), np.diff(exp["overlap_off"])), exp["overlap_flat"]], 1)
             exp = np.stack([exp["full"], exp["partial"], exp["otb"]], 1)
         else:  # the kept pairs from the same per-pair uniforms (Philox block (draw, target row), slot SCALE)
             exp = np.zeros((ts.size, 3), np.int64)
@@ -1007,7 +1009,29 @@ def test_native_random_geometries_exact(eng, seed):
                 n = n[NN.u53(x, y) <= w["scaling"]]
                 full = (rs[n] <= s) & (e <= re_[n])
                 exp[row] = [int(full.sum()), int((~full).sum()), int(ov[n].sum())]
+                pairs.append(np.stack([np.full(n.size, row), ov[n]], 1))
+            pairs = np.concatenate(pairs) if pairs else np.zeros((0, 2), np.int64)
         assert np.array_equal(t, exp), (seed, np.nonzero((t != exp).any(1))[0][:10])
+        if i and len(pairs) <= 400_000:
+            # the per-target `overlap` lists (counting.py:56) from device hit records of a solo run of this iteration; the
+            # buffer is a little short of the bulk kernel's overshoot on purpose when there are many pairs: overflow must be
+            # reported, not written past the end
+            try:
+                eng.set_length_sampler(w["sampler"])
+                eng.set_hit_buffer(len(pairs) + 64)
+                solo = eng.run_batch(w["seed"], w["combo"], w["it0"] + i, 1, w["cov"], w["consuming"], w["min_overlap"], w["scaling"])
+                try:
+                    hits = eng.take_hits(solo.n_reads)
+                except Exception as e:  # pairs of draws beyond the cut-off did not fit: once more with room for them
+                    assert getattr(e, "code", None) == -5, e
+                    eng.set_hit_buffer(4 * len(pairs) + 100_000)
+                    solo = eng.run_batch(w["seed"], w["combo"], w["it0"] + i, 1, w["cov"], w["consuming"], w["min_overlap"], w["scaling"])
+                    hits = eng.take_hits(solo.n_reads)
+            finally:
+                eng.set_hit_buffer(0)
+                eng.set_length_sampler("pool")
+            assert np.array_equal(solo.tallies[0].cpu().numpy(), t), seed  # recording hits does not change the tallies
+            assert np.array_equal(hits[:, 1], pairs[:, 0]) and np.array_equal(hits[:, 3], pairs[:, 1]), seed
 
 
 @pytest.mark.parametrize("B,owner", [(40, 20), (16, 15), (5, 3)])
