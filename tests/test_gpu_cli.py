@@ -277,3 +277,75 @@ def test_cli_reference_label_columns(tmp_path):
     row0 = d.iloc[0]
     assert [int(row0[k]) for k in labels] == [hist[k] for k in labels] and int(row0["N_bases"]) == covered
     assert (d["total_Reads"] == d[labels[0]] + d[labels[1]]).all()  # the reference's rule: the first n_barcodes COLUMNS
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_session_cache_random_sequences(seed):
+    """The session uploads only what changed since the last call (content-keyed, session.py).  A random sequence of calls
+    in which any subset of the inputs changes between one call and the next -- genome size, target dict (also edited in
+    place), blocked regions, barcode count / weights, length pool, sampler, nothing at all -- must give, call by call,
+    exactly what a session that forgot everything gives."""
+    import numpy as np
+    from esloco_b200.combined_calculations import run_simulation_batch
+    from esloco_b200.session import get_session
+    from esloco_b200.utils import build_mask_tree
+    rng = np.random.RandomState(40 + seed)
+    sess = get_session(0)
+    sess.invalidate()
+
+    def new_targets(G, B, mode):
+        n = int(rng.choice([1, 8, 60]))
+        s = np.sort(rng.randint(0, G - 20_000, n))
+        if mode == "I":
+            return {f"Barcode_{int(rng.randint(0, B))}_insertion_{i}": [int(a), int(a) + 5000] for i, a in enumerate(s)}
+        return {f"R{i}_{int(rng.randint(0, B))}": {"start": int(a), "end": int(a) + int(rng.randint(500, 20_000))} for i, a in enumerate(s)}
+
+    def new_mask(G, B):
+        if rng.rand() < 0.3:
+            return None
+        return {f"m{i}": {"start": int(a), "end": int(a) + int(rng.randint(1000, G // 10)), "weight": float(rng.choice([1, 0.5])),
+                          "barcode": [] if rng.rand() < 0.5 else [str(int(rng.randint(0, B)))]}
+                for i, a in enumerate(rng.randint(0, G - G // 10, int(rng.choice([1, 5]))))}
+
+    G, B, weights, sampler = 5_000_000, 3, None, "quantile"
+    targets, mask = new_targets(G, B, "I"), new_mask(G, B)
+    pool = np.random.RandomState(1).randint(200, 6000, 50_000)
+    for step in range(14):
+        for what in rng.choice(["genome", "targets", "edit", "mask", "barcodes", "weights", "pool", "sampler", "none"],
+                               size=int(rng.choice([1, 1, 2, 3])), replace=False):
+            if what == "genome":
+                G = int(rng.choice([3_000_000, 5_000_000, 40_000_000]))
+                targets, mask = new_targets(G, B, "I"), new_mask(G, B)
+            elif what == "targets":
+                targets = new_targets(G, B, str(rng.choice(["I", "ROI"])))
+            elif what == "edit":  # the caller's own dict, changed in place
+                k = next(iter(targets))
+                v = targets[k]
+                if isinstance(v, list):
+                    v[0] += 777; v[1] += 777
+                else:
+                    v["end"] += 333
+            elif what == "mask":
+                mask = new_mask(G, B)
+            elif what == "barcodes":
+                B = int(rng.choice([1, 3, 6]))
+                targets, mask = new_targets(G, B, "I"), new_mask(G, B)
+            elif what == "weights":
+                weights = None if rng.rand() < 0.4 else {str(int(rng.randint(0, B))): int(rng.randint(2, 9))}
+            elif what == "pool":
+                pool = np.random.RandomState(int(rng.randint(1 << 30))).randint(100, int(rng.choice([3000, 30_000])), 50_000)
+            elif what == "sampler":
+                sampler = "pool" if sampler == "quantile" else "quantile"
+        params = dict(n_barcodes=B, barcode_weights=weights, seed=11, scaling=1.0, combinations=[(3000, 4.0)], sequenced_data_path=None,
+                      sigma=1, min_read_length=1, consuming=bool(step & 1), min_overlap_for_detection=1, length_sampler=sampler)
+        tree = build_mask_tree(mask) if mask else None
+        got = []
+        for fresh in (False, True):
+            if fresh:
+                sess.invalidate()
+            res, keys = run_simulation_batch(range(step, step + 2), params, G, targets, tree, length_pools={0: pool})
+            got.append((res[0].tallies.numpy().copy(), res[0].label_counts.numpy().copy(), res[0].n_bases.numpy().copy(), list(keys)))
+        for a, b in zip(got[0][:3], got[1][:3]):
+            assert np.array_equal(a, b), (seed, step)
+        assert got[0][3] == got[1][3] == list(targets)
+        assert got[0][2].min() >= 4.0 * G
