@@ -1193,3 +1193,79 @@ def test_native_extreme_geometries_exact(eng, seed):
         exp = O.count_matches_indexed(ts, te, tb, B, it["start"], it["start"] + it["length"], it["label"], w["min_overlap"])
         t = res.tallies[i].numpy()
         assert np.array_equal(t[:, 0], exp["full"]) and np.array_equal(t[:, 1], exp["partial"]) and np.array_equal(t[:, 2], exp["otb"]), seed
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_engine_state_sequences_equal_fresh_context(eng, seed):
+    """One context driven through a random sequence of set-up calls (genome size across the 32 / 64-bit coordinate
+    switch, targets between 0 and 30 k across the device-builder threshold and the shared pre-filter limit, blocked
+    intervals, barcode tables, length tables with longer and shorter reads, sampler, index builder) gives, after every
+    change, exactly what a context created for those inputs gives: no set-up call leaves anything stale behind."""
+    from esloco_b200.engine import Engine
+    rng = np.random.RandomState(600 + seed)
+    st = dict(G=30_000_000, cdf=np.array([1.0]), ts=np.zeros(0, np.int64), te=np.zeros(0, np.int64), tb=np.zeros(0, np.int32),
+              mask=(), pool=np.array([2000, 3000]), sampler="pool", builder="auto")
+
+    def apply(e, only=None):
+        for k in (only or ["G", "cdf", "targets", "mask", "pool", "sampler", "builder"]):
+            if k == "G": e.set_genome(st["G"])
+            elif k == "cdf": e.set_barcode_cdf(st["cdf"])
+            elif k == "targets": e.set_targets(st["ts"], st["te"], st["tb"])
+            elif k == "mask": e.set_blocked(*st["mask"])
+            elif k == "pool": e.set_length_table(st["pool"])
+            elif k == "sampler": e.set_length_sampler(st["sampler"])
+            elif k == "builder": e.set_index_builder(st["builder"])
+
+    def new_targets():
+        B, G = st["cdf"].size, st["G"]
+        n = int(rng.choice([0, 5, 300, 30_000]))
+        tlen = int(rng.choice([200, 5000, G // 300]))
+        st["ts"] = (rng.rand(n) * G).astype(np.int64)
+        st["te"] = st["ts"] + (tlen if rng.rand() < 0.5 else rng.randint(1, 2 * tlen + 2, n))
+        st["tb"] = rng.randint(0, B, n).astype(np.int32)
+
+    try:
+        apply(eng)
+        for step in range(12):
+            changed = []
+            for what in rng.choice(["G", "cdf", "targets", "mask", "pool", "sampler", "builder"], size=int(rng.choice([1, 2, 3])), replace=False):
+                if what == "G":
+                    st["G"] = int(rng.choice([30_000_000, 400_000_000, 4_294_967_200, 4_294_967_400, 7_000_000_000]))
+                elif what == "cdf":
+                    B = int(rng.choice([1, 2, 40, 1100]))
+                    c = np.cumsum(rng.rand(B) + 0.1); st["cdf"] = c / c[-1]; st["cdf"][-1] = 1.0
+                    new_targets(); changed.append("targets")
+                    st["mask"] = (); changed.append("mask")
+                elif what == "targets":
+                    new_targets()
+                elif what == "mask":
+                    k = int(rng.choice([0, 1, 6]))
+                    ms = (rng.rand(k) * st["G"]).astype(np.int64)
+                    st["mask"] = (ms, ms + rng.randint(1, st["G"] // 20, k), rng.choice([1.0, 0.4], k),
+                                  rng.randint(-1, st["cdf"].size, k).astype(np.int32)) if k else ()
+                elif what == "pool":
+                    st["pool"] = O.lognormal_pool(O.Rng(int(rng.randint(1 << 30))), int(rng.choice([800, 20_000, 300_000])), 1, 5, n=20_000)
+                elif what == "sampler":
+                    st["sampler"] = "quantile" if st["sampler"] == "pool" else "pool"
+                elif what == "builder":
+                    st["builder"] = str(rng.choice(["auto", "host", "device"]))
+                changed.append(what)
+            # (targets / mask refer to genome and barcode count: re-send them when those change, as a caller would)
+            if "G" in changed or "cdf" in changed:
+                st["ts"], st["te"] = np.minimum(st["ts"], st["G"] - 1), np.minimum(st["te"], st["G"])
+                if st["mask"]:
+                    st["mask"] = (np.minimum(st["mask"][0], st["G"] - 1), np.minimum(st["mask"][1], st["G"]), st["mask"][2], st["mask"][3])
+                changed += ["targets", "mask"]
+            apply(eng, list(dict.fromkeys(changed)))
+            cov = 30_000 * float(st["pool"].mean()) / st["G"]
+            got = eng.run_batch(77, 1, step, 2, cov, bool(step & 1), 1, 1.0).cpu()
+            fresh = Engine(0)
+            try:
+                apply(fresh)
+                want = fresh.run_batch(77, 1, step, 2, cov, bool(step & 1), 1, 1.0).cpu()
+            finally:
+                fresh.close()
+            for f in ("tallies", "label_counts", "n_bases", "n_reads", "status"):
+                assert np.array_equal(getattr(got, f).numpy(), getattr(want, f).numpy()), (seed, step, f, changed)
+    finally:
+        eng.set_length_sampler("pool"); eng.set_index_builder("auto")
