@@ -810,7 +810,7 @@ __device__ __forceinline__ bool blocked_from(const DevCtx<C> &cx, const Src &src
 // Shared-memory layout of the bulk kernel, in 8-byte words, one definition for host (size) and device (offsets).
 // The arrays of compile-time size come first, so the hot ones sit at constant addresses.
 struct BulkSmem {
-    size_t queue, mqueue, mflags, hot, lut, sched, sgrid, desc, hist, cdf, mbits, qtab, total; // word offsets; total in BYTES
+    size_t queue, mqueue, mflags, hot, lut, sched, acc, sgrid, desc, hist, cdf, mbits, qtab, total; // word offsets; total in BYTES
 };
 __host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool mask, bool shared, bool hot, int B, int sgrid_n, int mbits_words, bool quant)
 {
@@ -823,6 +823,7 @@ __host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool ma
     o.hot = w; w += hot ? kHotWords / 2 : 0;
     o.lut = w; w += B > 1 ? kCdfLut : 0; // (one barcode: no table)
     o.sched = w; w += 2;
+    o.acc = w; w += (warps + 2) & ~(size_t)1; // (even: what follows keeps its 16-byte alignment)
     o.sgrid = w; w += ((size_t)(shared ? 2 * B * sgrid_n : 0) * coord_bytes + 15) / 16 * 2;
     o.desc = w; w += (size_t)(B <= kSmemDescs ? B : 0) * 2;
     o.hist = w; w += ((size_t)(B + 2) * 4 + 7) / 8;
@@ -872,6 +873,12 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     uint32_t *const s_hot = kHot ? (uint32_t *)(smem + lay.hot) : nullptr;
     uint2 *const s_lut = (uint2 *)(smem + lay.lut);             // [kCdfLut]
     i64 *const s_sched = (i64 *)(smem + lay.sched);             // [2] the claimed tile, broadcast to the CTA
+    // per-warp counted bases [warps] and the CTA's reads [1] since the last flush, touched once per tile by one lane.
+    // General variant: here and not in registers (at its 64-register cap the compiler kept them in local memory, and
+    // the reload behind a thrashed L1 was 5.7 % of config 4's stall samples).  Small-target variant: registers (it has
+    // them to spare; through shared memory config 2 loses 4 %).
+    u64 *const s_acc = smem + lay.acc;
+    u64 acc_bases = 0, acc_reads = 0;
     C *const s_grid = (C *)(smem + lay.sgrid);                  // [B][sgrid_n] pairs (small target sets)
     int4 *const s_desc = (int4 *)(smem + lay.desc);             // [min(B, kSmemDescs)] first-layer descriptors
     const int n_sdesc = B <= kSmemDescs ? B : 0;
@@ -889,6 +896,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     for (int i = tid; i < n_sdesc; i += kBulkBlock) s_desc[i] = __ldg(reinterpret_cast<const int4 *>(cx.seg + i));
     for (int i = tid; i < B + 2; i += kBulkBlock) s_hist[i] = 0;
     if (kMask && lane < kBulkIpt) mflags[lane] = 0;
+    if (tid <= kBulkBlock / 32) s_acc[tid] = 0;
     if (s_hot)
         for (int i = tid; i < kHotWords; i += kBulkBlock)
             s_hot[i] = i >= kHotSlots * 4 && i - kHotSlots * 4 < cx.n_hot ? (uint32_t)cx.hot_row[i - kHotSlots * 4] : 0u;
@@ -899,7 +907,6 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     __syncthreads();
 
     const bool plain_labels = !Src::kHasLabel && B == 1 && !kMask; // every read is label 0
-    u64 acc_bases = 0, acc_reads = 0; // lane 0 of each warp / thread 0
     int qn = 0, hot_tiles = 0, parity = 0;
 
     // The CTA's schedule (one loop body, so that it is compiled in line): first the iterations of its own group in
@@ -1114,11 +1121,11 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             if (lane == 0) {
                 ESL_CHK(t >= 0 && t < out.tiles_per_iter, "tile sum index");
                 if (my) atomicAdd(tile_sum_it + t, my);
-                acc_bases += my;
+                if (kShared) acc_bases += my; else s_acc[wid] += my;
             }
             if (tid == 0) {
-                const uint32_t left = hi - base;
-                acc_reads += left < (uint32_t)kBulkTile ? left : (uint32_t)kBulkTile;
+                const uint32_t left = hi - base, got = left < (uint32_t)kBulkTile ? left : (uint32_t)kBulkTile;
+                if (kShared) acc_reads += got; else s_acc[kBulkBlock / 32] += got;
             }
             } // tiles of the claim
         }
@@ -1129,6 +1136,10 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
             if (s_hot) { flush_hot(s_hot, cx.n_hot, tallies_it); hot_tiles = 0; }
             for (int i = tid; i < B + 2; i += kBulkBlock)
                 if (s_hist[i]) { atomicAdd(out.label_counts + (i64)it * (B + 2) + i, (u64)(uint32_t)s_hist[i]); s_hist[i] = 0; }
+            if (!kShared) {
+                if (lane == 0) { acc_bases = s_acc[wid]; s_acc[wid] = 0; }
+                if (tid == 0) { acc_reads = s_acc[kBulkBlock / 32]; s_acc[kBulkBlock / 32] = 0; }
+            }
             if (lane == 0 && acc_bases) atomicAdd(out.n_bases + it, acc_bases);
             if (tid == 0 && acc_reads) {
                 atomicAdd(out.n_reads + it, acc_reads);
