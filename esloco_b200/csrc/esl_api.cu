@@ -176,6 +176,10 @@ constexpr int kDeadScan = 16;
 // Small target sets whose targets meet more than this share of the reads skip the shared-memory pre-filter (24
 // whole-chromosome ROIs + 76 small ones: 63.7 -> 71.1 G reads/s without it).
 constexpr double kPrefilterMaxCover = 0.5;
+#ifndef ESL_MBITS_MAX_BUCKETS
+#define ESL_MBITS_MAX_BUCKETS 65536
+#endif
+constexpr u64 MBITS_MAX_BUCKETS = ESL_MBITS_MAX_BUCKETS; // blocked-bucket map: two bits per bucket in shared memory
 constexpr size_t kRelaxedLayers = 64;
 // Sort targets by (start, end, row).  Large sets: stable LSD radix sort on the start (11-bit digits), then the rare runs
 // of equal starts are ordered by (end, row) -- 10 k targets take ~0.1 ms instead of 0.7 ms with a comparison sort, and
@@ -744,15 +748,31 @@ int upload_index(esl_ctx *ctx, cudaStream_t st)
         ms.push_back((C) ~(C)0); me.push_back((C) ~(C)0); mp.push_back((C) ~(C)0); mw.push_back(0.0);
     }
     ctx->n_mask = n_real;
-    {   // blocked-bucket bitmap: at most 64 Ki buckets (8 KB of shared memory), at least 64 kb wide
+    {   // blocked-bucket map, two bits per bucket (kernels.cuh DevCtx::mbits): at most 64 Ki buckets (16 KB of shared
+        // memory; hg38: 47 k buckets of 64 kb, 12 KB -- measured on config 4: 58.7 G reads/s against 57.5 with 128-kb
+        // buckets in 6 KB and 56.5 without the second bit), at least 64 kb wide.  Bit 0: some blocked interval of any tree touches the bucket.  Bit 1: the bucket
+        // lies entirely inside the union of the "ALL" intervals of weight >= 1 -- a read inside such buckets is blocked
+        // whatever its barcode and whatever uniform would be drawn.
         int sh = 16;
-        while (((G + 1) >> sh) + 1 > 65536) ++sh;
-        const size_t nbits = (size_t)((G + 1) >> sh) + 2;
-        std::vector<uint32_t> bits((nbits + 31) / 32, 0u);
+        while (((G + 1) >> sh) + 1 > MBITS_MAX_BUCKETS) ++sh;
+        const size_t nb = (size_t)((G + 1) >> sh) + 2;
+        std::vector<uint32_t> bits((nb + 15) / 16, 0u);
+        std::vector<std::pair<u64, u64>> sure;
         for (size_t i = 0; i < ctx->m_start.size(); ++i) {
             const u64 a = (u64)std::max<i64>(ctx->m_start[i], 0), e = (u64)std::max<i64>(ctx->m_end[i], 0);
             if (e <= a || a > G) continue;
-            for (u64 b = a >> sh, b1 = (std::min<u64>(e, G + 1) - 1) >> sh; b <= b1; ++b) bits[b >> 5] |= 1u << (b & 31);
+            for (u64 b = a >> sh, b1 = (std::min<u64>(e, G + 1) - 1) >> sh; b <= b1; ++b) bits[b >> 4] |= 1u << ((b & 15) * 2);
+            if (ctx->m_bc[i] < 0 && ctx->m_w[i] >= 1.0) sure.emplace_back(a, e >= G ? ~0ull : e); // (reads end at or before G)
+        }
+        std::sort(sure.begin(), sure.end());
+        for (size_t i = 0; i < sure.size();) { // merged runs of certain intervals -> the buckets they cover completely
+            u64 a = sure[i].first, e = sure[i].second;
+            size_t j = i + 1;
+            while (j < sure.size() && sure[j].first <= e) { e = std::max(e, sure[j].second); ++j; }
+            const u64 first = (a + ((1ull << sh) - 1)) >> sh;
+            const u64 last = e == ~0ull ? nb : std::min<u64>(e >> sh, nb); // buckets [first, last) are inside [a, e)
+            for (u64 b = first; b < last; ++b) bits[b >> 4] |= 2u << ((b & 15) * 2);
+            i = j;
         }
         ctx->mbits_shift = sh;
         ctx->mbits_words = (int)bits.size();

@@ -156,9 +156,11 @@ struct DevCtx {
     int consuming;
     int has_mask;
     int mask_mode; // bit 0: some barcode has a tree of its own, bit 1: the "ALL" tree holds intervals
-    // coarse bitmap over the genome, staged in shared memory by the bulk kernel: bit b is set when ANY blocked interval
-    // (of any tree) touches bucket b = position >> mbits_shift.  A read spanning at most two buckets whose bits are
-    // clear is certainly not blocked -- no global load for the bulk of the reads; everything else takes the exact test.
+    // coarse map over the genome, staged in shared memory by the bulk kernel, two bits per bucket b = position >>
+    // mbits_shift.  Bit 0: ANY blocked interval (of any tree) touches the bucket -- a read spanning at most two buckets
+    // whose bits are clear is certainly not blocked.  Bit 1: the bucket lies entirely inside "ALL" intervals of weight >= 1
+    // -- a read spanning at most two such buckets is certainly blocked (u < 1 <= weight for every uniform, whichever tree
+    // is asked first).  Neither needs a global load; everything else takes the exact test.
     const uint32_t *__restrict__ mbits;
     int mbits_shift, mbits_words;
     uint32_t n_pool;
@@ -1003,13 +1005,18 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 // probe the barcode's tree (if any barcode has one) and the "ALL" tree, all four reads of the thread in
                 // flight together; reads with a candidate are queued and the warp walks them with its lanes busy
                 int mn = 0;
+                unsigned sure_bits = 0; // bit i: read i lies in buckets that are blocked for certain
                 const int2 d_all = __ldg(reinterpret_cast<const int2 *>(cx.grp + B) + 1);
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i) {
                     const C re = (C)(st[i] + L[i]);
                     const uint32_t b0 = (uint32_t)((u64)st[i] >> cx.mbits_shift), b1 = (uint32_t)((u64)(re - 1) >> cx.mbits_shift);
-                    const uint32_t b1c = b1 - b0 > 1u ? b0 : b1; // (keeps the second look-up in range whatever the length)
-                    const bool maybe = b1 - b0 > 1u || (((s_mbits[b0 >> 5] >> (b0 & 31)) | (s_mbits[b1c >> 5] >> (b1c & 31))) & 1u);
+                    const bool wide = b1 - b0 > 1u;
+                    const uint32_t b1c = wide ? b0 : b1; // (keeps the second look-up in range whatever the length)
+                    const uint32_t m0 = s_mbits[b0 >> 4] >> ((b0 & 15) * 2), m1 = s_mbits[b1c >> 4] >> ((b1c & 15) * 2);
+                    const bool sure = !wide && (m0 & m1 & 2u) && label[i] >= 0;
+                    const bool maybe = !sure && (wide || ((m0 | m1) & 1u));
+                    sure_bits |= (unsigned)sure << i;
                     int a_bc = -1, a_all = -1;
                     if (maybe && (cx.mask_mode & 1)) {
                         const int2 d = __ldg(reinterpret_cast<const int2 *>(cx.grp + (label[i] >= 0 ? label[i] : 0)) + 1);
@@ -1029,7 +1036,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < kBulkIpt; ++i) {
                     uint32_t counted = L[i];
-                    if (mflags[i] >> lane & 1) {
+                    if ((mflags[i] >> lane | sure_bits >> i) & 1) {
                         label[i] = cx.consuming ? kLabelBlockedConsuming : kLabelBlockedNotConsuming;
                         counted = cx.consuming ? L[i] : 0u;
                     }
