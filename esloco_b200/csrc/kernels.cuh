@@ -1049,9 +1049,23 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 for (int i = 0; i < kBulkIpt; ++i) my += (Src::kHasLabel && label[i] == kLabelBlockedNotConsuming) ? 0u : L[i];
             }
             if (!plain_labels) { // phase 3: label histogram
+                if (B <= 2) {
+                    // at most four label slots (one or two barcodes + the two blocked labels): the thread's four reads are
+                    // counted in one packed word, byte s = reads of slot s, the warp adds them with ONE REDUX (a byte holds
+                    // at most 4 x 32 = 128) and lanes 0..3 add a byte each to the shared histogram -- instead of a
+                    // match.any + atomic per read
+                    unsigned packed = 0;
 #pragma unroll
-                for (int i = 0; i < kBulkIpt; ++i)
-                    hist_add(s_hist, label[i] != kLabelInvalid && label[i] < B ? label_slot(label[i], B) : -1, 1, B + 2);
+                    for (int i = 0; i < kBulkIpt; ++i)
+                        if (label[i] != kLabelInvalid && label[i] < B) packed += 1u << (8 * label_slot(label[i], B));
+                    packed = __reduce_add_sync(0xffffffffu, packed);
+                    const unsigned cnt = lane < 4 ? (packed >> (8 * lane)) & 0xffu : 0u;
+                    if (cnt) atomicAdd(s_hist + lane, (int)cnt);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kBulkIpt; ++i)
+                        hist_add(s_hist, label[i] != kLabelInvalid && label[i] < B ? label_slot(label[i], B) : -1, 1, B + 2);
+                }
             }
             if (kShared) { // phase 4, small target sets: shared-memory pre-filter, exact path for the rest
                 unsigned maybe = 0; // bit i: read i may overlap a first-layer target
