@@ -123,7 +123,7 @@ struct esl_ctx {
     SortScratch sort;
     DevBuf d_idx_key_s, d_idx_key_b, d_idx_res; // device index builder
     DevBuf d_mbits;
-    int mbits_shift = 0, mbits_words = 0; // blocked-bucket bitmap (kernels.cuh DevCtx::mbits)
+    int mbits_shift = 0, mbits_words = 0; // blocked-bucket map, two bits per bucket (kernels.cuh DevCtx::mbits)
     u64 sgrid_lmax = 0;               // longest read its upper bounds were built for
 
     // optional hit-record buffer (esl_set_hit_buffer)

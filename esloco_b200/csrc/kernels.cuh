@@ -886,7 +886,7 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
     const int n_sdesc = B <= kSmemDescs ? B : 0;
     int *const s_hist = (int *)(smem + lay.hist);               // [B + 2] reads per label since the last flush
     uint32_t *const s_cdf = (uint32_t *)(smem + lay.cdf);       // [B]
-    uint32_t *const s_mbits = (uint32_t *)(smem + lay.mbits);   // [mbits_words] blocked-bucket bitmap
+    uint32_t *const s_mbits = (uint32_t *)(smem + lay.mbits);   // [mbits_words] blocked-bucket map, two bits per bucket
     uint32_t *const s_qtab = (uint32_t *)(smem + lay.qtab);     // [kQuantBins + 1] quantile table of the read lengths
     if (quant)
         for (int i = tid; i <= kQuantBins; i += kBulkBlock) s_qtab[i] = cx.qtab[i];
@@ -1001,7 +1001,8 @@ k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__
                 mn = 0;
             };
             if (!Src::kHasLabel && kMask) {
-                // phase 2: blocked regions -- a shared-memory bitmap clears most reads without a global load; the others
+                // phase 2: blocked regions -- a shared-memory bucket map clears most reads and settles most of the blocked
+                // ones (buckets wholly inside certain intervals) without a global load; the others
                 // probe the barcode's tree (if any barcode has one) and the "ALL" tree, all four reads of the thread in
                 // flight together; reads with a candidate are queued and the warp walks them with its lanes busy
                 int mn = 0;
