@@ -853,7 +853,10 @@ __host__ __device__ inline BulkSmem bulk_smem_layout(size_t coord_bytes, bool ma
 //   1 draw  2 blocked probes, queue, drain  3 label histogram  4 target probes, queue, rounds  5 tile sum
 // Warps only meet when the CTA claims tiles (one barrier, the next claim is fetched while the current one is worked
 // on) or moves to the next iteration and flushes its shared label histogram.
-constexpr int kIterSlots = 4;
+#ifndef ESL_ITER_SLOTS
+#define ESL_ITER_SLOTS 4
+#endif
+constexpr int kIterSlots = ESL_ITER_SLOTS; // (measured, config 3 / config 4 in G reads/s: 2 groups 140.2 / 55.0, 4 groups 140.6 / 59.3, 8 groups 141.9 / 59.4)
 template <typename C, typename Src, bool kMask, bool kShared, bool kHot>
 __global__ void __launch_bounds__(kBulkBlock, bulk_min_blocks<C, kShared>())
 k_place_tally_bulk(const __grid_constant__ DevCtx<C> cx, const __grid_constant__ Src src, const DevOut out, const i64 *__restrict__ lo_arr,
