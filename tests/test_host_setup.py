@@ -272,3 +272,51 @@ def test_native_contig_scanner_matches_python_scan(tmp_path):
     assert dict(fo.fasta_contig_lengths(str(tmp_path / "long.fa"))) == {"a": 16_000_000, "b": 3_000_001}
     with pytest.raises(OSError):
         fo._contigs_native(str(tmp_path / "missing.fa"))
+
+
+def test_shift_insertions_equals_the_sequential_walk():
+    """esl_shift_insertions against the reference's own loop written out (create_insertion_genome.py:60-64,76-80: every
+    new insertion pushes the earlier ones that start at or after it), random positions with many ties, 0..600
+    insertions, several lengths."""
+    from esloco_b200.create_insertion_genome import _shifted_starts
+    rng = np.random.RandomState(8)
+    for trial in range(60):
+        n = int(rng.choice([0, 1, 2, 17, 200, 600]))
+        length = int(rng.choice([1, 500, 5000, 10**7]))
+        span = int(rng.choice([5, 1000, 10**9]))  # a span of 5 makes nearly every position a tie
+        pos = rng.randint(0, span, n).astype(np.int64)
+        walk = []
+        for p in pos.tolist():
+            for k in range(len(walk)):
+                if walk[k] >= p:
+                    walk[k] += length
+            walk.append(p)
+        assert _shifted_starts(pos, length).tolist() == walk, (trial, n, length, span)
+
+
+def test_contig_scanner_random_files(tmp_path):
+    """Random FASTA text (line widths 1-120, LF / CRLF, blank lines, blanks and tabs inside sequence lines, empty records,
+    descriptions, leading junk, with and without a final line break) through the native scanner and the Python scan."""
+    from esloco_b200 import fasta_operations as fo
+    rng = np.random.RandomState(21)
+    for trial in range(40):
+        parts = []
+        if rng.rand() < 0.3:
+            parts.append("junk line\n")
+        for r in range(int(rng.choice([0, 1, 3, 40]))):
+            nl = "\r\n" if rng.rand() < 0.3 else "\n"
+            parts.append(">" + ("" if rng.rand() < 0.05 else f"c{trial}_{r}") + (" some text > here" if rng.rand() < 0.4 else "") + nl)
+            for _ in range(int(rng.choice([0, 1, 5, 60]))):
+                line = "".join(rng.choice(list("ACGTN"), int(rng.randint(1, 121))))
+                if rng.rand() < 0.1:
+                    line = line[: len(line) // 2] + rng.choice([" ", "\t", "  "]) + line[len(line) // 2:]
+                parts.append(line + nl)
+                if rng.rand() < 0.05:
+                    parts.append(nl)
+        text = "".join(parts)
+        if text.endswith("\n") and rng.rand() < 0.5:
+            text = text[:-1].rstrip("\r")
+        p = tmp_path / f"r{trial}.fa"
+        p.write_bytes(text.encode())
+        want = list(fo.fasta_contig_lengths(str(p), int(rng.choice([3, 64, 1 << 16]))))
+        assert fo._contigs_native(str(p)) == want, trial
