@@ -49,14 +49,21 @@ def _scan_native(fasta_file, is_fastq, min_read_length):
     except _native.NativeLibraryError:  # library not built yet: the Python pass below does the same job, slower
         return None
     mean = C.c_double()
-    n = lib.esl_scan_read_lengths(fasta_file.encode(), int(is_fastq), int(min_read_length), None, 0, C.byref(mean))
+    # one pass when the guess holds (long reads: at least ~1 kb of file per record), a second one with the exact count else
+    try:
+        guess = max(1 << 16, os.path.getsize(fasta_file) // 1000)
+    except OSError:
+        guess = 1 << 16
+    out = np.empty(guess, np.uint32)
+    n = lib.esl_scan_read_lengths(fasta_file.encode(), int(is_fastq), int(min_read_length), out.ctypes.data, guess, C.byref(mean))
     if n == -6:
         raise ValueError(f"This is not a correct FASTQ file {fasta_file}. Provide FASTA or FASTQ.")
     if n < 0:
         raise OSError(f"cannot read {fasta_file}")
-    out = np.empty(n, np.uint32)
-    lib.esl_scan_read_lengths(fasta_file.encode(), int(is_fastq), int(min_read_length), out.ctypes.data, n, C.byref(mean))
-    return out.astype(np.int64)
+    if n > guess:
+        out = np.empty(n, np.uint32)
+        lib.esl_scan_read_lengths(fasta_file.encode(), int(is_fastq), int(min_read_length), out.ctypes.data, n, C.byref(mean))
+    return out[:n].astype(np.int64)
 
 
 def seq_read_data(fasta_file, distribution=False, min_read_length=0):

@@ -320,3 +320,15 @@ def test_contig_scanner_random_files(tmp_path):
         p.write_bytes(text.encode())
         want = list(fo.fasta_contig_lengths(str(p), int(rng.choice([3, 64, 1 << 16]))))
         assert fo._contigs_native(str(p)) == want, trial
+
+
+def test_read_length_scan_second_pass_when_the_guess_is_short(tmp_path):
+    """The native read-length scan sizes its output from the file size (one pass for long reads); a file with more
+    records than that guess (70 k reads of 3-9 bases) takes the second pass and still returns every length."""
+    from esloco_b200 import config_handler as ch
+    rng = np.random.RandomState(2)
+    lens = rng.randint(3, 10, 70_000)
+    p = tmp_path / "short.fa"
+    p.write_text("".join(f">r{i}\n{'A' * n}\n" for i, n in enumerate(lens)))
+    got = ch._scan_native(str(p), False, 4)
+    assert got is not None and got.tolist() == [int(n) for n in lens if n > 4]
